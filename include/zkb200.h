@@ -1,0 +1,159 @@
+/* zkb200 -- C ABI of the B200-native Groth16/BN254 proving backend.
+ *
+ * This is the drop-in boundary for the reference's proving hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the Zelana-Labs/zelana tree).  The reference's
+ * `Groth16Prover: BatchProver` (core/src/sequencer/settlement/prover.rs:160-169, 252-447) would bind
+ * these through a Rust `extern "C"` block; tests bind them through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative zkb_status; nothing throws or aborts
+ *     (a failed prove must surface as an error, pipeline.rs:398-425 retries it next tick);
+ *   - a zkb_ctx owns one CUDA device + stream and is NOT thread-safe; distinct contexts may be
+ *     used concurrently from distinct threads (one per GPU, or several per GPU);
+ *   - field elements cross the ABI as 32-byte little-endian CANONICAL integers (what arkworks'
+ *     `into_bigint().to_bytes_le()` yields, prover.rs:311-331);
+ *   - G1 affine = x || y (64 B), G2 affine = x.c0 || x.c1 || y.c0 || y.c1 (128 B), no flag bits,
+ *     infinity = all zero bytes (prover/src/bin/convert_vk.rs:163-191);
+ *   - "host" pointers are ordinary CPU memory, "dev" pointers are CUDA device memory on ctx's device.
+ *   - there is NO CPU fallback: without a CUDA device zkb_ctx_create fails with ZKB_ERR_NO_DEVICE.
+ */
+#ifndef ZKB200_H
+#define ZKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ZKB_OK = 0,
+  ZKB_ERR_NO_DEVICE = -1,
+  ZKB_ERR_CUDA = -2,
+  ZKB_ERR_INVALID_ARG = -3,
+  ZKB_ERR_OOM = -4,
+  ZKB_ERR_NOT_CANONICAL = -5, /* a field element >= modulus, or a point not on the curve */
+  ZKB_ERR_SHAPE = -6          /* witness / key / matrix sizes disagree */
+} zkb_status;
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_g1_bases zkb_g1_bases; /* device-resident G1 affine points, Montgomery form */
+typedef struct zkb_g2_bases zkb_g2_bases;
+typedef struct zkb_r1cs zkb_r1cs;         /* device-resident constraint matrices (CSR) */
+typedef struct zkb_pk zkb_pk;             /* device-resident Groth16 proving key */
+
+/* ---- library / context --------------------------------------------------------------------- */
+const char* zkb_version(void);
+int zkb_device_count(void);
+int zkb_ctx_create(int device, zkb_ctx** out);
+/* Run on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); NULL = own stream. */
+int zkb_ctx_set_stream(zkb_ctx* ctx, void* cuda_stream);
+int zkb_ctx_synchronize(zkb_ctx* ctx);
+void zkb_ctx_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(zkb_ctx* ctx);
+/* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
+unsigned long long zkb_launch_count(zkb_ctx* ctx);
+/* force the MSM window width (0 = automatic) -- benchmarking/tests only */
+int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c);
+
+/* ---- field arithmetic parity hooks (ark-ff Fp<MontBackend<_,4>>: SURVEY.md 8a row a9) -------- */
+/* field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 inverse (b ignored; 0 -> 0), 4 neg (b ignored).
+ * a, b, out: n x 32 B canonical LE, host memory. */
+int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+
+/* ---- curve parity hooks (ark-ec short_weierstrass) ----------------------------------------- */
+/* out[i] = scalars[i] * points[i]; group: 1 = G1 (64 B points), 2 = G2 (128 B points); host memory. */
+int zkb_scalar_mul(zkb_ctx* ctx, int group, const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out);
+/* out = sum_i points[i] (plain point sum, exercises add/double/inverse edge cases); host memory. */
+int zkb_point_sum(zkb_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out);
+
+/* ---- bases (proving-key query vectors resident in HBM) --------------------------------------- */
+int zkb_g1_bases_load(zkb_ctx* ctx, const uint8_t* affine_host, size_t n, int validate, zkb_g1_bases** out);
+int zkb_g2_bases_load(zkb_ctx* ctx, const uint8_t* affine_host, size_t n, int validate, zkb_g2_bases** out);
+/* bases[i] = k_i * G (G = (1,2)), k_i = 32 B canonical LE Fr scalars in DEVICE memory: synthetic keys with
+ * known discrete logs, generated on the GPU. */
+int zkb_g1_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, zkb_g1_bases** out);
+int zkb_g2_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, zkb_g2_bases** out);
+size_t zkb_g1_bases_len(const zkb_g1_bases* b);
+size_t zkb_g2_bases_len(const zkb_g2_bases* b);
+/* copy bases [offset, offset+n) back as canonical affine bytes (host) */
+int zkb_g1_bases_read(zkb_ctx* ctx, const zkb_g1_bases* b, size_t offset, size_t n, uint8_t* out_host);
+int zkb_g2_bases_read(zkb_ctx* ctx, const zkb_g2_bases* b, size_t offset, size_t n, uint8_t* out_host);
+void zkb_g1_bases_free(zkb_g1_bases* b);
+void zkb_g2_bases_free(zkb_g2_bases* b);
+
+/* ---- MSM: ark-ec VariableBaseMSM::msm_bigint -------------------- */
+/* sum_{i<n} scalars[i] * bases[offset + i].  Host variant copies scalars H2D and the result D2H. */
+int zkb_msm_g1(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+               uint8_t out_affine_host[64]);
+int zkb_msm_g2(zkb_ctx* ctx, const zkb_g2_bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+               uint8_t out_affine_host[128]);
+/* Device variant: asynchronous on ctx's stream.  out_affine_dev: 64 / 128 B canonical (may be NULL);
+ * out_partial_dev: 128 / 256 B opaque projective partial sum for zkb_msm_g{1,2}_combine (may be NULL). */
+int zkb_msm_g1_dev(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                   void* out_affine_dev, void* out_partial_dev);
+int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_g2_bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                   void* out_affine_dev, void* out_partial_dev);
+/* Multi-GPU combine: k partial sums (gathered from k ranks, device memory) -> canonical affine (device). */
+int zkb_msm_g1_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
+int zkb_msm_g2_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
+#define ZKB_G1_PARTIAL_BYTES 128
+#define ZKB_G2_PARTIAL_BYTES 256
+
+/* ---- NTT: ark-poly Radix2EvaluationDomain ---------------------------- */
+/* direction: 0 forward (fft_in_place), 1 inverse (ifft_in_place, 1/n folded in).
+ * coset: 0 plain, 1 = domain.get_coset(Fr::GENERATOR = 5).  Natural order in and out; n = 2^log_n.
+ * Data is n x 32 B; canonical stays canonical.  in == out is allowed. */
+int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, int log_n, int direction, int coset);
+int zkb_ntt_dev(zkb_ctx* ctx, const void* in_dev, void* out_dev, int log_n, int direction, int coset);
+
+/* ---- R1CS matrices + witness map: LibsnarkReduction::witness_map_from_matrices (row a4) ----- */
+typedef struct {
+  const uint64_t* row_ptr; /* num_constraints + 1 offsets into col/coeff */
+  const uint32_t* col;     /* variable index: instance j -> j (0 = constant ONE), witness w -> num_instance + w */
+  const uint8_t* coeff;    /* nnz x 32 B canonical LE */
+} zkb_csr;
+
+typedef struct {
+  uint64_t num_constraints;
+  uint64_t num_instance; /* including the constant ONE */
+  uint64_t num_witness;
+  zkb_csr a, b, c;
+} zkb_r1cs_desc;
+
+int zkb_r1cs_load(zkb_ctx* ctx, const zkb_r1cs_desc* desc, zkb_r1cs** out);
+void zkb_r1cs_free(zkb_r1cs* m);
+/* log2 of the QAP domain: next_pow2(num_constraints + num_instance) */
+int zkb_r1cs_log_domain(const zkb_r1cs* m);
+/* z = full assignment [1, instance.., witness..], (num_instance + num_witness) x 32 B canonical, host.
+ * h_out: domain_size x 32 B canonical coefficients of h(X), host. */
+int zkb_witness_map(zkb_ctx* ctx, const zkb_r1cs* m, const uint8_t* z_host, uint8_t* h_out_host);
+
+/* ---- proving key + prove: ark-groth16 create_proof_with_reduction_and_matrices (rows a3, a8) - */
+typedef struct {
+  const uint8_t* alpha_g1; /* 64 B */
+  const uint8_t* beta_g1;  /* 64 B */
+  const uint8_t* beta_g2;  /* 128 B */
+  const uint8_t* delta_g1; /* 64 B */
+  const uint8_t* delta_g2; /* 128 B */
+  const uint8_t* a_query;    size_t a_len;    /* G1, num_instance + num_witness */
+  const uint8_t* b_g1_query; size_t b_g1_len; /* G1, same */
+  const uint8_t* b_g2_query; size_t b_g2_len; /* G2, same */
+  const uint8_t* h_query;    size_t h_len;    /* G1, domain_size - 1 */
+  const uint8_t* l_query;    size_t l_len;    /* G1, num_witness */
+} zkb_pk_desc;
+
+int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* desc, int validate, zkb_pk** out);
+void zkb_pk_free(zkb_pk* pk);
+
+/* Proof = (A in G1, B in G2, C in G1), canonical affine, A NOT negated (negation and flag bits are host-side
+ * formatting: prover.rs:304-334 / ark-serialize).  r, s: 32 B canonical Fr, the prover's randomness
+ * (StdRng::seed_from_u64(batch_id) -> Fr::rand twice, prover.rs:354).  z_host as in zkb_witness_map. */
+int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+              const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB200_H */

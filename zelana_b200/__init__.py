@@ -1,0 +1,8 @@
+"""zelana_b200 -- B200-native Groth16/BN254 proving backend for the Zelana prover hot path.
+
+Host-side mirror (Python, ctypes) of the C ABI in include/zkb200.h.  All arithmetic happens in the CUDA
+library `libzkb200.so`; there is no CPU fallback -- importing works without a GPU (so that symbols can be
+checked), but creating a Context without a CUDA device raises.
+"""
+from ._lib import LIB_PATH, ZkbError, load_library  # noqa: F401
+from .api import Context, G1Bases, G2Bases, R1csMatrices, ProvingKeyDev  # noqa: F401

@@ -1,0 +1,100 @@
+"""ctypes loader for libzkb200.so (built in-tree by __graft_entry__.build())."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libzkb200.so")
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("zkb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+STATUS = {0: "OK", -1: "NO_DEVICE", -2: "CUDA", -3: "INVALID_ARG", -4: "OOM", -5: "NOT_CANONICAL", -6: "SHAPE"}
+
+
+class Csr(C.Structure):
+    _fields_ = [("row_ptr", C.c_void_p), ("col", C.c_void_p), ("coeff", C.c_void_p)]
+
+
+class R1csDesc(C.Structure):
+    _fields_ = [("num_constraints", C.c_uint64), ("num_instance", C.c_uint64), ("num_witness", C.c_uint64),
+                ("a", Csr), ("b", Csr), ("c", Csr)]
+
+
+class PkDesc(C.Structure):
+    _fields_ = [("alpha_g1", C.c_void_p), ("beta_g1", C.c_void_p), ("beta_g2", C.c_void_p),
+                ("delta_g1", C.c_void_p), ("delta_g2", C.c_void_p),
+                ("a_query", C.c_void_p), ("a_len", C.c_size_t),
+                ("b_g1_query", C.c_void_p), ("b_g1_len", C.c_size_t),
+                ("b_g2_query", C.c_void_p), ("b_g2_len", C.c_size_t),
+                ("h_query", C.c_void_p), ("h_len", C.c_size_t),
+                ("l_query", C.c_void_p), ("l_len", C.c_size_t)]
+
+
+_P = C.c_void_p
+_SZ = C.c_size_t
+_I = C.c_int
+
+# every symbol include/zkb200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "zkb_version": (C.c_char_p, []),
+    "zkb_device_count": (_I, []),
+    "zkb_ctx_create": (_I, [_I, C.POINTER(_P)]),
+    "zkb_ctx_set_stream": (_I, [_P, _P]),
+    "zkb_ctx_synchronize": (_I, [_P]),
+    "zkb_ctx_destroy": (None, [_P]),
+    "zkb_last_error": (C.c_char_p, [_P]),
+    "zkb_launch_count": (C.c_ulonglong, [_P]),
+    "zkb_ctx_set_msm_window": (_I, [_P, _I]),
+    "zkb_field_op": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
+    "zkb_scalar_mul": (_I, [_P, _I, _P, _P, _SZ, _P]),
+    "zkb_point_sum": (_I, [_P, _I, _P, _SZ, _P]),
+    "zkb_g1_bases_load": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
+    "zkb_g2_bases_load": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
+    "zkb_g1_bases_generate": (_I, [_P, _P, _SZ, C.POINTER(_P)]),
+    "zkb_g2_bases_generate": (_I, [_P, _P, _SZ, C.POINTER(_P)]),
+    "zkb_g1_bases_len": (_SZ, [_P]),
+    "zkb_g2_bases_len": (_SZ, [_P]),
+    "zkb_g1_bases_read": (_I, [_P, _P, _SZ, _SZ, _P]),
+    "zkb_g2_bases_read": (_I, [_P, _P, _SZ, _SZ, _P]),
+    "zkb_g1_bases_free": (None, [_P]),
+    "zkb_g2_bases_free": (None, [_P]),
+    "zkb_msm_g1": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
+    "zkb_msm_g2": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
+    "zkb_msm_g1_dev": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P]),
+    "zkb_msm_g2_dev": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P]),
+    "zkb_msm_g1_combine": (_I, [_P, _P, _I, _P]),
+    "zkb_msm_g2_combine": (_I, [_P, _P, _I, _P]),
+    "zkb_ntt": (_I, [_P, _P, _P, _I, _I, _I]),
+    "zkb_ntt_dev": (_I, [_P, _P, _P, _I, _I, _I]),
+    "zkb_r1cs_load": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(_P)]),
+    "zkb_r1cs_free": (None, [_P]),
+    "zkb_r1cs_log_domain": (_I, [_P]),
+    "zkb_witness_map": (_I, [_P, _P, _P, _P]),
+    "zkb_pk_load": (_I, [_P, C.POINTER(PkDesc), _I, C.POINTER(_P)]),
+    "zkb_pk_free": (None, [_P]),
+    "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load_library():
+    """Load libzkb200.so and bind every declared symbol.  Fails loudly if the CUDA extension is missing:
+    there is deliberately no CPU implementation to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(no CPU fallback exists)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

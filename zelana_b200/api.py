@@ -1,0 +1,324 @@
+"""Thin object layer over the C ABI: contexts, device-resident bases, MSM, NTT, witness map, prove."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import ZkbError, load_library, R1csDesc, PkDesc, Csr
+
+FR, FQ = 0, 1
+OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_NEG = range(5)
+G1_PARTIAL_BYTES, G2_PARTIAL_BYTES = 128, 256
+
+
+def _buf(x):
+    """bytes / bytearray / numpy uint8 array -> (ctypes pointer, keepalive)."""
+    if isinstance(x, np.ndarray):
+        a = np.ascontiguousarray(x)
+        return a.ctypes.data_as(C.c_void_p), a
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(bytes(x), dtype=np.uint8)
+        return a.ctypes.data_as(C.c_void_p), a
+    raise TypeError("expected bytes or numpy array, got %r" % type(x))
+
+
+def _devptr(t):
+    """torch CUDA tensor or int device address -> c_void_p."""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """One CUDA device + stream.  Not thread-safe; make one per thread / per GPU."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.zkb_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise ZkbError(rc, "zkb_ctx_create(device=%d) failed (a CUDA device is required; no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ZkbError(rc, self.lib.zkb_last_error(self.h).decode())
+
+    def set_stream(self, stream):
+        self._check(self.lib.zkb_ctx_set_stream(self.h, C.c_void_p(int(stream) if stream else 0)))
+
+    def synchronize(self):
+        self._check(self.lib.zkb_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.zkb_launch_count(self.h))
+
+    def set_msm_window(self, c):
+        self._check(self.lib.zkb_ctx_set_msm_window(self.h, c))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zkb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parity hooks
+    def field_op(self, field, op, a, b=None):
+        pa, ka = _buf(a)
+        n = len(ka) // 32
+        out = np.empty(n * 32, dtype=np.uint8)
+        if b is not None:
+            pb, kb = _buf(b)
+        else:
+            pb, kb = C.c_void_p(0), None
+        self._check(self.lib.zkb_field_op(self.h, field, op, pa, pb, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def scalar_mul(self, group, points, scalars):
+        pp, kp = _buf(points)
+        ps, ks = _buf(scalars)
+        sz = 64 if group == 1 else 128
+        n = len(kp) // sz
+        out = np.empty(n * sz, dtype=np.uint8)
+        self._check(self.lib.zkb_scalar_mul(self.h, group, pp, ps, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def point_sum(self, group, points):
+        sz = 64 if group == 1 else 128
+        if len(points) == 0:
+            pp, kp, n = C.c_void_p(0), None, 0
+        else:
+            pp, kp = _buf(points)
+            n = len(kp) // sz
+        out = np.empty(sz, dtype=np.uint8)
+        self._check(self.lib.zkb_point_sum(self.h, group, pp, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    # ---- bases
+    def g1_bases(self, affine_bytes, validate=True):
+        return G1Bases._load(self, affine_bytes, validate)
+
+    def g2_bases(self, affine_bytes, validate=True):
+        return G2Bases._load(self, affine_bytes, validate)
+
+    def g1_bases_generate(self, k_dev, n):
+        h = C.c_void_p()
+        self._check(self.lib.zkb_g1_bases_generate(self.h, _devptr(k_dev), n, C.byref(h)))
+        return G1Bases(self, h)
+
+    def g2_bases_generate(self, k_dev, n):
+        h = C.c_void_p()
+        self._check(self.lib.zkb_g2_bases_generate(self.h, _devptr(k_dev), n, C.byref(h)))
+        return G2Bases(self, h)
+
+    # ---- MSM
+    def msm_g1(self, bases, scalars, offset=0):
+        ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
+        n = len(scalars) // 32
+        out = np.empty(64, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_g1(self.h, bases.h, offset, ps, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def msm_g2(self, bases, scalars, offset=0):
+        ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
+        n = len(scalars) // 32
+        out = np.empty(128, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_g2(self.h, bases.h, offset, ps, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def msm_g1_dev(self, bases, scalars_dev, n, out_affine_dev=None, out_partial_dev=None, offset=0):
+        self._check(self.lib.zkb_msm_g1_dev(self.h, bases.h, offset, _devptr(scalars_dev), n,
+                                            _devptr(out_affine_dev), _devptr(out_partial_dev)))
+
+    def msm_g2_dev(self, bases, scalars_dev, n, out_affine_dev=None, out_partial_dev=None, offset=0):
+        self._check(self.lib.zkb_msm_g2_dev(self.h, bases.h, offset, _devptr(scalars_dev), n,
+                                            _devptr(out_affine_dev), _devptr(out_partial_dev)))
+
+    def msm_g1_combine(self, partials_dev, k, out_affine_dev):
+        self._check(self.lib.zkb_msm_g1_combine(self.h, _devptr(partials_dev), k, _devptr(out_affine_dev)))
+
+    def msm_g2_combine(self, partials_dev, k, out_affine_dev):
+        self._check(self.lib.zkb_msm_g2_combine(self.h, _devptr(partials_dev), k, _devptr(out_affine_dev)))
+
+    # ---- NTT
+    def ntt(self, data, log_n, inverse=False, coset=False):
+        pi, ki = _buf(data)
+        assert len(ki) == 32 << log_n
+        out = np.empty(len(ki), dtype=np.uint8)
+        self._check(self.lib.zkb_ntt(self.h, pi, out.ctypes.data_as(C.c_void_p), log_n, int(inverse), int(coset)))
+        return out.tobytes()
+
+    def ntt_dev(self, in_dev, out_dev, log_n, inverse=False, coset=False):
+        self._check(self.lib.zkb_ntt_dev(self.h, _devptr(in_dev), _devptr(out_dev), log_n, int(inverse), int(coset)))
+
+    # ---- Groth16
+    def r1cs(self, num_instance, num_witness, a, b, c):
+        return R1csMatrices(self, num_instance, num_witness, a, b, c)
+
+    def proving_key(self, **parts):
+        return ProvingKeyDev(self, **parts)
+
+    def witness_map(self, r1cs, z_bytes):
+        pz, kz = _buf(z_bytes)
+        n = 1 << r1cs.log_domain
+        out = np.empty(n * 32, dtype=np.uint8)
+        self._check(self.lib.zkb_witness_map(self.h, r1cs.h, pz, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def prove(self, pk, r1cs, z_bytes, r_bytes, s_bytes):
+        pz, kz = _buf(z_bytes)
+        pr, kr = _buf(r_bytes)
+        ps, ks = _buf(s_bytes)
+        oa = np.empty(64, dtype=np.uint8)
+        ob = np.empty(128, dtype=np.uint8)
+        oc = np.empty(64, dtype=np.uint8)
+        self._check(self.lib.zkb_prove(self.h, pk.h, r1cs.h, pz, pr, ps, oa.ctypes.data_as(C.c_void_p),
+                                       ob.ctypes.data_as(C.c_void_p), oc.ctypes.data_as(C.c_void_p)))
+        return oa.tobytes(), ob.tobytes(), oc.tobytes()
+
+
+class _Bases:
+    _free = None
+    _len = None
+    _read = None
+    _size = 0
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __len__(self):
+        return int(getattr(self.ctx.lib, self._len)(self.h))
+
+    def read(self, offset=0, n=None):
+        n = len(self) - offset if n is None else n
+        out = np.empty(n * self._size, dtype=np.uint8)
+        self.ctx._check(getattr(self.ctx.lib, self._read)(self.ctx.h, self.h, offset, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def free(self):
+        if self.h:
+            getattr(self.ctx.lib, self._free)(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class G1Bases(_Bases):
+    _free, _len, _read, _size = "zkb_g1_bases_free", "zkb_g1_bases_len", "zkb_g1_bases_read", 64
+
+    @classmethod
+    def _load(cls, ctx, data, validate):
+        p, k = _buf(data) if len(data) else (C.c_void_p(0), None)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.zkb_g1_bases_load(ctx.h, p, len(data) // 64, int(validate), C.byref(h)))
+        return cls(ctx, h)
+
+
+class G2Bases(_Bases):
+    _free, _len, _read, _size = "zkb_g2_bases_free", "zkb_g2_bases_len", "zkb_g2_bases_read", 128
+
+    @classmethod
+    def _load(cls, ctx, data, validate):
+        p, k = _buf(data) if len(data) else (C.c_void_p(0), None)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.zkb_g2_bases_load(ctx.h, p, len(data) // 128, int(validate), C.byref(h)))
+        return cls(ctx, h)
+
+
+def _csr_arrays(rows):
+    """rows: list of [(coeff:int, var:int), ...] -> (row_ptr u64, col u32, coeff bytes)."""
+    row_ptr = np.zeros(len(rows) + 1, dtype=np.uint64)
+    cols, coeffs = [], bytearray()
+    k = 0
+    for i, row in enumerate(rows):
+        for co, v in row:
+            cols.append(v)
+            coeffs += int(co).to_bytes(32, "little")
+            k += 1
+        row_ptr[i + 1] = k
+    col = np.asarray(cols, dtype=np.uint32) if cols else np.zeros(1, dtype=np.uint32)
+    coeff = np.frombuffer(bytes(coeffs), dtype=np.uint8) if coeffs else np.zeros(32, dtype=np.uint8)
+    return row_ptr, col, coeff
+
+
+class R1csMatrices:
+    """Device-resident ConstraintMatrices (ark-relations): rows of (coeff, variable)."""
+
+    def __init__(self, ctx, num_instance, num_witness, a, b, c):
+        assert len(a) == len(b) == len(c)
+        self.ctx = ctx
+        keep = []
+        d = R1csDesc()
+        d.num_constraints, d.num_instance, d.num_witness = len(a), num_instance, num_witness
+        for name, rows in (("a", a), ("b", b), ("c", c)):
+            rp, col, co = _csr_arrays(rows)
+            keep += [rp, col, co]
+            setattr(d, name, Csr(rp.ctypes.data, col.ctypes.data, co.ctypes.data))
+        h = C.c_void_p()
+        ctx._check(ctx.lib.zkb_r1cs_load(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.log_domain = int(ctx.lib.zkb_r1cs_log_domain(h))
+        self.num_instance, self.num_witness = num_instance, num_witness
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.zkb_r1cs_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ProvingKeyDev:
+    """Device-resident Groth16 proving key built from raw affine byte strings."""
+
+    def __init__(self, ctx, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query, b_g2_query,
+                 h_query, l_query, validate=True):
+        self.ctx = ctx
+        keep = []
+
+        def ptr(x):
+            if len(x) == 0:
+                return None
+            p, k = _buf(x)
+            keep.append(k)
+            return p.value
+
+        d = PkDesc()
+        d.alpha_g1, d.beta_g1, d.beta_g2 = ptr(alpha_g1), ptr(beta_g1), ptr(beta_g2)
+        d.delta_g1, d.delta_g2 = ptr(delta_g1), ptr(delta_g2)
+        d.a_query, d.a_len = ptr(a_query), len(a_query) // 64
+        d.b_g1_query, d.b_g1_len = ptr(b_g1_query), len(b_g1_query) // 64
+        d.b_g2_query, d.b_g2_len = ptr(b_g2_query), len(b_g2_query) // 128
+        d.h_query, d.h_len = ptr(h_query), len(h_query) // 64
+        d.l_query, d.l_len = ptr(l_query), len(l_query) // 64
+        h = C.c_void_p()
+        ctx._check(ctx.lib.zkb_pk_load(ctx.h, C.byref(d), int(validate), C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.zkb_pk_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
