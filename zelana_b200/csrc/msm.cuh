@@ -63,6 +63,7 @@ static inline MsmPlan msm_make_plan(size_t n, int c_override, int sm_count, int 
   if (chunk > 1024) chunk = 1024;
   p.chunk = int((chunk + 3) & ~size_t(3));
   p.seg = p.nbuck >= 4096 ? 16 : (p.nbuck >= 256 ? 8 : 4);
+  if (uint32_t(p.seg) > p.nbuck) p.seg = int(p.nbuck);
   return p;
 }
 
