@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- BN254 G1 MSM (2^24 points) on N B200s, the configuration BASELINE.json's metric is quoted on.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 24] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one variable-base MSM  sum_i s_i * P_i  over n = 2^log_n synthetic (base, scalar) pairs:
+  * bases  P_i = [k_i] G, generated on the GPU from seeded k_i (they are the proving key: resident in HBM);
+  * scalars s_i uniform below r (top 32-bit limb drawn below r's top limb), seeded, identical for every N.
+N > 1: the n pairs are split into N contiguous ranges (north_star: "by scalar range per GPU"), each rank runs the
+whole Pippenger pipeline on its range, the N projective partial sums (128 B each) are all-gathered over NCCL and
+added by one small kernel -> strong scaling of one 2^24 MSM.
+
+Printed JSON (one line, rank 0): value = ms per MSM (device time, max over ranks, inputs resident in HBM);
+e2e = the same through the host-buffer API (scalars copied H2D from pinned memory inside the timed region, the
+64-byte affine result copied back); roofline = accumulate kernel vs the MEASURED INT32 multiply peak of this GPU;
+cpu_baseline = oracle/cpu_oracle.cpp (arkworks' msm_bigint_wnaf restated) on the host cores, bounded sample.
+
+--impl reference: the reference's CPU algorithm (the C++ restatement -- the Rust reference cannot be built in this
+image) timed on the host cores for the same metric; rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R_TOP_LIMB = 0x30644E72          # top 32-bit limb of the Fr modulus
+BLOCK_LOG = 20                   # synthetic data is generated in 2^20-element blocks seeded by block index
+SEED_BASES = 0xBA5E0000
+SEED_SCALARS = 0x5EED0000
+# W_G1(n) = n * 16 windows * 10 modmul * 136 mul32 (c = 16 signed-digit Pippenger, XYZZ mixed add)
+MUL32_PER_POINT = 16 * 10 * 136
+METRIC = "BN254 G1 MSM 2^%d ms"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="0 = choose for ~10-30 s of CPU work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic data
+def rand_fr_block(torch, seed, block, device):
+    """2^20 canonical Fr elements as int32 [2^20, 8] little-endian limbs; depends only on (seed, block)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + block)
+    x = torch.randint(0, 1 << 32, (1 << BLOCK_LOG, 8), dtype=torch.int64, device=device, generator=g)
+    x[:, 7] %= R_TOP_LIMB
+    return x.to(torch.int32)
+
+
+def rand_fr_range(torch, seed, start, count, device):
+    blk = 1 << BLOCK_LOG
+    out = torch.empty((count, 8), dtype=torch.int32, device=device)
+    pos = 0
+    while pos < count:
+        b, o = divmod(start + pos, blk)
+        take = min(blk - o, count - pos)
+        out[pos:pos + take] = rand_fr_block(torch, seed, b, device)[o:o + take]
+        pos += take
+    return out
+
+
+def numpy_scalars(np, seed, n):
+    rs = np.random.RandomState(seed & 0x7FFFFFFF)
+    s = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    s[:, 7] %= R_TOP_LIMB
+    return s
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_msm_rate(orc, np, log_n, threads, repeats=1, bases=None, scalars=None):
+    """Seconds per MSM of 2^log_n points with the C++ restatement of arkworks' msm_bigint (bases pre-parsed)."""
+    n = 1 << log_n
+    own = bases is None
+    if own:
+        bases = orc.G1Bases.arithmetic(0x1234567, n, threads)
+        scalars = numpy_scalars(np, SEED_SCALARS + log_n, n)
+    best, out = None, None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        out = bases.msm(scalars, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    if own:
+        bases.free()
+    return best, out
+
+
+def choose_cpu_sample(orc, np, threads, budget_s, hi=22, lo=16):
+    t18, _ = cpu_msm_rate(orc, np, 18, threads)
+    lg = 18
+    while lg < hi and t18 * (1 << (lg + 1 - 18)) * 0.9 <= budget_s:
+        lg += 1
+    while lg > lo and t18 * (1 << (lg - 18)) > budget_s * 1.5:
+        lg -= 1
+    return lg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import cpu as orc
+    threads = orc.max_threads()
+    total = args.steps + args.warmup
+    lg = args.cpu_sample_log_n or choose_cpu_sample(orc, np, threads, budget_s=150.0 / max(total, 1))
+    lg = min(lg, args.log_n)
+    n = 1 << lg
+    bases = orc.G1Bases.arithmetic(0x1234567, n, threads)
+    scalars = numpy_scalars(np, SEED_SCALARS + lg, n)
+    for _ in range(args.warmup):
+        bases.msm(scalars, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bases.msm(scalars, threads=threads)
+    per_step = (time.perf_counter() - t0) / max(args.steps, 1)
+    scale = float(1 << (args.log_n - lg))
+    ms_full = per_step * 1e3 * scale
+    sample = ("each step = one MSM of 2^%d points ((k0+i)G bases pre-parsed to Montgomery form, uniform scalars), "
+              "time scaled x%d to 2^%d points; C++ restatement of ark-ec msm_bigint_wnaf (window parallelism only), "
+              "not arkworks itself (no Rust toolchain / un-vendored crates)" % (lg, int(scale), args.log_n))
+    line = {
+        "impl": "reference", "metric": METRIC % args.log_n, "value": ms_full, "unit": "ms", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery)", "data": "synthetic",
+        "config": {"workload": "bn254_g1_msm", "log_n": args.log_n, "parallelism": "cpu x%d threads" % threads},
+        "cpu_baseline": {"value": ms_full, "unit": "ms", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": ms_full, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import zelana_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE=%d but --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = 1 << args.log_n
+    assert n % world == 0
+    shard = n // world
+    lo = rank * shard
+    stream = torch.cuda.current_stream()
+    ctx = zelana_b200.Context(local, stream=stream.cuda_stream)
+
+    # ---- synthetic workload (identical for every N): bases = proving-key points resident in HBM
+    k = rand_fr_range(torch, SEED_BASES, lo, shard, dev)
+    bases = ctx.g1_bases_generate(k, shard)
+    ctx.synchronize()
+    del k
+    scal = rand_fr_range(torch, SEED_SCALARS, lo, shard, dev)
+    part = torch.zeros(128, dtype=torch.uint8, device=dev)
+    parts = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
+    out_aff = torch.zeros(64, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        if world == 1:
+            ctx.msm_g1_dev(bases, scal, shard, out_affine_dev=out_aff)
+        else:
+            ctx.msm_g1_dev(bases, scal, shard, out_partial_dev=part)
+            dist.all_gather_into_tensor(parts, part)
+            ctx.msm_g1_combine(parts, world, out_aff)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- INT32 multiply peak of this GPU, measured now (roofline denominator)
+    peak_wide, _ = ctx.int32_peak(0)
+    peak_pair, _ = ctx.int32_peak(1)
+    peak = max(peak_wide, peak_pair)
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ctx.profile(True)
+    ctx.profile_reset()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = ctx.launch_count() - launches0
+    phases = ctx.profile_read()
+    ctx.profile(False)
+    result_hex = bytes(out_aff.cpu().numpy()).hex()
+
+    # ---- end to end through the host-buffer API: H2D scalars (pinned) + MSM + D2H result, every step
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((shard, 8), dtype=torch.int32, pin_memory=True)
+        host.copy_(scal)
+        torch.cuda.synchronize()
+        host_np = host.numpy().view(np.uint8).reshape(-1)
+        out_host = torch.empty(64, dtype=torch.uint8, pin_memory=True)
+
+        def step_e2e():
+            if world == 1:
+                return ctx.msm_g1(bases, host_np)      # the C-ABI call a user makes: zkb_msm_g1(host scalars) -> 64 B
+            scal.copy_(host, non_blocking=True)
+            step_device()
+            out_host.copy_(out_aff, non_blocking=True)
+            stream.synchronize()
+            return bytes(out_host.numpy())
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            r_e2e = step_e2e()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            r_e2e = step_e2e()
+        f1.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+        assert bytes(r_e2e).hex() == result_hex, "host-buffer path and device path disagree"
+        e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": shard * 32 * world, "d2h_bytes_per_step": 64 * world}
+
+    # ---- roofline of the dominant kernel (bucket accumulation), device time from CUDA events around it
+    acc_ms, acc_spans = phases.get("msm_g1_accumulate", (0.0, 0))
+    roof = None
+    if acc_spans:
+        t_acc = acc_ms / acc_spans * 1e-3
+        achieved = MUL32_PER_POINT * shard / t_acc
+        roof = {"bound": "int32_mul", "kernel": "msm_accumulate_kernel<Fq>", "achieved": achieved / 1e12, "peak": peak / 1e12,
+                "unit": "Tmul32/s", "frac": achieved / peak, "traffic": None,
+                "kernel_ms": t_acc * 1e3,
+                "peak_source": "measured live: zkb_bench_int32_peak (mad.wide.u32 %.2f, lo/hi pairs %.2f Tmul32/s)" % (
+                    peak_wide / 1e12, peak_pair / 1e12),
+                "algorithmic_mul32_per_launch": MUL32_PER_POINT * shard,
+                "whole_msm_frac": MUL32_PER_POINT * shard / (ms_dev * 1e-3) / peak,
+                "hbm_gather_gbs": (shard * 16 * 64 + shard * 16 * 8) / t_acc / 1e9}
+    phase_ms = {k2: v[0] / args.steps for k2, v in phases.items()}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): same bases/scalars, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu as orc
+        threads = orc.max_threads()
+        lg = min(args.cpu_sample_log_n or choose_cpu_sample(orc, np, threads, budget_s=20.0), args.log_n)
+        m = 1 << lg
+        cb = orc.G1Bases.from_raw(bases.read(0, m), threads)
+        sc_np = scal[:m].cpu().numpy().view(np.uint8).reshape(-1)
+        t_cpu, cpu_out = cpu_msm_rate(orc, np, lg, threads, bases=cb, scalars=sc_np)
+        cb.free()
+        gpu_out = ctx.msm_g1(bases, sc_np)     # same sub-range through the GPU path: must be byte-identical
+        if bytes(gpu_out) != bytes(cpu_out):
+            raise SystemExit("PARITY FAILURE: GPU MSM != CPU restatement on the first 2^%d points" % lg)
+        scale = float(1 << (args.log_n - lg))
+        cpu = {"value": t_cpu * 1e3 * scale, "unit": "ms", "cores": threads, "kind": "port",
+               "sample": "first 2^%d of the 2^%d (base, scalar) pairs, %.2f s, scaled x%d; C++ restatement of ark-ec "
+                         "msm_bigint_wnaf (parallel over windows only); GPU result on the same sample byte-identical"
+                         % (lg, args.log_n, t_cpu, int(scale))}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC % args.log_n, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery)", "data": "synthetic",
+            "config": {"workload": "bn254_g1_msm", "log_n": args.log_n, "points_per_gpu": shard,
+                       "parallelism": "range-sharded x%d + NCCL all-gather of partial sums" % world if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (bases %d MB + scalars %d MB per GPU)" % (shard * 64 >> 20, shard * 32 >> 20)},
+            "points_per_s": n / (ms_dev * 1e-3),
+            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "phase_ms_per_step": phase_ms,
+            "cpu_baseline": cpu, "clocks": clocks, "result": result_hex,
+        }
+        print(json.dumps(line), flush=True)
+    bases.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

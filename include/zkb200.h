@@ -57,6 +57,19 @@ unsigned long long zkb_launch_count(zkb_ctx* ctx);
 /* force the MSM window width (0 = automatic) -- benchmarking/tests only */
 int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c);
 
+/* ---- per-phase device timing (replaces the reference's only timer, `proving_time_ms = start.elapsed()`,
+ * core/src/sequencer/settlement/prover.rs:351,418, with CUDA-event spans on ctx's stream) -------------- */
+int zkb_prof_phase_count(void);
+const char* zkb_prof_phase_name(int phase);   /* "msm_g1_accumulate", "ntt", ... */
+int zkb_prof_enable(zkb_ctx* ctx, int on);    /* off by default; when on, every phase is bracketed by two events */
+int zkb_prof_reset(zkb_ctx* ctx);             /* synchronises the stream, zeroes the totals */
+/* synchronises the stream; total_ms = device time spent in `phase` since the last reset, spans = how many times */
+int zkb_prof_read(zkb_ctx* ctx, int phase, double* total_ms, unsigned long long* spans);
+
+/* INT32 multiply-pipe peak of this GPU (the MSM roofline denominator): dependency-free
+ * 32x32->64 multiply-accumulates per second.  variant 0 = mad.wide.u32, 1 = mad.lo.cc/madc.hi pairs. */
+int zkb_bench_int32_peak(zkb_ctx* ctx, int variant, int iters, double* mul32_per_s, double* elapsed_ms);
+
 /* ---- field arithmetic parity hooks (ark-ff Fp<MontBackend<_,4>>: SURVEY.md 8a row a9) -------- */
 /* field: 0 = Fr, 1 = Fq.  op: 0 add, 1 sub, 2 mul, 3 inverse (b ignored; 0 -> 0), 4 neg (b ignored).
  * a, b, out: n x 32 B canonical LE, host memory. */

@@ -1,0 +1,716 @@
+// ORACLE (test infrastructure + CPU baseline only; the product path never links or loads this file).
+//
+// Multithreaded C++ restatement of the CPU algorithms the reference's prover executes inside arkworks
+// 0.5.0 (crates.io dependencies pinned in Cargo.lock:226-229,290-293,344-347,411-414,440-443 and NOT
+// vendored under /root/reference, so the reference itself cannot be compiled here -- there is no Rust
+// toolchain either).  The reference enters this code from
+//   core/src/sequencer/settlement/prover.rs:408     Groth16::<Bn254>::prove
+//   prover/src/snarkjs.rs:156-163                   setup / prove / verify of SquareCircuit
+// Restated, with the same algorithmic choices as the published crates:
+//   ark-ff   Fp<MontBackend<_,4>>          4 x 64-bit limb Montgomery CIOS (R = 2^256)
+//   ark-ec   VariableBaseMSM::msm_bigint   -> msm_bigint_wnaf: signed digits, c = 3 if n < 32 else
+//                                             ceil(log2 n)*69/100 + 2, 2^c Jacobian buckets per window,
+//                                             mixed additions, running-sum reduction, parallel OVER
+//                                             WINDOWS ONLY (rayon cfg_into_iter over 0..digits_count)
+//   ark-poly Radix2EvaluationDomain        in-place radix-2 FFT (bit reversal + butterflies), coset
+//                                             offset Fr::GENERATOR = 5, 1/n folded into the inverse
+//   ark-groth16 r1cs_to_qap / prover       witness_map_from_matrices, create_proof_with_assignment
+//
+// Parity status: PINNED through tests/test_cpu_oracle.py, which checks every export against
+// oracle/*.py, itself pinned by the reference's committed fixtures (tests/test_oracle_kat.py: the
+// seed-42 SquareCircuit proof of onchain-programs/verifier/proof_for_onchain.json is reproduced byte
+// for byte).  Timed rows produced with this file are labelled "CPU restatement (port), not arkworks".
+#include <omp.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+// ------------------------------------------------------------------------------------------ fields
+struct FqP {
+  static constexpr u64 M[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  static constexpr u64 INV = 0x87d20782e4866389ull;
+  static constexpr u64 R1[4] = {0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full};
+  static constexpr u64 R2[4] = {0xf32cfc5b538afa89ull, 0xb5e71911d44501fbull, 0x47ab1eff0a417ff6ull, 0x06d89f71cab8351full};
+};
+struct FrP {
+  static constexpr u64 M[4] = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  static constexpr u64 INV = 0xc2e1f593efffffffull;
+  static constexpr u64 R1[4] = {0xac96341c4ffffffbull, 0x36fc76959f60cd29ull, 0x666ea36f7879462eull, 0x0e0a77c19a07df2full};
+  static constexpr u64 R2[4] = {0x1bb8e645ae216da7ull, 0x53fe3ab1e35c59e3ull, 0x8c49833d53bb8085ull, 0x0216d0b17f4e44a5ull};
+};
+
+template <class P>
+struct Fp {
+  u64 v[4];
+  static Fp zero() { return Fp{{0, 0, 0, 0}}; }
+  static Fp one() { return Fp{{P::R1[0], P::R1[1], P::R1[2], P::R1[3]}}; }
+  bool is_zero() const { return (v[0] | v[1] | v[2] | v[3]) == 0; }
+  bool operator==(const Fp& o) const { return v[0] == o.v[0] && v[1] == o.v[1] && v[2] == o.v[2] && v[3] == o.v[3]; }
+  bool operator!=(const Fp& o) const { return !(*this == o); }
+  static bool geq_mod(const u64* a) {
+    for (int i = 3; i >= 0; i--) {
+      if (a[i] > P::M[i]) return true;
+      if (a[i] < P::M[i]) return false;
+    }
+    return true;
+  }
+  static void sub_mod(u64* a) {
+    u128 b = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)a[i] - P::M[i] - (u64)b;
+      a[i] = (u64)d;
+      b = (d >> 64) & 1;
+    }
+  }
+  Fp operator+(const Fp& o) const {
+    Fp r;
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)v[i] + o.v[i];
+      r.v[i] = (u64)c;
+      c >>= 64;
+    }
+    if (geq_mod(r.v)) sub_mod(r.v);
+    return r;
+  }
+  Fp operator-(const Fp& o) const {
+    Fp r;
+    u64 b = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)v[i] - o.v[i] - b;
+      r.v[i] = (u64)d;
+      b = (u64)(d >> 64) & 1;
+    }
+    if (b) {
+      u128 c = 0;
+      for (int i = 0; i < 4; i++) {
+        c += (u128)r.v[i] + P::M[i];
+        r.v[i] = (u64)c;
+        c >>= 64;
+      }
+    }
+    return r;
+  }
+  Fp neg() const { return is_zero() ? *this : Fp::zero() - *this; }
+  Fp dbl() const { return *this + *this; }
+  // CIOS Montgomery product (ark-ff montgomery_backend.rs mul_assign, no-carry variant is an optimisation of this)
+  Fp operator*(const Fp& o) const {
+    u64 t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+      u128 c = 0;
+      for (int j = 0; j < 4; j++) {
+        c += (u128)v[j] * o.v[i] + t[j];
+        t[j] = (u64)c;
+        c >>= 64;
+      }
+      c += t[4];
+      t[4] = (u64)c;
+      t[5] = (u64)(c >> 64);
+      u64 m = t[0] * P::INV;
+      c = (u128)m * P::M[0] + t[0];
+      c >>= 64;
+      for (int j = 1; j < 4; j++) {
+        c += (u128)m * P::M[j] + t[j];
+        t[j - 1] = (u64)c;
+        c >>= 64;
+      }
+      c += t[4];
+      t[3] = (u64)c;
+      t[4] = t[5] + (u64)(c >> 64);
+    }
+    Fp r{{t[0], t[1], t[2], t[3]}};
+    if (t[4] || geq_mod(r.v)) sub_mod(r.v);
+    return r;
+  }
+  Fp sqr() const { return *this * *this; }
+  Fp pow(const u64* e, int nlimbs) const {
+    Fp r = one();
+    bool started = false;
+    for (int i = nlimbs - 1; i >= 0; i--)
+      for (int b = 63; b >= 0; b--) {
+        if (started) r = r.sqr();
+        if ((e[i] >> b) & 1) {
+          r = started ? r * *this : *this;
+          started = true;
+        }
+      }
+    return r;
+  }
+  Fp inverse() const {
+    u64 e[4] = {P::M[0] - 2, P::M[1], P::M[2], P::M[3]};
+    return pow(e, 4);
+  }
+  static Fp from_canonical(const uint8_t* b) {
+    Fp x;
+    memcpy(x.v, b, 32);
+    Fp r2{{P::R2[0], P::R2[1], P::R2[2], P::R2[3]}};
+    return x * r2;
+  }
+  void to_canonical(uint8_t* b) const {
+    Fp o{{1, 0, 0, 0}};
+    Fp c = *this * o;
+    memcpy(b, c.v, 32);
+  }
+  static Fp from_u64(u64 x) {
+    uint8_t b[32] = {0};
+    memcpy(b, &x, 8);
+    return from_canonical(b);
+  }
+};
+typedef Fp<FqP> Fq;
+typedef Fp<FrP> Fr;
+
+struct Fq2 {
+  Fq c0, c1;
+  static Fq2 zero() { return {Fq::zero(), Fq::zero()}; }
+  static Fq2 one() { return {Fq::one(), Fq::zero()}; }
+  bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+  bool operator!=(const Fq2& o) const { return !(*this == o); }
+  Fq2 operator+(const Fq2& o) const { return {c0 + o.c0, c1 + o.c1}; }
+  Fq2 operator-(const Fq2& o) const { return {c0 - o.c0, c1 - o.c1}; }
+  Fq2 operator*(const Fq2& o) const {
+    Fq v0 = c0 * o.c0, v1 = c1 * o.c1;
+    return {v0 - v1, (c0 + c1) * (o.c0 + o.c1) - v0 - v1};
+  }
+  Fq2 sqr() const {
+    Fq t = c0 * c1;
+    return {(c0 + c1) * (c0 - c1), t + t};
+  }
+  Fq2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+  Fq2 neg() const { return {c0.neg(), c1.neg()}; }
+  Fq2 inverse() const {
+    Fq d = (c0.sqr() + c1.sqr()).inverse();
+    return {c0 * d, (c1 * d).neg()};
+  }
+  static Fq2 from_canonical(const uint8_t* b) { return {Fq::from_canonical(b), Fq::from_canonical(b + 32)}; }
+  void to_canonical(uint8_t* b) const {
+    c0.to_canonical(b);
+    c1.to_canonical(b + 32);
+  }
+};
+
+template <class F> struct FBytes;
+template <> struct FBytes<Fq> { static constexpr int N = 32; };
+template <> struct FBytes<Fq2> { static constexpr int N = 64; };
+
+// ------------------------------------------------------------------------------------------ curve (Jacobian, a = 0)
+template <class F>
+struct Aff {
+  F x, y;
+  bool inf;
+};
+
+template <class F>
+struct Jac {
+  F x, y, z;
+  static Jac zero() { return {F::one(), F::one(), F::zero()}; }
+  bool is_zero() const { return z.is_zero(); }
+  static Jac from_affine(const Aff<F>& p) { return p.inf ? zero() : Jac{p.x, p.y, F::one()}; }
+  // dbl-2009-l
+  void double_in_place() {
+    if (is_zero()) return;
+    F a = x.sqr(), b = y.sqr(), c = b.sqr();
+    F d = ((x + b).sqr() - a - c).dbl();
+    F e = a + a.dbl();
+    F f = e.sqr();
+    F z3 = (z * y).dbl();
+    F x3 = f - d.dbl();
+    F c8 = c.dbl().dbl().dbl();
+    y = (d - x3) * e - c8;
+    x = x3;
+    z = z3;
+  }
+  // madd-2007-bl
+  void add_affine(const Aff<F>& q) {
+    if (q.inf) return;
+    if (is_zero()) {
+      *this = from_affine(q);
+      return;
+    }
+    F z1z1 = z.sqr();
+    F u2 = q.x * z1z1;
+    F s2 = q.y * z * z1z1;
+    if (x == u2) {
+      if (y == s2) double_in_place();
+      else *this = zero();
+      return;
+    }
+    F h = u2 - x;
+    F hh = h.sqr();
+    F i = hh.dbl().dbl();
+    F j = h * i;
+    F r = (s2 - y).dbl();
+    F v = x * i;
+    F x3 = r.sqr() - j - v.dbl();
+    F y3 = r * (v - x3) - (y * j).dbl();
+    F z3 = (z + h).sqr() - z1z1 - hh;
+    x = x3;
+    y = y3;
+    z = z3;
+  }
+  void sub_affine(const Aff<F>& q) {
+    Aff<F> n{q.x, q.y.neg(), q.inf};
+    add_affine(n);
+  }
+  // add-2007-bl
+  void add(const Jac& q) {
+    if (q.is_zero()) return;
+    if (is_zero()) {
+      *this = q;
+      return;
+    }
+    F z1z1 = z.sqr(), z2z2 = q.z.sqr();
+    F u1 = x * z2z2, u2 = q.x * z1z1;
+    F s1 = y * q.z * z2z2, s2 = q.y * z * z1z1;
+    if (u1 == u2) {
+      if (s1 == s2) double_in_place();
+      else *this = zero();
+      return;
+    }
+    F h = u2 - u1;
+    F i = h.dbl().sqr();
+    F j = h * i;
+    F r = (s2 - s1).dbl();
+    F v = u1 * i;
+    F x3 = r.sqr() - j - v.dbl();
+    F y3 = r * (v - x3) - (s1 * j).dbl();
+    F z3 = ((z + q.z).sqr() - z1z1 - z2z2) * h;
+    x = x3;
+    y = y3;
+    z = z3;
+  }
+  Jac neg() const { return {x, y.neg(), z}; }
+  Jac mul_bits(const u64* k, int nlimbs) const {
+    Jac r = zero();
+    for (int i = nlimbs - 1; i >= 0; i--)
+      for (int b = 63; b >= 0; b--) {
+        r.double_in_place();
+        if ((k[i] >> b) & 1) r.add(*this);
+      }
+    return r;
+  }
+  Aff<F> to_affine() const {
+    if (is_zero()) return {F::zero(), F::zero(), true};
+    F zi = z.inverse();
+    F zi2 = zi.sqr();
+    return {x * zi2, y * zi2 * zi, false};
+  }
+};
+
+template <class F>
+static Aff<F> aff_from_raw(const uint8_t* b) {
+  constexpr int N = FBytes<F>::N;
+  bool allz = true;
+  for (int i = 0; i < 2 * N; i++)
+    if (b[i]) {
+      allz = false;
+      break;
+    }
+  if (allz) return {F::zero(), F::zero(), true};
+  return {F::from_canonical(b), F::from_canonical(b + N), false};
+}
+template <class F>
+static void aff_to_raw(const Aff<F>& p, uint8_t* b) {
+  constexpr int N = FBytes<F>::N;
+  if (p.inf) {
+    memset(b, 0, 2 * N);
+    return;
+  }
+  p.x.to_canonical(b);
+  p.y.to_canonical(b + N);
+}
+
+// ------------------------------------------------------------------------------------------ MSM (ark-ec msm_bigint_wnaf)
+static int ceil_log2(size_t n) {
+  int l = 0;
+  while ((size_t(1) << l) < n) l++;
+  return l;
+}
+static int ark_window(size_t n) { return n < 32 ? 3 : ceil_log2(n) * 69 / 100 + 2; }
+
+// make_digits(scalar, w, num_bits = 254): signed radix-2^w digits
+static void make_digits(const u64* s, int w, int num_bits, int64_t* out, int digits_count) {
+  u64 radix = u64(1) << w, window_mask = radix - 1;
+  u64 carry = 0;
+  for (int i = 0; i < digits_count; i++) {
+    int bit_offset = i * w, u64_idx = bit_offset / 64, bit_idx = bit_offset % 64;
+    u64 bit_buf;
+    if (bit_idx < 64 - w || u64_idx == 3) bit_buf = s[u64_idx] >> bit_idx;
+    else bit_buf = (s[u64_idx] >> bit_idx) | (s[u64_idx + 1] << (64 - bit_idx));
+    u64 coef = carry + (bit_buf & window_mask);
+    carry = (coef + radix / 2) >> w;
+    int64_t d = (int64_t)coef - (int64_t)(carry << w);
+    if (i == digits_count - 1) d += (int64_t)(carry << w);
+    out[i] = d;
+  }
+  (void)num_bits;
+}
+
+template <class F>
+static Jac<F> msm_bigint(const Aff<F>* bases, const u64* scalars /* n x 4, canonical */, size_t n, int threads) {
+  if (n == 0) return Jac<F>::zero();
+  const int c = ark_window(n);
+  const int num_bits = 254;
+  const int digits_count = (num_bits + c - 1) / c;
+  std::vector<int64_t> digits(size_t(digits_count) * n);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) make_digits(scalars + 4 * i, c, num_bits, &digits[i * digits_count], digits_count);
+  std::vector<Jac<F>> window_sums(digits_count);
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1)
+  for (int w = 0; w < digits_count; w++) {
+    std::vector<Jac<F>> buckets(size_t(1) << c, Jac<F>::zero());
+    for (size_t i = 0; i < n; i++) {
+      int64_t d = digits[i * digits_count + w];
+      if (d > 0) buckets[d - 1].add_affine(bases[i]);
+      else if (d < 0) buckets[-d - 1].sub_affine(bases[i]);
+    }
+    Jac<F> running = Jac<F>::zero(), res = Jac<F>::zero();
+    for (size_t b = buckets.size(); b-- > 0;) {
+      running.add(buckets[b]);
+      res.add(running);
+    }
+    window_sums[w] = res;
+  }
+  Jac<F> total = Jac<F>::zero();
+  for (int w = digits_count - 1; w >= 1; w--) {
+    total.add(window_sums[w]);
+    for (int k = 0; k < c; k++) total.double_in_place();
+  }
+  total.add(window_sums[0]);
+  return total;
+}
+
+// ------------------------------------------------------------------------------------------ NTT (ark-poly radix-2)
+static Fr fr_pow_u64(Fr b, u64 e) { return b.pow(&e, 1); }
+static Fr fr_generator() { return Fr::from_u64(5); }
+static Fr fr_root_of_unity(int logn) {
+  // 5^((r-1)/2^28) then squared down to order 2^logn
+  u64 e[4] = {FrP::M[0] - 1, FrP::M[1], FrP::M[2], FrP::M[3]};
+  // (r - 1) >> 28
+  u64 s[4];
+  for (int i = 0; i < 4; i++) s[i] = (e[i] >> 28) | (i < 3 ? e[i + 1] << 36 : 0);
+  Fr w = fr_generator().pow(s, 4);
+  for (int k = logn; k < 28; k++) w = w.sqr();
+  return w;
+}
+
+static void ntt_in_place(Fr* a, int logn, const Fr& omega, int threads) {
+  const size_t n = size_t(1) << logn;
+  if (n == 1) return;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) {
+    size_t r = 0;
+    for (int b = 0; b < logn; b++) r |= ((i >> b) & 1) << (logn - 1 - b);
+    if (i < r) {
+      Fr t = a[i];
+      a[i] = a[r];
+      a[r] = t;
+    }
+  }
+  // twiddles omega^j, j < n/2 (ark-poly caches the roots of unity per call as well)
+  std::vector<Fr> tw(n / 2);
+  {
+    const size_t blk = 1 << 12;
+    size_t nb = (n / 2 + blk - 1) / blk;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t b = 0; b < nb; b++) {
+      size_t s = b * blk, e = s + blk < n / 2 ? s + blk : n / 2;
+      Fr w = fr_pow_u64(omega, s);
+      for (size_t j = s; j < e; j++) {
+        tw[j] = w;
+        w = w * omega;
+      }
+    }
+  }
+  for (int st = 0; st < logn; st++) {
+    const size_t m = size_t(1) << st;
+    const size_t step = n >> (st + 1);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t t = 0; t < n / 2; t++) {
+      size_t k = (t >> st) << (st + 1), j = t & (m - 1);
+      Fr u = a[k + j];
+      Fr v = j ? a[k + j + m] * tw[j * step] : a[k + j + m];
+      a[k + j] = u + v;
+      a[k + j + m] = u - v;
+    }
+  }
+}
+
+static void scale_powers(Fr* a, size_t n, const Fr& g, const Fr& c0, int threads) {
+  const size_t blk = 1 << 12;
+  size_t nb = (n + blk - 1) / blk;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t b = 0; b < nb; b++) {
+    size_t s = b * blk, e = s + blk < n ? s + blk : n;
+    Fr w = fr_pow_u64(g, s) * c0;
+    for (size_t j = s; j < e; j++) {
+      a[j] = a[j] * w;
+      w = w * g;
+    }
+  }
+}
+
+// direction 0 fft, 1 ifft; coset: offset g = 5
+static void domain_transform(Fr* a, int logn, int inverse, int coset, int threads) {
+  const size_t n = size_t(1) << logn;
+  Fr w = fr_root_of_unity(logn);
+  if (!inverse) {
+    if (coset) scale_powers(a, n, fr_generator(), Fr::one(), threads);
+    ntt_in_place(a, logn, w, threads);
+  } else {
+    ntt_in_place(a, logn, w.inverse(), threads);
+    Fr ninv = Fr::from_u64((u64)n).inverse();
+    scale_powers(a, n, coset ? fr_generator().inverse() : Fr::one(), ninv, threads);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ R1CS / Groth16
+struct Csr {
+  const u64* row_ptr;
+  const uint32_t* col;
+  const uint8_t* coeff;
+};
+
+static void matvec(const Csr& m, size_t nc, const std::vector<Fr>& z, Fr* out, int threads) {
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < nc; i++) {
+    Fr acc = Fr::zero();
+    for (u64 k = m.row_ptr[i]; k < m.row_ptr[i + 1]; k++) acc = acc + Fr::from_canonical(m.coeff + 32 * k) * z[m.col[k]];
+    out[i] = acc;
+  }
+}
+
+static int witness_map(size_t nc, size_t ni, size_t nw, const Csr& A, const Csr& B, const Csr& C, const uint8_t* z_bytes,
+                       std::vector<Fr>& h, int threads) {
+  int logn = ceil_log2(nc + ni);
+  size_t n = size_t(1) << logn;
+  std::vector<Fr> z(ni + nw);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < ni + nw; i++) z[i] = Fr::from_canonical(z_bytes + 32 * i);
+  std::vector<Fr> a(n, Fr::zero()), b(n, Fr::zero()), c(n, Fr::zero());
+  matvec(A, nc, z, a.data(), threads);
+  matvec(B, nc, z, b.data(), threads);
+  for (size_t j = 0; j < ni; j++) a[nc + j] = z[j];
+  domain_transform(a.data(), logn, 1, 0, threads);
+  domain_transform(b.data(), logn, 1, 0, threads);
+  domain_transform(a.data(), logn, 0, 1, threads);
+  domain_transform(b.data(), logn, 0, 1, threads);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) a[i] = a[i] * b[i];
+  matvec(C, nc, z, c.data(), threads);
+  domain_transform(c.data(), logn, 1, 0, threads);
+  domain_transform(c.data(), logn, 0, 1, threads);
+  Fr gn = fr_generator();
+  for (int k = 0; k < logn; k++) gn = gn.sqr();
+  Fr zinv = (gn - Fr::one()).inverse();
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) a[i] = (a[i] - c[i]) * zinv;
+  domain_transform(a.data(), logn, 1, 1, threads);
+  h.swap(a);
+  return logn;
+}
+
+template <class F>
+static std::vector<Aff<F>> load_points(const uint8_t* raw, size_t n, int threads) {
+  std::vector<Aff<F>> v(n);
+  constexpr int N = 2 * FBytes<F>::N;
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) v[i] = aff_from_raw<F>(raw + N * i);
+  return v;
+}
+
+static std::vector<u64> fr_to_bigints(const Fr* v, size_t n, int threads) {
+  std::vector<u64> out(4 * n);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) v[i].to_canonical(reinterpret_cast<uint8_t*>(&out[4 * i]));
+  return out;
+}
+
+template <class F>
+static Jac<F> calculate_coeff(Jac<F> initial, const std::vector<Aff<F>>& query, const Aff<F>& vk_param,
+                              const u64* assignment, size_t na, int threads) {
+  Jac<F> acc = msm_bigint<F>(query.data() + 1, assignment, na < query.size() - 1 ? na : query.size() - 1, threads);
+  Jac<F> res = initial;
+  res.add_affine(query[0]);
+  res.add(acc);
+  res.add_affine(vk_param);
+  return res;
+}
+
+extern "C" {
+
+int orc_max_threads(void) { return omp_get_max_threads(); }
+
+// field: 0 Fr, 1 Fq; op: 0 add 1 sub 2 mul 3 inverse 4 neg; canonical 32 B LE in and out
+void orc_field_op(int field, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    if (field == 0) {
+      Fr x = Fr::from_canonical(a + 32 * i), y = b ? Fr::from_canonical(b + 32 * i) : Fr::zero(), r;
+      r = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 3 ? x.inverse() : x.neg();
+      r.to_canonical(out + 32 * i);
+    } else {
+      Fq x = Fq::from_canonical(a + 32 * i), y = b ? Fq::from_canonical(b + 32 * i) : Fq::zero(), r;
+      r = op == 0 ? x + y : op == 1 ? x - y : op == 2 ? x * y : op == 3 ? x.inverse() : x.neg();
+      r.to_canonical(out + 32 * i);
+    }
+  }
+}
+
+int orc_msm_window(size_t n) { return ark_window(n); }
+
+void orc_msm_g1(const uint8_t* bases, const uint8_t* scalars, size_t n, int threads, uint8_t out[64]) {
+  auto pts = load_points<Fq>(bases, n, threads);
+  Jac<Fq> r = msm_bigint<Fq>(pts.data(), reinterpret_cast<const u64*>(scalars), n, threads);
+  aff_to_raw<Fq>(r.to_affine(), out);
+}
+void orc_msm_g2(const uint8_t* bases, const uint8_t* scalars, size_t n, int threads, uint8_t out[128]) {
+  auto pts = load_points<Fq2>(bases, n, threads);
+  Jac<Fq2> r = msm_bigint<Fq2>(pts.data(), reinterpret_cast<const u64*>(scalars), n, threads);
+  aff_to_raw<Fq2>(r.to_affine(), out);
+}
+
+// Opaque pre-parsed bases so that a timed MSM excludes the byte->Montgomery conversion (arkworks holds the
+// proving key in Montgomery form in memory as well).
+void* orc_g1_bases_new(const uint8_t* bases, size_t n, int threads) {
+  return new std::vector<Aff<Fq>>(load_points<Fq>(bases, n, threads));
+}
+// bases[i] = (k0 + i) * G with G = (1, 2): a cheap way to make many valid points (repeated mixed addition +
+// per-point inversion would be slow, so this normalises in batches with Montgomery's trick).
+void* orc_g1_bases_arith(uint64_t k0, size_t n, int threads) {
+  auto* v = new std::vector<Aff<Fq>>(n);
+  Aff<Fq> g{Fq::from_u64(1), Fq::from_u64(2), false};
+  const size_t blk = 1 << 12;
+  size_t nb = (n + blk - 1) / blk;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 4)
+  for (size_t b = 0; b < nb; b++) {
+    size_t s = b * blk, e = s + blk < n ? s + blk : n;
+    u64 k = k0 + s;
+    Jac<Fq> cur = Jac<Fq>::from_affine(g).mul_bits(&k, 1);
+    std::vector<Jac<Fq>> js(e - s);
+    for (size_t i = s; i < e; i++) {
+      js[i - s] = cur;
+      cur.add_affine(g);
+    }
+    // batch inversion of z
+    std::vector<Fq> pre(e - s);
+    Fq acc = Fq::one();
+    for (size_t i = 0; i < e - s; i++) {
+      pre[i] = acc;
+      if (!js[i].is_zero()) acc = acc * js[i].z;
+    }
+    Fq inv = acc.inverse();
+    for (size_t i = e - s; i-- > 0;) {
+      if (js[i].is_zero()) {
+        (*v)[s + i] = {Fq::zero(), Fq::zero(), true};
+        continue;
+      }
+      Fq zi = inv * pre[i];
+      inv = inv * js[i].z;
+      Fq zi2 = zi.sqr();
+      (*v)[s + i] = {js[i].x * zi2, js[i].y * zi2 * zi, false};
+    }
+  }
+  return v;
+}
+void orc_g1_bases_read(void* h, size_t off, size_t n, uint8_t* out) {
+  auto* v = static_cast<std::vector<Aff<Fq>>*>(h);
+  for (size_t i = 0; i < n; i++) aff_to_raw<Fq>((*v)[off + i], out + 64 * i);
+}
+void orc_g1_bases_free(void* h) { delete static_cast<std::vector<Aff<Fq>>*>(h); }
+void orc_msm_g1_pre(void* h, size_t off, const uint8_t* scalars, size_t n, int threads, uint8_t out[64]) {
+  auto* v = static_cast<std::vector<Aff<Fq>>*>(h);
+  Jac<Fq> r = msm_bigint<Fq>(v->data() + off, reinterpret_cast<const u64*>(scalars), n, threads);
+  aff_to_raw<Fq>(r.to_affine(), out);
+}
+
+// in place on n x 32 B canonical LE
+void orc_ntt(uint8_t* data, int logn, int inverse, int coset, int threads) {
+  size_t n = size_t(1) << logn;
+  std::vector<Fr> a(n);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) a[i] = Fr::from_canonical(data + 32 * i);
+  domain_transform(a.data(), logn, inverse, coset, threads);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) a[i].to_canonical(data + 32 * i);
+}
+
+int orc_witness_map(uint64_t nc, uint64_t ni, uint64_t nw, const u64* a_rp, const uint32_t* a_col, const uint8_t* a_co,
+                    const u64* b_rp, const uint32_t* b_col, const uint8_t* b_co, const u64* c_rp, const uint32_t* c_col,
+                    const uint8_t* c_co, const uint8_t* z, uint8_t* h_out, int threads) {
+  std::vector<Fr> h;
+  int logn = witness_map(nc, ni, nw, Csr{a_rp, a_col, a_co}, Csr{b_rp, b_col, b_co}, Csr{c_rp, c_col, c_co}, z, h, threads);
+  for (size_t i = 0; i < h.size(); i++) h[i].to_canonical(h_out + 32 * i);
+  return logn;
+}
+
+// ---- Groth16 prove with a pre-parsed key (create_proof_with_assignment) --------------------------------
+struct OrcPk {
+  Aff<Fq> alpha_g1, beta_g1, delta_g1;
+  Aff<Fq2> beta_g2, delta_g2;
+  std::vector<Aff<Fq>> a_query, b_g1_query, h_query, l_query;
+  std::vector<Aff<Fq2>> b_g2_query;
+};
+
+void* orc_pk_new(const uint8_t* alpha_g1, const uint8_t* beta_g1, const uint8_t* beta_g2, const uint8_t* delta_g1,
+                 const uint8_t* delta_g2, const uint8_t* a_query, size_t a_len, const uint8_t* b_g1_query,
+                 const uint8_t* b_g2_query, const uint8_t* h_query, size_t h_len, const uint8_t* l_query, size_t l_len,
+                 int threads) {
+  OrcPk* pk = new OrcPk();
+  pk->alpha_g1 = aff_from_raw<Fq>(alpha_g1);
+  pk->beta_g1 = aff_from_raw<Fq>(beta_g1);
+  pk->delta_g1 = aff_from_raw<Fq>(delta_g1);
+  pk->beta_g2 = aff_from_raw<Fq2>(beta_g2);
+  pk->delta_g2 = aff_from_raw<Fq2>(delta_g2);
+  pk->a_query = load_points<Fq>(a_query, a_len, threads);
+  pk->b_g1_query = load_points<Fq>(b_g1_query, a_len, threads);
+  pk->b_g2_query = load_points<Fq2>(b_g2_query, a_len, threads);
+  pk->h_query = load_points<Fq>(h_query, h_len, threads);
+  pk->l_query = load_points<Fq>(l_query, l_len, threads);
+  return pk;
+}
+void orc_pk_free(void* pk) { delete static_cast<OrcPk*>(pk); }
+
+int orc_prove(void* pkh, uint64_t nc, uint64_t ni, uint64_t nw, const u64* a_rp, const uint32_t* a_col, const uint8_t* a_co,
+              const u64* b_rp, const uint32_t* b_col, const uint8_t* b_co, const u64* c_rp, const uint32_t* c_col,
+              const uint8_t* c_co, const uint8_t* z, const uint8_t r_b[32], const uint8_t s_b[32], uint8_t out_a[64],
+              uint8_t out_b[128], uint8_t out_c[64], int threads) {
+  OrcPk* pk = static_cast<OrcPk*>(pkh);
+  if (pk->a_query.size() != ni + nw || pk->l_query.size() != nw) return -6;
+  std::vector<Fr> h;
+  witness_map(nc, ni, nw, Csr{a_rp, a_col, a_co}, Csr{b_rp, b_col, b_co}, Csr{c_rp, c_col, c_co}, z, h, threads);
+  std::vector<u64> hb = fr_to_bigints(h.data(), h.size(), threads);
+  const u64* zb = reinterpret_cast<const u64*>(z);
+  const u64* r = reinterpret_cast<const u64*>(r_b);
+  const u64* s = reinterpret_cast<const u64*>(s_b);
+  size_t hn = pk->h_query.size() < h.size() ? pk->h_query.size() : h.size();
+  Jac<Fq> h_acc = msm_bigint<Fq>(pk->h_query.data(), hb.data(), hn, threads);
+  Jac<Fq> l_acc = msm_bigint<Fq>(pk->l_query.data(), zb + 4 * ni, nw, threads);
+  Fr rm = Fr::from_canonical(r_b), sm = Fr::from_canonical(s_b);
+  u64 rs[4];
+  (rm * sm).to_canonical(reinterpret_cast<uint8_t*>(rs));
+  Jac<Fq> d1 = Jac<Fq>::from_affine(pk->delta_g1);
+  Jac<Fq2> d2 = Jac<Fq2>::from_affine(pk->delta_g2);
+  Jac<Fq> rs_delta = d1.mul_bits(rs, 4);
+  size_t na = ni + nw - 1;
+  Jac<Fq> g_a = calculate_coeff<Fq>(d1.mul_bits(r, 4), pk->a_query, pk->alpha_g1, zb + 4, na, threads);
+  bool r_zero = (r[0] | r[1] | r[2] | r[3]) == 0;
+  Jac<Fq> g1_b = r_zero ? Jac<Fq>::zero() : calculate_coeff<Fq>(d1.mul_bits(s, 4), pk->b_g1_query, pk->beta_g1, zb + 4, na, threads);
+  Jac<Fq2> g2_b = calculate_coeff<Fq2>(d2.mul_bits(s, 4), pk->b_g2_query, pk->beta_g2, zb + 4, na, threads);
+  Jac<Fq> g_c = g_a.mul_bits(s, 4);
+  g_c.add(g1_b.mul_bits(r, 4));
+  g_c.add(rs_delta.neg());
+  g_c.add(l_acc);
+  g_c.add(h_acc);
+  aff_to_raw<Fq>(g_a.to_affine(), out_a);
+  aff_to_raw<Fq2>(g2_b.to_affine(), out_b);
+  aff_to_raw<Fq>(g_c.to_affine(), out_c);
+  return 0;
+}
+
+}  // extern "C"

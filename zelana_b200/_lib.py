@@ -49,6 +49,12 @@ SIGNATURES = {
     "zkb_last_error": (C.c_char_p, [_P]),
     "zkb_launch_count": (C.c_ulonglong, [_P]),
     "zkb_ctx_set_msm_window": (_I, [_P, _I]),
+    "zkb_prof_phase_count": (_I, []),
+    "zkb_prof_phase_name": (C.c_char_p, [_I]),
+    "zkb_prof_enable": (_I, [_P, _I]),
+    "zkb_prof_reset": (_I, [_P]),
+    "zkb_prof_read": (_I, [_P, _I, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "zkb_bench_int32_peak": (_I, [_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "zkb_field_op": (_I, [_P, _I, _I, _P, _P, _SZ, _P]),
     "zkb_scalar_mul": (_I, [_P, _I, _P, _P, _SZ, _P]),
     "zkb_point_sum": (_I, [_P, _I, _P, _SZ, _P]),

@@ -13,7 +13,7 @@ G1_PARTIAL_BYTES, G2_PARTIAL_BYTES = 128, 256
 def _buf(x):
     """bytes / bytearray / numpy uint8 array -> (ctypes pointer, keepalive)."""
     if isinstance(x, np.ndarray):
-        a = np.ascontiguousarray(x)
+        a = np.ascontiguousarray(x).view(np.uint8).reshape(-1)
         return a.ctypes.data_as(C.c_void_p), a
     if isinstance(x, (bytes, bytearray, memoryview)):
         a = np.frombuffer(bytes(x), dtype=np.uint8)
@@ -59,6 +59,29 @@ class Context:
 
     def set_msm_window(self, c):
         self._check(self.lib.zkb_ctx_set_msm_window(self.h, c))
+
+    def profile(self, on=True):
+        """Bracket every phase (MSM digits/sort/accumulate/reduce, NTT, ...) with CUDA events on the context's stream."""
+        self._check(self.lib.zkb_prof_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.lib.zkb_prof_reset(self.h))
+
+    def profile_read(self):
+        """-> {phase name: (total device ms, spans)} since the last reset (synchronises the stream)."""
+        out = {}
+        for ph in range(self.lib.zkb_prof_phase_count()):
+            ms, cnt = C.c_double(), C.c_ulonglong()
+            self._check(self.lib.zkb_prof_read(self.h, ph, C.byref(ms), C.byref(cnt)))
+            if cnt.value:
+                out[self.lib.zkb_prof_phase_name(ph).decode()] = (ms.value, int(cnt.value))
+        return out
+
+    def int32_peak(self, variant=0, iters=2000):
+        """Measured INT32 multiply-pipe peak (mul32/s) of this GPU; variant 0 = IMAD.WIDE, 1 = lo/hi pairs."""
+        rate, ms = C.c_double(), C.c_double()
+        self._check(self.lib.zkb_bench_int32_peak(self.h, variant, iters, C.byref(rate), C.byref(ms)))
+        return rate.value, ms.value
 
     def close(self):
         if getattr(self, "h", None):
@@ -123,14 +146,14 @@ class Context:
     # ---- MSM
     def msm_g1(self, bases, scalars, offset=0):
         ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
-        n = len(scalars) // 32
+        n = len(ks) // 32 if ks is not None else 0
         out = np.empty(64, dtype=np.uint8)
         self._check(self.lib.zkb_msm_g1(self.h, bases.h, offset, ps, n, out.ctypes.data_as(C.c_void_p)))
         return out.tobytes()
 
     def msm_g2(self, bases, scalars, offset=0):
         ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
-        n = len(scalars) // 32
+        n = len(ks) // 32 if ks is not None else 0
         out = np.empty(128, dtype=np.uint8)
         self._check(self.lib.zkb_msm_g2(self.h, bases.h, offset, ps, n, out.ctypes.data_as(C.c_void_p)))
         return out.tobytes()

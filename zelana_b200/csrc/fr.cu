@@ -1,0 +1,320 @@
+// Fr-side kernels and drivers: the seven NTTs, the sparse mat-vecs and the pointwise QAP division of ark-groth16's
+// LibsnarkReduction::witness_map_from_matrices, entered by the reference at
+// core/src/sequencer/settlement/prover.rs:408.
+#include "internal.h"
+#include "ntt.cuh"
+
+namespace zkb {
+namespace {
+
+constexpr int NTT_LRMAX = 8;
+
+struct NttTables {
+  Fr* mem = nullptr;  // one allocation
+  PowTable fwd, inv, coset_pre, coset_inv_post;
+  const Fr* ninv = nullptr;
+};
+
+struct FrState {
+  Fr* wr_fwd = nullptr;  // omega_(2^LRMAX)^e
+  Fr* wr_inv = nullptr;
+  std::map<int, NttTables> tables;
+};
+
+FrState* state(zkb_ctx* ctx) {
+  if (!ctx->fr_state) ctx->fr_state = new FrState();
+  return static_cast<FrState*>(ctx->fr_state);
+}
+
+__device__ __forceinline__ bool fr_is_canonical(const Fr& a) {
+  Fr m = Fr::modulus();
+  for (int i = 7; i >= 0; i--) {
+    if (a.v[i] < m.v[i]) return true;
+    if (a.v[i] > m.v[i]) return false;
+  }
+  return false;
+}
+
+__global__ void fr_field_op_kernel(int op, const Fr* a, const Fr* b, size_t n, Fr* out, int* bad) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = a[i];
+  if (!fr_is_canonical(x)) { atomicExch(bad, 1); return; }
+  Fr y = Fr::zero();
+  if (op <= 2) {
+    y = b[i];
+    if (!fr_is_canonical(y)) { atomicExch(bad, 1); return; }
+  }
+  Fr r;
+  switch (op) {
+    case 0: r = x + y; break;
+    case 1: r = x - y; break;
+    case 2: r = (x.to_mont() * y.to_mont()).from_mont(); break;
+    case 3: r = x.to_mont().inverse().from_mont(); break;
+    default: r = x.neg(); break;
+  }
+  out[i] = r;
+}
+
+// canonical bytes -> Montgomery; flags non-canonical input
+__global__ void to_mont_kernel(const Fr* in, Fr* out, size_t n, int* bad) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = in[i];
+  if (!fr_is_canonical(x)) { atomicExch(bad, 1); return; }
+  out[i] = x.to_mont();
+}
+
+// out[i] = <row_i, z> for i < nc ; optionally out[nc + j] = z[j] for j < ni ; zero up to n
+__global__ void csr_matvec_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                                  const Fr* __restrict__ coeff, const Fr* __restrict__ z, uint64_t nc, uint64_t ni,
+                                  int append_instance, size_t n, Fr* __restrict__ out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr acc = Fr::zero();
+  if (i < nc) {
+    for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) acc = acc + coeff[k] * z[col[k]];
+  } else if (append_instance && i < nc + ni) {
+    acc = z[i - nc];
+  }
+  out[i] = acc;
+}
+
+// ab[i] = (a[i] * b[i] - c[i]) * zinv ; a is in Montgomery form, b and c canonical, zinv Montgomery -> canonical
+__global__ void qap_pointwise_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
+                                     int logn, size_t n, Fr* __restrict__ out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  __shared__ Fr zinv_sh;
+  if (threadIdx.x == 0) {
+    // (g^n - 1)^-1, g = 5
+    Fr gn = fr_base(FRB_GEN);
+    for (int k = 0; k < logn; k++) gn = gn.sqr();
+    zinv_sh = (gn - Fr::one()).inverse();
+  }
+  __syncthreads();
+  if (i >= n) return;
+  out[i] = (a[i] * b[i] - c[i]) * zinv_sh;
+}
+
+// scalars for the folded MSMs (all canonical):
+//   za[0..nv-1) = z[1..nv) ; za[nv-1] = 1 ; za[nv] = 1 ; za[nv+1] = r
+//   zl[0..nw) = z[ni..nv)  ; zl[nw] = -(r*s) mod r_mod
+__global__ void prove_tail_scalars_kernel(const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail) {
+  if (blockIdx.x || threadIdx.x) return;
+  Fr one = Fr::zero();
+  one.v[0] = 1;
+  za_tail[0] = one;
+  za_tail[1] = one;
+  za_tail[2] = *r;
+  Fr rs = (r->to_mont() * s->to_mont()).from_mont();
+  zl_tail[0] = rs.neg();
+}
+
+int ensure_wr(zkb_ctx* ctx, FrState* S) {
+  if (S->wr_fwd) return ZKB_OK;
+  const uint32_t cnt = 1u << (NTT_LRMAX - 1);
+  CUDA_TRY(ctx, cudaMalloc(&S->wr_fwd, cnt * sizeof(Fr)));
+  CUDA_TRY(ctx, cudaMalloc(&S->wr_inv, cnt * sizeof(Fr)));
+  unsigned long long mult = 1ull << (28 - NTT_LRMAX);
+  fr_pow_table_kernel<<<blocks_for(cnt, 64), 64, 0, ctx->stream>>>(S->wr_fwd, cnt, FRB_ROOT, mult, 1, 0, 0);
+  fr_pow_table_kernel<<<blocks_for(cnt, 64), 64, 0, ctx->stream>>>(S->wr_inv, cnt, FRB_ROOT_INV, mult, 1, 0, 0);
+  ctx->launches += 2;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
+  auto it = S->tables.find(logn);
+  if (it != S->tables.end()) {
+    *out = &it->second;
+    return ZKB_OK;
+  }
+  NttTables t;
+  int lb = (logn + 1) / 2;
+  uint32_t nlo = 1u << lb, nhi = 1u << (logn - lb);
+  size_t per = size_t(nlo) + nhi;
+  CUDA_TRY(ctx, cudaMalloc(&t.mem, (4 * per + 1) * sizeof(Fr)));
+  Fr* p = t.mem;
+  unsigned long long wmult = 1ull << (28 - logn);
+  auto gen = [&](Fr* lo, int base, unsigned long long mult, int sbase, unsigned long long sexp) {
+    Fr* hi = lo + nlo;
+    fr_pow_table_kernel<<<blocks_for(nlo, 64), 64, 0, ctx->stream>>>(lo, nlo, base, mult, 1, 0, 0);
+    fr_pow_table_kernel<<<blocks_for(nhi, 64), 64, 0, ctx->stream>>>(hi, nhi, base, mult, 1ull << lb, sbase, sexp);
+    ctx->launches += 2;
+    PowTable pt;
+    pt.lo = lo;
+    pt.hi = hi;
+    pt.lo_bits = lb;
+    pt.scaled = sexp ? 1 : 0;
+    return pt;
+  };
+  t.fwd = gen(p, FRB_ROOT, wmult, 0, 0);
+  t.inv = gen(p + per, FRB_ROOT_INV, wmult, 0, 0);
+  t.coset_pre = gen(p + 2 * per, FRB_GEN, 1, 0, 0);
+  t.coset_inv_post = gen(p + 3 * per, FRB_GEN_INV, 1, FRB_INV2, (unsigned long long)logn);  // n^-1 g^-k
+  Fr* ninv = p + 4 * per;
+  // single constant n^-1 = (1/2)^logn: i = 0 gives base^0 = 1, times sbase^sexp
+  fr_pow_table_kernel<<<1, 32, 0, ctx->stream>>>(ninv, 1, FRB_INV2, 1, 1, FRB_INV2, (unsigned long long)logn);
+  ctx->launches++;
+  t.ninv = ninv;
+  CUDA_TRY(ctx, cudaGetLastError());
+  auto ins = S->tables.emplace(logn, t);
+  *out = &ins.first->second;
+  return ZKB_OK;
+}
+
+template <int LR>
+void launch_pass(const NttPassArgs& a, cudaStream_t st) {
+  constexpr int TQ = 4;
+  constexpr int NE = (1 << LR) * TQ;
+  constexpr int NT = NE / 2 < 32 ? 32 : NE / 2;
+  size_t nq = size_t(1) << (a.logn - LR);
+  unsigned blocks = unsigned((nq + TQ - 1) / TQ);
+  ntt_pass_kernel<LR, TQ><<<blocks, NT, 0, st>>>(a);
+}
+
+}  // namespace
+
+void fr_state_free(zkb_ctx* ctx) {
+  if (!ctx->fr_state) return;
+  FrState* S = static_cast<FrState*>(ctx->fr_state);
+  if (S->wr_fwd) cudaFree(S->wr_fwd);
+  if (S->wr_inv) cudaFree(S->wr_inv);
+  for (auto& kv : S->tables) cudaFree(kv.second.mem);
+  delete S;
+  ctx->fr_state = nullptr;
+}
+
+int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+  size_t bytes = n * 32;
+  CUDA_TRY(ctx, ctx->tmp0.reserve(bytes));
+  CUDA_TRY(ctx, ctx->tmp1.reserve(bytes));
+  CUDA_TRY(ctx, ctx->tmp2.reserve(bytes));
+  ZKB_TRY(clear_flag(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (op <= 2) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp1.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  fr_field_op_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(op, ctx->tmp0.as<Fr>(), ctx->tmp1.as<Fr>(), n, ctx->tmp2.as<Fr>(), ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_flag(ctx, "zkb_field_op");
+}
+
+int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n) {
+  if (!n) return ZKB_OK;
+  to_mont_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(in, out, n, ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail) {
+  prove_tail_scalars_kernel<<<1, 32, 0, ctx->stream>>>(r, s, za_tail, zl_tail);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset) {
+  if (logn < 0 || logn > 28) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: log_n %d outside [0, 28]", logn);
+  size_t n = size_t(1) << logn;
+  if (logn == 0) {
+    // size-1 domain: identity (coset scale g^0 = 1, 1/n = 1)
+    if (in != out) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    return ZKB_OK;
+  }
+  FrState* S = state(ctx);
+  ZKB_TRY(ensure_wr(ctx, S));
+  NttTables* T = nullptr;
+  ZKB_TRY(ensure_ntt_tables(ctx, S, logn, &T));
+  int npass = (logn + NTT_LRMAX - 1) / NTT_LRMAX;
+  int base = logn / npass, extra = logn % npass;
+  Fr* scratch[2] = {nullptr, nullptr};
+  if (npass >= 2 || in == out) {
+    CUDA_TRY(ctx, ctx->tmp0.reserve(n * sizeof(Fr)));
+    scratch[0] = ctx->tmp0.as<Fr>();
+  }
+  if (npass >= 3) {
+    CUDA_TRY(ctx, ctx->tmp1.reserve(n * sizeof(Fr)));
+    scratch[1] = ctx->tmp1.as<Fr>();
+  }
+  const Fr* src = in;
+  int logm = logn;
+  PowTable ninv_tab;
+  ninv_tab.lo = T->ninv;
+  ninv_tab.hi = T->ninv;
+  ninv_tab.lo_bits = -1;  // constant
+  ProfScope ps(ctx, PH_NTT);
+  for (int p = 0; p < npass; p++) {
+    int lr = base + (p < extra ? 1 : 0);
+    bool last = (p == npass - 1);
+    Fr* dst;
+    if (last) {
+      dst = (npass == 1 && in == out) ? scratch[0] : out;
+    } else {
+      dst = scratch[p & 1];
+    }
+    NttPassArgs a;
+    a.in = src;
+    a.out = dst;
+    a.logn = logn;
+    a.logm = logm;
+    a.wr = inverse ? S->wr_inv : S->wr_fwd;
+    a.lrmax = NTT_LRMAX;
+    a.tw = inverse ? T->inv : T->fwd;
+    a.has_pre = (p == 0 && !inverse && coset) ? 1 : 0;
+    a.pre = T->coset_pre;
+    a.has_post = (last && inverse) ? 1 : 0;
+    a.post = coset ? T->coset_inv_post : ninv_tab;
+    switch (lr) {
+      case 1: launch_pass<1>(a, ctx->stream); break;
+      case 2: launch_pass<2>(a, ctx->stream); break;
+      case 3: launch_pass<3>(a, ctx->stream); break;
+      case 4: launch_pass<4>(a, ctx->stream); break;
+      case 5: launch_pass<5>(a, ctx->stream); break;
+      case 6: launch_pass<6>(a, ctx->stream); break;
+      case 7: launch_pass<7>(a, ctx->stream); break;
+      default: launch_pass<8>(a, ctx->stream); break;
+    }
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    src = dst;
+    logm -= lr;
+  }
+  if (npass == 1 && in == out) CUDA_TRY(ctx, cudaMemcpyAsync(out, scratch[0], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  return ZKB_OK;
+}
+
+// h (canonical, device, domain_size elements) <- witness_map_from_matrices(m, z canonical in w.z)
+int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
+                    int lg, const WitnessBufs& w, Fr* h_out) {
+  const size_t n = size_t(1) << lg;
+  const size_t nv = ni + nw;
+  cudaStream_t st = ctx->stream;
+  // a-chain in Montgomery form (so that a*b of a Montgomery and a canonical value is canonical)
+  ZKB_TRY(clear_flag(ctx));
+  {
+    ProfScope ps(ctx, PH_MATVEC);
+    ZKB_TRY(fr_to_mont(ctx, w.z, w.zm, nv));
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(A.row_ptr, A.col, A.coeff, w.zm, nc, ni, 1, n, w.wa);
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(B.row_ptr, B.col, B.coeff, w.z, nc, ni, 0, n, w.wb);
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(C.row_ptr, C.col, C.coeff, w.z, nc, ni, 0, n, w.wc);
+    ctx->launches += 3;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  Fr* chains[3] = {w.wa, w.wb, w.wc};
+  for (Fr* v : chains) {
+    ZKB_TRY(ntt_dev_impl(ctx, v, v, lg, 1, 0));  // domain.ifft_in_place
+    ZKB_TRY(ntt_dev_impl(ctx, v, v, lg, 0, 1));  // coset_domain.fft_in_place
+  }
+  {
+    ProfScope ps(ctx, PH_POINTWISE);
+    qap_pointwise_kernel<<<blocks_for(n, 128), 128, 0, st>>>(w.wa, w.wb, w.wc, lg, n, w.wa);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  ZKB_TRY(ntt_dev_impl(ctx, w.wa, h_out, lg, 1, 1));  // coset_domain.ifft_in_place
+  return ZKB_OK;
+}
+
+}  // namespace zkb

@@ -1,0 +1,355 @@
+// Group-generic kernels and host drivers (G1 over Fq, G2 over Fq2).  Included by g1.cu and g2.cu only; each
+// ends with explicit instantiations of the host templates declared in internal.h.
+#pragma once
+#include "internal.h"
+#include "msm.cuh"
+
+namespace zkb {
+
+template <class F>
+__device__ __forceinline__ bool fp_is_canonical(const F& a) {
+  F m = F::modulus();
+  for (int i = 7; i >= 0; i--) {
+    if (a.v[i] < m.v[i]) return true;
+    if (a.v[i] > m.v[i]) return false;
+  }
+  return false;  // equal to the modulus
+}
+
+template <class F> struct CurveB;
+template <> struct CurveB<Fq> {
+  static __device__ __forceinline__ Fq b() {  // 3 in Montgomery form
+    Fq r;
+    const uint32_t w[8] = {0x50ad28d7u, 0x7a17caa9u, 0xe15521b9u, 0x1f6ac17au, 0x696bd284u, 0x334bea4eu, 0xce179d8eu, 0x2a1f6744u};
+    for (int i = 0; i < 8; i++) r.v[i] = w[i];
+    return r;
+  }
+};
+template <> struct CurveB<Fq2> {
+  static __device__ __forceinline__ Fq2 b() {  // b' = 3/(9+u) in Montgomery form (oracle/bn254.py B_G2)
+    const uint32_t w[16] = {0x77b802a8u, 0x3bf938e3u, 0x3633535du, 0x020b1b27u, 0x49755260u, 0x26b7edf0u,
+                            0x4384a86du, 0x2514c632u, 0xd1dcff67u, 0x38e7ecccu, 0x93ce0d3eu, 0x65f0b37du,
+                            0x22ac00aau, 0xd749d0ddu, 0x4a688d4du, 0x0141b9ceu};
+    Fq2 r;
+    for (int i = 0; i < 8; i++) { r.c0.v[i] = w[i]; r.c1.v[i] = w[8 + i]; }
+    return r;
+  }
+};
+
+template <class F> struct FieldIO;
+template <> struct FieldIO<Fq> {
+  static constexpr int WORDS = 8;
+  static __device__ __forceinline__ bool load(const uint32_t* w, Fq& out) {
+    for (int i = 0; i < 8; i++) out.v[i] = w[i];
+    return fp_is_canonical(out);
+  }
+};
+template <> struct FieldIO<Fq2> {
+  static constexpr int WORDS = 16;
+  static __device__ __forceinline__ bool load(const uint32_t* w, Fq2& out) {
+    for (int i = 0; i < 8; i++) { out.c0.v[i] = w[i]; out.c1.v[i] = w[8 + i]; }
+    return fp_is_canonical(out.c0) && fp_is_canonical(out.c1);
+  }
+};
+
+// canonical affine bytes -> Montgomery affine, optional on-curve validation
+template <class F>
+__global__ void affine_import_kernel(const uint32_t* in, Affine<F>* out, size_t n, int validate, int* bad) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int W = FieldIO<F>::WORDS;
+  F x, y;
+  bool ok = FieldIO<F>::load(in + i * 2 * W, x);
+  ok = FieldIO<F>::load(in + i * 2 * W + W, y) && ok;
+  if (!ok) { atomicExch(bad, 1); return; }
+  Affine<F> p{x.to_mont(), y.to_mont()};
+  if (validate && !p.is_inf()) {
+    F lhs = p.y.sqr();
+    F rhs = p.x.sqr() * p.x + CurveB<F>::b();
+    if (lhs != rhs) { atomicExch(bad, 2); return; }
+  }
+  out[i] = p;
+}
+
+template <class F>
+__global__ void affine_export_kernel(const Affine<F>* in, uint32_t* out, size_t n) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_affine_canonical<F>(in[i], out + i * (sizeof(Affine<F>) / 4));
+}
+
+template <class F>
+__global__ void scalar_mul_kernel(const Affine<F>* pts, const uint32_t* scalars, size_t n, uint32_t* out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8];
+  for (int j = 0; j < 8; j++) k[j] = scalars[i * 8 + j];
+  XYZZ<F> r = XYZZ<F>::from_affine(pts[i]).mul_words(k);
+  store_affine_canonical<F>(r.to_affine(), out + i * (sizeof(Affine<F>) / 4));
+}
+
+template <class F>
+__global__ void point_sum_kernel(const Affine<F>* pts, size_t n, uint32_t* out) {
+  if (blockIdx.x || threadIdx.x) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (size_t i = 0; i < n; i++) acc.madd(pts[i]);
+  store_affine_canonical<F>(acc.to_affine(), out);
+}
+
+// table[w * 255 + d - 1] = d * 2^(8w) * G
+template <class F>
+__global__ void fixed_base_table_kernel(Affine<F> gen, Affine<F>* table) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 32 * 255) return;
+  int w = t / 255, d = t % 255 + 1;
+  uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  k[w / 4] = uint32_t(d) << (8 * (w % 4));
+  table[t] = XYZZ<F>::from_affine(gen).mul_words(k).to_affine();
+}
+
+template <class F>
+__global__ void fixed_base_mul_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ scalars,
+                                      size_t n, Affine<F>* __restrict__ out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int w = 0; w < 32; w++) {
+    uint32_t d = (scalars[i * 8 + w / 4] >> (8 * (w % 4))) & 0xffu;
+    if (d) acc.madd(table[w * 255 + d - 1]);
+  }
+  out[i] = acc.to_affine();
+}
+
+// ------------------------------------------------------------------------------------------- host drivers
+template <class F>
+int import_points(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, Affine<F>* dst) {
+  if (n == 0) return ZKB_OK;
+  size_t bytes = n * sizeof(Affine<F>);
+  CUDA_TRY(ctx, ctx->tmp0.reserve(bytes));
+  ZKB_TRY(clear_flag(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  affine_import_kernel<F><<<blocks_for(n, 128), 128, 0, ctx->stream>>>(ctx->tmp0.as<uint32_t>(), dst, n, validate, ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return check_flag(ctx, "point import");
+}
+
+template <class F>
+int scalar_mul_impl(zkb_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out) {
+  if (n == 0) return ZKB_OK;
+  size_t pbytes = n * sizeof(Affine<F>);
+  CUDA_TRY(ctx, ctx->tmp1.reserve(pbytes));
+  ZKB_TRY(import_points<F>(ctx, points, n, 1, ctx->tmp1.as<Affine<F>>()));
+  CUDA_TRY(ctx, ctx->scal.reserve(n * 32));
+  CUDA_TRY(ctx, ctx->tmp2.reserve(pbytes));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  scalar_mul_kernel<F><<<blocks_for(n, 64), 64, 0, ctx->stream>>>(ctx->tmp1.as<Affine<F>>(), ctx->scal.as<uint32_t>(), n, ctx->tmp2.as<uint32_t>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp2.p, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+template <class F>
+int point_sum_impl(zkb_ctx* ctx, const uint8_t* points, size_t n, uint8_t* out) {
+  size_t pbytes = n * sizeof(Affine<F>);
+  CUDA_TRY(ctx, ctx->tmp1.reserve(pbytes + sizeof(Affine<F>)));
+  ZKB_TRY(import_points<F>(ctx, points, n, 1, ctx->tmp1.as<Affine<F>>()));
+  CUDA_TRY(ctx, ctx->res.reserve(512));
+  point_sum_kernel<F><<<1, 32, 0, ctx->stream>>>(ctx->tmp1.as<Affine<F>>(), n, ctx->res.as<uint32_t>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+template <class F>
+int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out) {
+  using H = typename GroupOf<F>::Bases;
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || (!host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_load: bad argument");
+  *out = nullptr;
+  ZKB_TRY(set_device(ctx));
+  H* h = new (std::nothrow) H{ctx->device, nullptr, n};
+  if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_load: host allocation failed");
+  if (n) {
+    cudaError_t e = cudaMalloc(&h->p, n * sizeof(Affine<F>));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      delete h;
+      ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_load: cudaMalloc(%zu) failed: %s", n * sizeof(Affine<F>), cudaGetErrorString(e));
+    }
+    int s = import_points<F>(ctx, host, n, validate, h->p);
+    if (s != ZKB_OK) {
+      cudaFree(h->p);
+      delete h;
+      return s;
+    }
+  }
+  *out = h;
+  return ZKB_OK;
+}
+
+template <class F> struct Generator;
+template <> struct Generator<Fq> {
+  static void canonical(uint8_t* out) {  // (1, 2)
+    memset(out, 0, 64);
+    out[0] = 1;
+    out[32] = 2;
+  }
+  static void** slot(zkb_ctx* ctx) { return &ctx->g1_table; }
+};
+template <> struct Generator<Fq2> {
+  static void canonical(uint8_t* out) {  // ark-bn254 g2::G2_GENERATOR_{X,Y}
+    static const uint32_t w[32] = {
+        0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu,
+        0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u,
+        0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u,
+        0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
+    memcpy(out, w, 128);
+  }
+  static void** slot(zkb_ctx* ctx) { return &ctx->g2_table; }
+};
+
+template <class F>
+int ensure_fixed_table(zkb_ctx* ctx) {
+  void** slot = Generator<F>::slot(ctx);
+  if (*slot) return ZKB_OK;
+  Affine<F>* table = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&table, 32 * 255 * sizeof(Affine<F>)));
+  uint8_t gen[128];
+  Generator<F>::canonical(gen);
+  CUDA_TRY(ctx, ctx->tmp1.reserve(sizeof(Affine<F>)));
+  int s = import_points<F>(ctx, gen, 1, 1, ctx->tmp1.as<Affine<F>>());
+  if (s != ZKB_OK) {
+    cudaFree(table);
+    return s;
+  }
+  Affine<F> g;
+  CUDA_TRY(ctx, cudaMemcpy(&g, ctx->tmp1.p, sizeof(g), cudaMemcpyDeviceToHost));
+  fixed_base_table_kernel<F><<<blocks_for(32 * 255, 64), 64, 0, ctx->stream>>>(g, table);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  *slot = table;
+  return ZKB_OK;
+}
+
+template <class F>
+void fixed_table_free(zkb_ctx* ctx) {
+  void** slot = Generator<F>::slot(ctx);
+  if (*slot) cudaFree(*slot);
+  *slot = nullptr;
+}
+
+template <class F>
+int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename GroupOf<F>::Bases** out) {
+  using H = typename GroupOf<F>::Bases;
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || (!k_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_generate: bad argument");
+  *out = nullptr;
+  ZKB_TRY(set_device(ctx));
+  ZKB_TRY(ensure_fixed_table<F>(ctx));
+  H* h = new (std::nothrow) H{ctx->device, nullptr, n};
+  if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_generate: host allocation failed");
+  if (n) {
+    cudaError_t e = cudaMalloc(&h->p, n * sizeof(Affine<F>));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      delete h;
+      ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_generate: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    fixed_base_mul_kernel<F><<<blocks_for(n, 64), 64, 0, ctx->stream>>>(
+        static_cast<const Affine<F>*>(*Generator<F>::slot(ctx)), static_cast<const uint32_t*>(k_dev), n, h->p);
+    ctx->launches++;
+    cudaError_t e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) {
+      cudaFree(h->p);
+      delete h;
+      ZKB_FAIL(ctx, ZKB_ERR_CUDA, "fixed_base_mul_kernel: %s", cudaGetErrorString(e2));
+    }
+  }
+  *out = h;
+  return ZKB_OK;
+}
+
+template <class F>
+int bases_read_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* b, size_t offset, size_t n, uint8_t* out_host) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!b || !out_host || offset + n > b->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_read: bad range");
+  if (n == 0) return ZKB_OK;
+  ZKB_TRY(set_device(ctx));
+  CUDA_TRY(ctx, ctx->tmp0.reserve(n * sizeof(Affine<F>)));
+  affine_export_kernel<F><<<blocks_for(n, 128), 128, 0, ctx->stream>>>(b->p + offset, ctx->tmp0.as<uint32_t>(), n);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_host, ctx->tmp0.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+template <class F>
+void bases_free_impl(typename GroupOf<F>::Bases* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->p) cudaFree(b->p);
+  delete b;
+}
+
+template <class F>
+int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                 void* out_affine_dev, void* out_partial_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!bases || offset + n > bases->n || (!scalars_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
+  if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
+  ZKB_TRY(set_device(ctx));
+  cudaError_t e = msm_run<F>(ctx, bases->p + offset, static_cast<const uint32_t*>(scalars_dev), n,
+                             static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run: %s", cudaGetErrorString(e));
+  }
+  return ZKB_OK;
+}
+
+template <class F>
+int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+                  uint8_t* out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || (!scalars_host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: null argument");
+  ZKB_TRY(set_device(ctx));
+  CUDA_TRY(ctx, ctx->scal.reserve(n * 32 + 32));
+  CUDA_TRY(ctx, ctx->res.reserve(512));
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_TRY((msm_dev_impl<F>(ctx, bases, offset, ctx->scal.p, n, ctx->res.p, nullptr)));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+template <class F>
+int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!parts || k <= 0 || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_combine: bad argument");
+  ZKB_TRY(set_device(ctx));
+  msm_combine_kernel<F><<<1, 32, 0, ctx->stream>>>(static_cast<const XYZZ<F>*>(parts), k, static_cast<uint32_t*>(out));
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+#define ZKB_INSTANTIATE_GROUP(F)                                                                                            \
+  template int import_points<F>(zkb_ctx*, const uint8_t*, size_t, int, Affine<F>*);                                        \
+  template int bases_load_impl<F>(zkb_ctx*, const uint8_t*, size_t, int, GroupOf<F>::Bases**);                              \
+  template int bases_generate_impl<F>(zkb_ctx*, const void*, size_t, GroupOf<F>::Bases**);                                  \
+  template int bases_read_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, size_t, uint8_t*);                            \
+  template void bases_free_impl<F>(GroupOf<F>::Bases*);                                                                     \
+  template int scalar_mul_impl<F>(zkb_ctx*, const uint8_t*, const uint8_t*, size_t, uint8_t*);                              \
+  template int point_sum_impl<F>(zkb_ctx*, const uint8_t*, size_t, uint8_t*);                                               \
+  template int msm_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, void*, void*);              \
+  template int msm_host_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const uint8_t*, size_t, uint8_t*);              \
+  template int msm_combine_impl<F>(zkb_ctx*, const void*, int, void*);                                                      \
+  template void fixed_table_free<F>(zkb_ctx*);
+
+}  // namespace zkb

@@ -1,0 +1,216 @@
+// Internal (non-ABI) declarations shared by the translation units of libzkb200.so:
+//   zkb200.cu  context, profiling, R1CS / proving-key handles, prove orchestration, the extern "C" surface
+//   fr.cu      Fr kernels: NTT passes, CSR mat-vec, QAP pointwise, witness map
+//   g1.cu      G1 (Fq)  instantiation of group_impl.cuh: point import/export, MSM, fixed-base generation
+//   g2.cu      G2 (Fq2) instantiation of the same
+// Split so that nvcc compiles them in parallel (one TU took ~6 minutes).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/zkb200.h"
+#include "ec.cuh"
+
+namespace zkb {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- per-phase device timing (CUDA events on the context's stream) ------------------------------------
+enum Phase {
+  PH_G1_DIGITS = 0, PH_G1_SORT, PH_G1_ACCUM, PH_G1_REDUCE,
+  PH_G2_DIGITS, PH_G2_SORT, PH_G2_ACCUM, PH_G2_REDUCE,
+  PH_NTT, PH_MATVEC, PH_POINTWISE, PH_ASSEMBLE,
+  PH_COUNT
+};
+
+struct Prof {
+  bool on = false;
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> pending;
+  std::vector<cudaEvent_t> pool;
+  double ms[PH_COUNT] = {0};
+  unsigned long long cnt[PH_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
+}  // namespace zkb
+
+struct zkb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  unsigned long long launches = 0;
+  int msm_c = 0;
+  zkb::Prof prof;
+  zkb::DevBuf msm_ws;                             // MSM scratch (keys, sort space, buckets)
+  zkb::DevBuf scal, res, tmp0, tmp1, tmp2, flag;  // staging
+  zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzl, prs, ppts;  // prove scratch
+  void* fr_state = nullptr;                       // NTT tables, owned by fr.cu
+  void* g1_table = nullptr;                       // fixed-base tables, owned by g1.cu / g2.cu
+  void* g2_table = nullptr;
+};
+
+struct zkb_g1_bases {
+  int device;
+  zkb::Affine<zkb::Fq>* p;
+  size_t n;
+};
+struct zkb_g2_bases {
+  int device;
+  zkb::Affine<zkb::Fq2>* p;
+  size_t n;
+};
+
+namespace zkb {
+
+struct ProfScope {
+  zkb_ctx* ctx;
+  cudaEvent_t b = nullptr;
+  int phase;
+  ProfScope(zkb_ctx* c, int ph) : ctx(c), phase(ph) {
+    if (!c->prof.on) return;
+    cudaEvent_t a = c->prof.get();
+    b = c->prof.get();
+    cudaEventRecord(a, c->stream);
+    c->prof.pending.push_back({ph, a, b});
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, ctx->stream);
+  }
+};
+
+#define ZKB_FAIL(ctx, code, ...)           \
+  do {                                     \
+    char _b[512];                          \
+    snprintf(_b, sizeof(_b), __VA_ARGS__); \
+    (ctx)->err = _b;                       \
+    return (code);                         \
+  } while (0)
+
+#define CUDA_TRY(ctx, expr)                                                                                  \
+  do {                                                                                                       \
+    cudaError_t _e = (expr);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      cudaGetLastError();                                                                                    \
+      ZKB_FAIL(ctx, _e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "%s: %s (%s:%d)", #expr,   \
+               cudaGetErrorString(_e), __FILE__, __LINE__);                                                  \
+    }                                                                                                        \
+  } while (0)
+
+#define ZKB_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != ZKB_OK) return _s; \
+  } while (0)
+
+inline unsigned blocks_for(size_t n, int threads) { return unsigned((n + threads - 1) / threads); }
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// zkb200.cu
+int set_device(zkb_ctx* ctx);
+int clear_flag(zkb_ctx* ctx);
+int check_flag(zkb_ctx* ctx, const char* what);  // synchronises the stream
+
+template <class F> struct GroupOf;
+template <> struct GroupOf<Fq> { using Bases = zkb_g1_bases; static constexpr int PH0 = PH_G1_DIGITS; };
+template <> struct GroupOf<Fq2> { using Bases = zkb_g2_bases; static constexpr int PH0 = PH_G2_DIGITS; };
+
+// group_impl.cuh, instantiated for Fq in g1.cu and Fq2 in g2.cu
+template <class F> int import_points(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, Affine<F>* dst);
+template <class F> int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out);
+template <class F> int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename GroupOf<F>::Bases** out);
+template <class F> int bases_read_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* b, size_t offset, size_t n, uint8_t* out_host);
+template <class F> void bases_free_impl(typename GroupOf<F>::Bases* b);
+template <class F> int scalar_mul_impl(zkb_ctx* ctx, const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out);
+template <class F> int point_sum_impl(zkb_ctx* ctx, const uint8_t* points, size_t n, uint8_t* out);
+template <class F> int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
+                                    size_t n, void* out_affine_dev, void* out_partial_dev);
+template <class F> int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host,
+                                     size_t n, uint8_t* out);
+template <class F> int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out);
+template <class F> void fixed_table_free(zkb_ctx* ctx);
+
+// g1.cu
+int fq_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+// C = s*A + r*B1 + L + H (projective partial sums on device) -> canonical affine
+int prove_assemble_c(zkb_ctx* ctx, const void* pA, const void* pB1, const void* pL, const void* pH, const void* r_dev,
+                     const void* s_dev, void* out_c_dev);
+
+// fr.cu
+struct CsrDev {
+  uint64_t* row_ptr = nullptr;
+  uint32_t* col = nullptr;
+  Fr* coeff = nullptr;  // Montgomery
+  size_t nnz = 0;
+};
+int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
+int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);  // flags non-canonical input in ctx->flag
+int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset);
+void fr_state_free(zkb_ctx* ctx);
+struct WitnessBufs {
+  Fr *z, *zm, *wa, *wb, *wc;
+};
+int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
+                    int log_domain, const WitnessBufs& w, Fr* h_out);
+int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail);
+
+}  // namespace zkb
+
+struct zkb_r1cs {
+  int device;
+  uint64_t nc, ni, nw;
+  int log_domain;
+  zkb::CsrDev a, b, c;
+};
+
+struct zkb_pk {
+  int device;
+  size_t nv;  // num_instance + num_witness
+  size_t nw;  // l_query length
+  size_t nh;  // h_query length
+  // each query with the constant terms appended so that the whole coefficient is ONE msm:
+  //   a_ext  = a_query[1..]  || a_query[0]  || alpha_g1 || delta_g1      scalars: z[1..] || 1 || 1 || r
+  //   b1_ext = b_g1_query[1..] || b_g1_query[0] || beta_g1 || delta_g1   scalars: z[1..] || 1 || 1 || s
+  //   b2_ext = b_g2_query[1..] || b_g2_query[0] || beta_g2 || delta_g2   scalars: z[1..] || 1 || 1 || s
+  //   l_ext  = l_query || delta_g1                                       scalars: aux   || -(r s)
+  zkb_g1_bases *a_ext = nullptr, *b1_ext = nullptr, *l_ext = nullptr, *h = nullptr;
+  zkb_g2_bases* b2_ext = nullptr;
+};

@@ -23,7 +23,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
-#include "ec.cuh"
+#include "internal.h"
 
 namespace zkb {
 
@@ -69,7 +69,7 @@ static inline MsmPlan msm_make_plan(size_t n, int c_override, int sm_count, int 
 
 // ------------------------------------------------------------------------------------------- 1. digits
 // scalars: n x 32 bytes canonical little-endian (NOT Montgomery): what msm_bigint receives.
-__global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t nbuck,
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t nbuck,
                                   uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -282,28 +282,7 @@ __global__ void msm_combine_kernel(const XYZZ<F>* __restrict__ parts, int k, uin
   store_affine_canonical<F>(acc.to_affine(), out_affine);
 }
 
-// ------------------------------------------------------------------------------------------- workspace + driver
-struct MsmWorkspace {
-  void* buf = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (buf) cudaFree(buf);
-    buf = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc(&buf, bytes);
-    if (e == cudaSuccess) cap = bytes;
-    return e;
-  }
-  void release() {
-    if (buf) cudaFree(buf);
-    buf = nullptr;
-    cap = 0;
-  }
-};
-
-static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
+// ------------------------------------------------------------------------------------------- driver
 template <class F>
 struct MsmTraits;
 template <>
@@ -317,23 +296,20 @@ struct MsmTraits<Fq2> {
   static constexpr int THREADS_PER_SM = 256;
 };
 
-// Launch counter so bench.py can report how many of our kernels ran (cub launches are not counted).
-struct LaunchCounter {
-  unsigned long long n = 0;
-};
-
 // bases: device, Montgomery affine.  scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
 template <class F>
-cudaError_t msm_run(MsmWorkspace& ws, LaunchCounter& lc, int sm_count, int c_override, const Affine<F>* bases,
-                    const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz, uint32_t* out_affine, cudaStream_t st) {
+cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* bases, const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz,
+                    uint32_t* out_affine) {
   using T = MsmTraits<F>;
+  constexpr int PH0 = GroupOf<F>::PH0;
+  cudaStream_t st = ctx->stream;
   if (n == 0) {
     // empty sum = infinity = all-zero encoding
     if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(XYZZ<F>), st);
     if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>), st);
     return cudaGetLastError();
   }
-  MsmPlan p = msm_make_plan(n, c_override, sm_count, T::THREADS_PER_SM);
+  MsmPlan p = msm_make_plan(n, ctx->msm_c, ctx->sm_count, T::THREADS_PER_SM);
   size_t total = size_t(p.nwin) * n;
   if (total >= (size_t(1) << 31)) return cudaErrorInvalidValue;
   size_t nthreads = (total + p.chunk - 1) / p.chunk;
@@ -356,9 +332,9 @@ cudaError_t msm_run(MsmWorkspace& ws, LaunchCounter& lc, int sm_count, int c_ove
   size_t o_hk = take(nthreads * 4);
   size_t o_seg = take(size_t(p.nwin) * nseg * sizeof(XYZZ<F>));
   size_t o_win = take(size_t(p.nwin) * sizeof(XYZZ<F>));
-  cudaError_t e = ws.reserve(off);
+  cudaError_t e = ctx->msm_ws.reserve(off);
   if (e != cudaSuccess) return e;
-  char* base = static_cast<char*>(ws.buf);
+  char* base = static_cast<char*>(ctx->msm_ws.p);
   uint32_t *k0 = (uint32_t*)(base + o_k0), *v0 = (uint32_t*)(base + o_v0);
   uint32_t *k1 = (uint32_t*)(base + o_k1), *v1 = (uint32_t*)(base + o_v1);
   XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buck);
@@ -367,25 +343,34 @@ cudaError_t msm_run(MsmWorkspace& ws, LaunchCounter& lc, int sm_count, int c_ove
   XYZZ<F>* seg_out = (XYZZ<F>*)(base + o_seg);
   XYZZ<F>* win_out = (XYZZ<F>*)(base + o_win);
 
-  msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, p.c, p.nwin, p.nbuck, p.sentinel, k0, v0);
-  lc.n++;
-  e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, k0, k1, v0, v1, int(total), 0, p.key_bits, st);
-  if (e != cudaSuccess) return e;
+  {
+    ProfScope ps(ctx, PH0 + 0);
+    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, p.c, p.nwin, p.nbuck, p.sentinel, k0, v0);
+    ctx->launches++;
+  }
+  {
+    ProfScope ps(ctx, PH0 + 1);
+    e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, k0, k1, v0, v1, int(total), 0, p.key_bits, st);
+    if (e != cudaSuccess) return e;
+  }
   cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), st);
   cudaMemsetAsync(head_keys, 0xff, nthreads * 4, st);
-  unsigned acc_blocks = unsigned((nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
-  msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(
-      bases, k1, v1, total, p.chunk, p.sentinel, buckets, heads, head_keys);
-  lc.n++;
-  msm_heads_kernel<F><<<unsigned((nthreads + 63) / 64), 64, 0, st>>>(heads, head_keys, nthreads, p.sentinel, buckets);
-  lc.n++;
-  size_t rthreads = size_t(p.nwin) * nseg;
-  msm_reduce_kernel<F><<<unsigned((rthreads + 31) / 32), 32, 0, st>>>(buckets, p.nwin, p.nbuck, p.seg, seg_out);
-  lc.n++;
-  msm_window_sum_kernel<F, 64><<<p.nwin, 64, 0, st>>>(seg_out, nseg, win_out);
-  lc.n++;
-  msm_final_kernel<F><<<1, 32, 0, st>>>(win_out, p.nwin, p.c, out_xyzz, out_affine);
-  lc.n++;
+  {
+    ProfScope ps(ctx, PH0 + 2);
+    unsigned acc_blocks = unsigned((nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
+    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(
+        bases, k1, v1, total, p.chunk, p.sentinel, buckets, heads, head_keys);
+    ctx->launches++;
+  }
+  {
+    ProfScope ps(ctx, PH0 + 3);
+    msm_heads_kernel<F><<<unsigned((nthreads + 63) / 64), 64, 0, st>>>(heads, head_keys, nthreads, p.sentinel, buckets);
+    size_t rthreads = size_t(p.nwin) * nseg;
+    msm_reduce_kernel<F><<<unsigned((rthreads + 31) / 32), 32, 0, st>>>(buckets, p.nwin, p.nbuck, p.seg, seg_out);
+    msm_window_sum_kernel<F, 64><<<p.nwin, 64, 0, st>>>(seg_out, nseg, win_out);
+    msm_final_kernel<F><<<1, 32, 0, st>>>(win_out, p.nwin, p.c, out_xyzz, out_affine);
+    ctx->launches += 4;
+  }
   return cudaGetLastError();
 }
 
