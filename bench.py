@@ -224,7 +224,9 @@ def run_ours(args):
     assert n % world == 0
     shard = n // world
     lo = rank * shard
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library: CUDA events recorded on it see our kernels
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx = zelana_b200.Context(local, stream=stream.cuda_stream)
 
     # ---- synthetic workload (identical for every N): bases = proving-key points resident in HBM
