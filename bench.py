@@ -90,7 +90,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def start(self):
         if self.nv is not None:
@@ -220,10 +220,9 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from zelana_b200.multi import GpuMsmEngine, ShardedMsm, shard_range
     n = 1 << args.log_n
-    assert n % world == 0
-    shard = n // world
-    lo = rank * shard
+    lo, shard = shard_range(n, world, rank)
     # a real (non-default) stream shared by torch and the library: CUDA events recorded on it see our kernels
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -235,17 +234,15 @@ def run_ours(args):
     ctx.synchronize()
     del k
     scal = rand_fr_range(torch, SEED_SCALARS, lo, shard, dev)
-    part = torch.zeros(128, dtype=torch.uint8, device=dev)
-    parts = torch.zeros(world * 128, dtype=torch.uint8, device=dev)
-    out_aff = torch.zeros(64, dtype=torch.uint8, device=dev)
+    engine = GpuMsmEngine(ctx, bases, group=1)
+    sharded = ShardedMsm(engine)          # partial MSM per rank -> NCCL all-gather of world x 128 B -> point sum
+    out_aff = engine._out
 
     def step_device():
         if world == 1:
             ctx.msm_g1_dev(bases, scal, shard, out_affine_dev=out_aff)
         else:
-            ctx.msm_g1_dev(bases, scal, shard, out_partial_dev=part)
-            dist.all_gather_into_tensor(parts, part)
-            ctx.msm_g1_combine(parts, world, out_aff)
+            sharded.run(scal, shard)
 
     def barrier():
         if world > 1:

@@ -54,7 +54,8 @@ void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(zkb_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
 unsigned long long zkb_launch_count(zkb_ctx* ctx);
-/* force the MSM window width (0 = automatic) -- benchmarking/tests only */
+/* force the MSM window width c in [2, 23] (0 = automatic) for bases loaded AFTER this call: the width is fixed when a
+ * bases handle builds its window tables 2^(c j) P.  Benchmarking/tests only. */
 int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c);
 
 /* ---- per-phase device timing (replaces the reference's only timer, `proving_time_ms = start.elapsed()`,

@@ -108,20 +108,24 @@ def test_msm_g1_matches_oracle(ctx, n):
         assert out == bn.g1_to_raw(bn.G1.msm_naive(pts, sc))
 
 
-@pytest.mark.parametrize("c", [2, 5, 8, 11, 13, 16])
+@pytest.mark.parametrize("c", [2, 5, 8, 11, 13, 16, 19, 22, 23])
 def test_msm_g1_every_window_width(ctx, c):
+    """The window width is fixed when the bases build their tables 2^(c j) P: force it, then load."""
     rnd = random.Random(200 + c)
-    n = 3000
+    n = 3000 if c > 2 else 600
     pts, ks = arithmetic_bases(bn.G1, bn.G1_GEN, n, 17, 1)
     sc = [rnd.randrange(R) for _ in range(n)]
     sc[:6] = [0, 1, R - 1, (1 << 253), R >> 1, 2]
-    bases = ctx.g1_bases(g1_raw(pts))
     ctx.set_msm_window(c)
     try:
-        out = ctx.msm_g1(bases, fr_bytes(sc))
+        bases = ctx.g1_bases(g1_raw(pts))
     finally:
         ctx.set_msm_window(0)
+    out = ctx.msm_g1(bases, fr_bytes(sc))
     assert out == bn.g1_to_raw(_expected_msm(bn.G1, bn.G1_GEN, ks, sc))
+    # a sub-range on the same tables
+    out = ctx.msm_g1(bases, fr_bytes(sc[100:500]), offset=100)
+    assert out == bn.g1_to_raw(_expected_msm(bn.G1, bn.G1_GEN, ks[100:500], sc[100:500]))
 
 
 def test_msm_g1_witness_like_and_degenerate(ctx):

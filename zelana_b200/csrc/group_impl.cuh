@@ -165,6 +165,40 @@ int point_sum_impl(zkb_ctx* ctx, const uint8_t* points, size_t n, uint8_t* out) 
   return ZKB_OK;
 }
 
+// Allocates the handle and the whole window table (nwin x n points); the bases go to its first n entries.
+// The window width is fixed here, from n (or the context's override), and kept for every MSM on this handle.
+template <class F>
+int bases_alloc(zkb_ctx* ctx, size_t n, typename GroupOf<F>::Bases** out) {
+  using H = typename GroupOf<F>::Bases;
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+  int c = ctx->msm_c > 0 ? ctx->msm_c : msm_choose_window(n, sizeof(Affine<F>), free_b / 2);
+  if (c <= 0 || double(msm_windows_for(c)) * double(n) >= 2147483648.0)
+    ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: no window width fits %zu points in %zu MB of free device memory", n, free_b >> 20);
+  int nwin = msm_windows_for(c);
+  H* h = new (std::nothrow) H{ctx->device, nullptr, n, c, nwin};
+  if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: host allocation failed");
+  if (n) {
+    cudaError_t e = cudaMalloc(&h->p, size_t(nwin) * n * sizeof(Affine<F>));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      delete h;
+      ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: cudaMalloc(%zu) failed: %s", size_t(nwin) * n * sizeof(Affine<F>), cudaGetErrorString(e));
+    }
+  }
+  *out = h;
+  return ZKB_OK;
+}
+
+template <class F>
+int build_window_tables(zkb_ctx* ctx, typename GroupOf<F>::Bases* h) {
+  if (h->n == 0 || h->nwin <= 1) return ZKB_OK;
+  window_tables_kernel<F><<<blocks_for(h->n, 128), 128, 0, ctx->stream>>>(h->p, h->n, h->c, h->nwin);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
 template <class F>
 int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out) {
   using H = typename GroupOf<F>::Bases;
@@ -172,16 +206,11 @@ int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, t
   if (!out || (!host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_load: bad argument");
   *out = nullptr;
   ZKB_TRY(set_device(ctx));
-  H* h = new (std::nothrow) H{ctx->device, nullptr, n};
-  if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_load: host allocation failed");
+  H* h = nullptr;
+  ZKB_TRY(bases_alloc<F>(ctx, n, &h));
   if (n) {
-    cudaError_t e = cudaMalloc(&h->p, n * sizeof(Affine<F>));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      delete h;
-      ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_load: cudaMalloc(%zu) failed: %s", n * sizeof(Affine<F>), cudaGetErrorString(e));
-    }
     int s = import_points<F>(ctx, host, n, validate, h->p);
+    if (s == ZKB_OK) s = build_window_tables<F>(ctx, h);
     if (s != ZKB_OK) {
       cudaFree(h->p);
       delete h;
@@ -251,15 +280,9 @@ int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename Grou
   *out = nullptr;
   ZKB_TRY(set_device(ctx));
   ZKB_TRY(ensure_fixed_table<F>(ctx));
-  H* h = new (std::nothrow) H{ctx->device, nullptr, n};
-  if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_generate: host allocation failed");
+  H* h = nullptr;
+  ZKB_TRY(bases_alloc<F>(ctx, n, &h));
   if (n) {
-    cudaError_t e = cudaMalloc(&h->p, n * sizeof(Affine<F>));
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      delete h;
-      ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_generate: cudaMalloc failed: %s", cudaGetErrorString(e));
-    }
     fixed_base_mul_kernel<F><<<blocks_for(n, 64), 64, 0, ctx->stream>>>(
         static_cast<const Affine<F>*>(*Generator<F>::slot(ctx)), static_cast<const uint32_t*>(k_dev), n, h->p);
     ctx->launches++;
@@ -268,6 +291,12 @@ int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename Grou
       cudaFree(h->p);
       delete h;
       ZKB_FAIL(ctx, ZKB_ERR_CUDA, "fixed_base_mul_kernel: %s", cudaGetErrorString(e2));
+    }
+    int s = build_window_tables<F>(ctx, h);
+    if (s != ZKB_OK) {
+      cudaFree(h->p);
+      delete h;
+      return s;
     }
   }
   *out = h;
@@ -304,7 +333,7 @@ int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t o
   if (!bases || offset + n > bases->n || (!scalars_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
   if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
   ZKB_TRY(set_device(ctx));
-  cudaError_t e = msm_run<F>(ctx, bases->p + offset, static_cast<const uint32_t*>(scalars_dev), n,
+  cudaError_t e = msm_run<F>(ctx, bases->p, bases->n, bases->c, bases->nwin, offset, static_cast<const uint32_t*>(scalars_dev), n,
                              static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
   if (e != cudaSuccess) {
     cudaGetLastError();

@@ -88,15 +88,18 @@ struct zkb_ctx {
   void* g2_table = nullptr;
 };
 
+// Device-resident bases with their window tables: p[j * n + i] = 2^(c j) * base_i, j < nwin (msm.cuh).
 struct zkb_g1_bases {
   int device;
   zkb::Affine<zkb::Fq>* p;
   size_t n;
+  int c, nwin;
 };
 struct zkb_g2_bases {
   int device;
   zkb::Affine<zkb::Fq2>* p;
   size_t n;
+  int c, nwin;
 };
 
 namespace zkb {

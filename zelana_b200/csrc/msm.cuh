@@ -4,21 +4,29 @@
 // sites of ark-groth16's create_proof_with_assignment (h_query, l_query, a_query, b_g1_query in G1 and
 // b_g2_query in G2), which the reference enters from core/src/sequencer/settlement/prover.rs:408.
 //
+// B200 design.  A 254-bit Montgomery product costs ~570 scheduler cycles per warp whatever the occupancy
+// (profiles/r01_kbench_field_mul_variants.txt), so the lever is the NUMBER of point additions:
+//   * the bases are a proving key: they stay in HBM across proofs, so at load time every base P gets the
+//     table 2^(c j) P, j < nwin (window_tables_kernel).  Digit j of a scalar then selects a point of table j
+//     and ALL windows share one set of 2^(c-1) buckets: no per-window bucket reduction, no Horner doublings,
+//     and c can grow to 22 (12 windows instead of 16) because the 2^21 buckets are reduced once, not 16 times.
+//   * one (key, value) entry per (point, window): key = |digit| - 1, value = table index | sign << 31;
+//     zero digits get the sentinel key and sort last.
 // Pipeline (all on one stream, no host synchronisation):
-//   1. msm_digits_kernel     canonical 254-bit scalars -> signed c-bit digits; one (key, value) entry
-//                            per (point, window): key = window * 2^(c-1) + |digit| - 1, value =
-//                            point index | sign << 31; zero digits get the sentinel key (sorts last).
-//   2. cub::DeviceRadixSort  entries by key (bucket id).  Library sort, HBM-bound, a few % of the run.
-//   3. msm_accumulate_kernel the hot loop.  The sorted entry list is cut into equal chunks, one per
-//                            thread, so load balance does not depend on the scalar distribution.  A
-//                            thread sums the runs in its chunk with XYZZ mixed additions (8M+2S) on
-//                            gathered 64-byte affine bases; a run that starts inside the chunk is
-//                            owned by the thread and stored to its bucket, the run that was already
-//                            open at the chunk start goes to a per-thread "head" slot.
-//   4. msm_heads_kernel      folds head partial sums into their buckets (one leader per bucket id).
-//   5. msm_reduce_kernel     per window, per segment of buckets: running-sum sum_b (b+1) B_b.
-//   6. msm_window_sum_kernel tree-sum of segment results per window.
-//   7. msm_final_kernel      Horner over windows (c doublings each), XYZZ -> affine -> canonical bytes.
+//   1. msm_digits_kernel        canonical scalars -> signed c-bit digits -> entries.
+//   2. cub::DeviceRadixSort     entries by bucket.  Library sort, HBM-bound.
+//   3. msm_accumulate_kernel    the hot loop.  The sorted entry list is cut into equal chunks, one per thread, so
+//                               load balance does not depend on the scalar distribution.  A thread sums the runs
+//                               in its chunk with XYZZ mixed additions (8M+2S) on gathered 64-byte affine points;
+//                               a run that starts inside the chunk is stored to its bucket, the run that was
+//                               already open at the chunk start goes to a per-thread "head" slot.
+//   4. msm_heads_level_kernel   heads are again a sorted list: the same chunking, 16 per thread, level after level
+//                               (a bucket holding millions of entries -- scalars 0/1 of real witnesses -- is
+//                               folded in log_16 steps), then msm_heads_kernel for the last <= 256.
+//   5. msm_bucket_seg_kernel    sum_b (b+1) B_b by segments of S buckets: W_s = local weighted sum, T_s = plain
+//                               sum; sum_b (b+1) B_b = sum_s W_s + S * R(T[1..]) -> recursion on the T array.
+//      msm_sum_kernel           tree sums of the W arrays.
+//   6. msm_final_kernel         Horner over the levels (log2 S doublings each), XYZZ -> affine -> canonical bytes.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -27,50 +35,75 @@
 
 namespace zkb {
 
-struct MsmPlan {
-  int c;            // window bits
-  int nwin;         // number of windows
-  uint32_t nbuck;   // buckets per window = 2^(c-1)
-  uint32_t sentinel;  // key of a zero digit
-  int key_bits;
-  int chunk;        // sorted entries per accumulate thread
-  int seg;          // buckets per reduce thread
-};
-
 static inline int ilog2_ceil(size_t n) {
   int l = 0;
   while ((size_t(1) << l) < n) l++;
   return l;
 }
 
-static inline MsmPlan msm_make_plan(size_t n, int c_override, int sm_count, int threads_per_sm) {
-  MsmPlan p;
-  int lg = ilog2_ceil(n < 2 ? 2 : n);
-  int c = lg - 3;
-  if (c < 6) c = 6;
-  if (c > 16) c = 16;
-  if (c_override > 0) c = c_override;
-  p.c = c;
-  p.nwin = (255 + c - 1) / c;
-  p.nbuck = 1u << (c - 1);
-  p.sentinel = uint32_t(p.nwin) * p.nbuck;
-  p.key_bits = ilog2_ceil(size_t(p.sentinel) + 1);
-  // aim for ~8 waves of accumulate threads, chunks of at least 32 and at most 1024 entries
-  size_t total = size_t(p.nwin) * n;
-  size_t resident = size_t(sm_count) * threads_per_sm;
-  size_t chunk = (total + resident * 8 - 1) / (resident * 8);
-  if (chunk < 32) chunk = 32;
-  if (chunk > 1024) chunk = 1024;
-  p.chunk = int((chunk + 3) & ~size_t(3));
-  p.seg = p.nbuck >= 4096 ? 16 : (p.nbuck >= 256 ? 8 : 4);
-  if (uint32_t(p.seg) > p.nbuck) p.seg = int(p.nbuck);
-  return p;
+constexpr int MSM_SEG_LOG = 5;   // bucket reduction: segments of 32
+constexpr int MSM_MAX_LEVELS = 8;
+
+static inline int msm_windows_for(int c) { return (255 + c - 1) / c; }  // nwin * c >= 255: the top digit absorbs the carry
+
+// Window width for a table of n bases: minimise  nwin(c) * n  (mixed additions)  +  2.8 * 2^(c-1)  (two full additions per
+// bucket, ~1.4 mixed additions each), subject to the table fitting `mem_budget` bytes and nwin * n < 2^31 entries.
+static inline int msm_choose_window(size_t n, size_t point_bytes, size_t mem_budget) {
+  if (n == 0) return 8;
+  int best = 0;
+  double best_cost = 0;
+  for (int c = 4; c <= 23; c++) {
+    int nwin = msm_windows_for(c);
+    if (double(nwin) * double(n) >= 2147483648.0) continue;
+    if (double(nwin) * double(n) * double(point_bytes) > double(mem_budget)) continue;
+    double cost = double(nwin) * double(n) + 2.8 * double(size_t(1) << (c - 1)) + 4096.0 * nwin;
+    if (!best || cost < best_cost) {
+      best = c;
+      best_cost = cost;
+    }
+  }
+  return best;  // 0: no admissible width
+}
+
+// ------------------------------------------------------------------------------------------- window tables
+template <class F>
+__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p) {
+  // 64 B (G1) / 128 B (G2) as 16-byte vector loads through the read-only path
+  Affine<F> r;
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+  uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+  for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++) dst[k] = __ldg(src + k);
+  return r;
+}
+
+template <class F>
+__device__ __forceinline__ void store_affine(Affine<F>* p, const Affine<F>& v) {
+  const uint4* src = reinterpret_cast<const uint4*>(&v);
+  uint4* dst = reinterpret_cast<uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++) dst[k] = src[k];
+}
+
+// table[j * n + i] = 2^(c j) * table[i] for 1 <= j < nwin (table[0..n) holds the bases).  One thread per base.
+template <class F>
+__global__ void __launch_bounds__(128) window_tables_kernel(Affine<F>* table, size_t n, int c, int nwin) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> a = table[i];
+  for (int j = 1; j < nwin; j++) {
+    XYZZ<F> cur = XYZZ<F>::dbl_affine(a);
+    for (int k = 1; k < c; k++) cur = cur.dbl();
+    a = cur.to_affine();
+    store_affine(table + size_t(j) * n + i, a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- 1. digits
 // scalars: n x 32 bytes canonical little-endian (NOT Montgomery): what msm_bigint receives.
-static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t nbuck,
-                                  uint32_t sentinel, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// entry (w, i): keys[w * n + i] = |digit| - 1 (sentinel for 0), vals[w * n + i] = (w * table_n + first + i) | neg << 31
+static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t sentinel,
+                                         size_t table_n, size_t first, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * 8);
@@ -93,23 +126,12 @@ static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, s
       carry = 0;
     }
     size_t o = size_t(w) * n + i;
-    keys[o] = v ? (uint32_t(w) * nbuck + v - 1u) : sentinel;
-    vals[o] = uint32_t(i) | (neg << 31);
+    keys[o] = v ? (v - 1u) : sentinel;
+    vals[o] = uint32_t(size_t(w) * table_n + first + i) | (neg << 31);
   }
 }
 
 // ------------------------------------------------------------------------------------------- 3. accumulate
-template <class F>
-__device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p) {
-  // 64 B (G1) / 128 B (G2) as 16-byte vector loads through the read-only path
-  Affine<F> r;
-  const uint4* src = reinterpret_cast<const uint4*>(p);
-  uint4* dst = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-  for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++) dst[k] = __ldg(src + k);
-  return r;
-}
-
 template <class F>
 __device__ __forceinline__ void store_xyzz(XYZZ<F>* p, const XYZZ<F>& v) {
   const uint4* src = reinterpret_cast<const uint4*>(&v);
@@ -130,7 +152,7 @@ __device__ __forceinline__ XYZZ<F> load_xyzz(const XYZZ<F>* p) {
 
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ keys,
+msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ keys,
                       const uint32_t* __restrict__ vals, size_t total, int chunk, uint32_t sentinel,
                       XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
   size_t t = size_t(blockIdx.x) * THREADS + threadIdx.x;
@@ -146,9 +168,9 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
   }
   bool first_run = true;
   XYZZ<F> acc = XYZZ<F>::inf();
-  // software pipeline: the base of entry j+1 is in flight while entry j is added
+  // software pipeline: the point of entry j+1 is in flight while entry j is added
   uint32_t v = vals[start];
-  Affine<F> nxt = load_affine(bases + (v & 0x7fffffffu));
+  Affine<F> nxt = load_affine(table + (v & 0x7fffffffu));
   uint32_t nxt_neg = v >> 31;
   for (size_t j = start; j < end; j++) {
     Affine<F> pt = nxt;
@@ -159,7 +181,7 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
       k = keys[j + 1];
       if (k < sentinel) {
         uint32_t v2 = vals[j + 1];
-        nxt = load_affine(bases + (v2 & 0x7fffffffu));
+        nxt = load_affine(table + (v2 & 0x7fffffffu));
         nxt_neg = v2 >> 31;
         more = true;
       }
@@ -183,6 +205,44 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ bases, const uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------- 4. heads
+// One level: the (sorted) head list is chunked again, CHUNK per thread.  A run that starts inside the chunk is complete
+// up to the next level's heads and is ADDED to its bucket; the run open at the chunk start becomes a head of the next level.
+template <class F, int CHUNK>
+__global__ void __launch_bounds__(64)
+msm_heads_level_kernel(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, size_t count, uint32_t sentinel,
+                       XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ out, uint32_t* __restrict__ out_keys) {
+  size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  size_t start = t * CHUNK;
+  if (start >= count) return;
+  size_t end = start + CHUNK < count ? start + CHUNK : count;
+  uint32_t cur = in_keys[start];
+  if (cur >= sentinel) {
+    out_keys[t] = sentinel;
+    return;
+  }
+  bool first_run = true;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (size_t j = start; j < end; j++) {
+    acc.add(load_xyzz(in + j));
+    uint32_t k = (j + 1 < end) ? in_keys[j + 1] : sentinel;
+    if (k != cur) {
+      if (first_run) {
+        store_xyzz(out + t, acc);
+        out_keys[t] = cur;
+        first_run = false;
+      } else {
+        XYZZ<F> b = load_xyzz(buckets + cur);
+        b.add(acc);
+        store_xyzz(buckets + cur, b);
+      }
+      acc = XYZZ<F>::inf();
+      cur = k;
+      if (k >= sentinel) break;
+    }
+  }
+}
+
+// last level: one leader per distinct key folds its heads into the bucket
 template <class F>
 __global__ void msm_heads_kernel(const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ head_keys,
                                  size_t nthreads, uint32_t sentinel, XYZZ<F>* __restrict__ buckets) {
@@ -198,35 +258,32 @@ __global__ void msm_heads_kernel(const XYZZ<F>* __restrict__ heads, const uint32
   store_xyzz(buckets + k, b);
 }
 
-// ------------------------------------------------------------------------------------------- 5. reduce
-// thread (w, s): R = sum_{b in segment} (b+1) * B[w][b] = running-sum part + b0 * (segment sum)
+// ------------------------------------------------------------------------------------------- 5. bucket reduction
+// R(A) = sum_{b < m} (b + 1) A[b].  Segment s of S = 2^MSM_SEG_LOG entries: W[s] = sum_i (i + 1) A[sS + i], T[s] = sum_i A[sS + i];
+// then R(A) = sum_s W[s] + S * R(T[1..]).
 template <class F>
-__global__ void msm_reduce_kernel(const XYZZ<F>* __restrict__ buckets, int nwin, uint32_t nbuck, int seg,
-                                  XYZZ<F>* __restrict__ seg_out) {
-  uint32_t nseg = nbuck / seg;
-  size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= size_t(nwin) * nseg) return;
-  uint32_t w = uint32_t(t / nseg), s = uint32_t(t % nseg);
-  uint32_t b0 = s * seg;
-  const XYZZ<F>* B = buckets + size_t(w) * nbuck + b0;
-  XYZZ<F> run = XYZZ<F>::inf(), tot = XYZZ<F>::inf();
-  for (int b = seg - 1; b >= 0; b--) {
-    run.add(load_xyzz(B + b));
-    tot.add(run);
+__global__ void __launch_bounds__(64)
+msm_bucket_seg_kernel(const XYZZ<F>* __restrict__ in, size_t m, XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ T, size_t nseg) {
+  size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  constexpr int S = 1 << MSM_SEG_LOG;
+  size_t b0 = s * S;
+  XYZZ<F> run = XYZZ<F>::inf(), w = XYZZ<F>::inf();
+  for (int i = S - 1; i >= 0; i--) {
+    if (b0 + i < m) run.add(load_xyzz(in + b0 + i));
+    w.add(run);
   }
-  if (b0) tot.add(run.mul_u32(b0));
-  store_xyzz(seg_out + t, tot);
+  store_xyzz(W + s, w);
+  store_xyzz(T + s, run);
 }
 
-// ------------------------------------------------------------------------------------------- 6. window sums
-// one block per window: tree reduction of nseg partial sums through shared memory
-template <class F, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg_out, uint32_t nseg, XYZZ<F>* __restrict__ win_out) {
+// out[blockIdx.x] = sum of in[blockIdx.x * PER .. +PER) (tree in shared memory); called until one point is left
+template <class F, int THREADS, int PER>
+__global__ void __launch_bounds__(THREADS) msm_sum_kernel(const XYZZ<F>* __restrict__ in, size_t count, XYZZ<F>* __restrict__ out) {
   __shared__ XYZZ<F> sh[THREADS];
-  const XYZZ<F>* in = seg_out + size_t(blockIdx.x) * nseg;
+  size_t base = size_t(blockIdx.x) * PER;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t i = threadIdx.x; i < nseg; i += THREADS) acc.add(load_xyzz(in + i));
+  for (size_t i = base + threadIdx.x; i < base + PER && i < count; i += THREADS) acc.add(load_xyzz(in + i));
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int stride = THREADS / 2; stride > 0; stride >>= 1) {
@@ -237,10 +294,10 @@ msm_window_sum_kernel(const XYZZ<F>* __restrict__ seg_out, uint32_t nseg, XYZZ<F
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_xyzz(win_out + blockIdx.x, sh[0]);
+  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
 }
 
-// ------------------------------------------------------------------------------------------- 7. final
+// ------------------------------------------------------------------------------------------- 6. final
 template <class F>
 __device__ void store_affine_canonical(const Affine<F>& a, uint32_t* out);
 template <>
@@ -259,15 +316,16 @@ __device__ inline void store_affine_canonical<Fq2>(const Affine<Fq2>& a, uint32_
     for (int i = 0; i < 8; i++) out[8 * k + i] = v[k].v[i];
 }
 
-// Horner over windows; writes the XYZZ sum (Montgomery, for multi-GPU combining) and the canonical affine bytes.
+// level_sums[l] = sum_s W^(l)[s];  result = sum_l S^l level_sums[l]  (Horner, MSM_SEG_LOG doublings per level).
+// Writes the XYZZ sum (Montgomery, for multi-GPU combining) and the canonical affine bytes.
 template <class F>
-__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ win, int nwin, int c, XYZZ<F>* __restrict__ out_xyzz,
+__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ level_sums, int nlevels, XYZZ<F>* __restrict__ out_xyzz,
                                  uint32_t* __restrict__ out_affine) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<F> acc = load_xyzz(win + (nwin - 1));
-  for (int w = nwin - 2; w >= 0; w--) {
-    for (int k = 0; k < c; k++) acc = acc.dbl();
-    acc.add(load_xyzz(win + w));
+  XYZZ<F> acc = load_xyzz(level_sums + (nlevels - 1));
+  for (int l = nlevels - 2; l >= 0; l--) {
+    for (int k = 0; k < MSM_SEG_LOG; k++) acc = acc.dbl();
+    acc.add(load_xyzz(level_sums + l));
   }
   if (out_xyzz) store_xyzz(out_xyzz, acc);
   if (out_affine) store_affine_canonical<F>(acc.to_affine(), out_affine);
@@ -296,29 +354,47 @@ struct MsmTraits<Fq2> {
   static constexpr int THREADS_PER_SM = 256;
 };
 
-// bases: device, Montgomery affine.  scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
+// table: device, Montgomery affine, nwin x table_n (window-major).  The MSM covers bases [first, first + n).
+// scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
 template <class F>
-cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* bases, const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz,
-                    uint32_t* out_affine) {
+cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
+                    const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
   using T = MsmTraits<F>;
+  using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
+  constexpr int HCHUNK = 16;
+  constexpr int S = 1 << MSM_SEG_LOG;
   cudaStream_t st = ctx->stream;
   if (n == 0) {
     // empty sum = infinity = all-zero encoding
-    if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(XYZZ<F>), st);
+    if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(P), st);
     if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>), st);
     return cudaGetLastError();
   }
-  MsmPlan p = msm_make_plan(n, ctx->msm_c, ctx->sm_count, T::THREADS_PER_SM);
-  size_t total = size_t(p.nwin) * n;
-  if (total >= (size_t(1) << 31)) return cudaErrorInvalidValue;
-  size_t nthreads = (total + p.chunk - 1) / p.chunk;
-  size_t nbuckets = size_t(p.nwin) * p.nbuck;
-  uint32_t nseg = p.nbuck / p.seg;
+  const uint32_t nbuck = 1u << (c - 1);
+  const uint32_t sentinel = nbuck;
+  const int key_bits = ilog2_ceil(size_t(nbuck) + 1);
+  const size_t total = size_t(nwin) * n;
+  if (total >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
+  // ~8 waves of accumulate threads, chunks of 32..1024 entries
+  size_t resident = size_t(ctx->sm_count) * T::THREADS_PER_SM;
+  size_t chunk = (total + resident * 8 - 1) / (resident * 8);
+  chunk = chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk);
+  chunk = (chunk + 3) & ~size_t(3);
+  const size_t nthreads = (total + chunk - 1) / chunk;
+
+  // bucket-reduction levels: m_0 = nbuck, m_{l+1} = ceil(m_l / S) - 1 (the T array without its first entry)
+  size_t lvl_m[MSM_MAX_LEVELS], lvl_seg[MSM_MAX_LEVELS];
+  int nlevels = 0;
+  for (size_t m = nbuck; m > 0 && nlevels < MSM_MAX_LEVELS; nlevels++) {
+    lvl_m[nlevels] = m;
+    lvl_seg[nlevels] = (m + S - 1) / S;
+    m = lvl_seg[nlevels] - 1;
+  }
 
   size_t sort_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, int(total), 0, p.key_bits, st);
+                                  (uint32_t*)nullptr, int(total), 0, key_bits, st);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -327,49 +403,89 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* bases, const uint32_t* scalar
   };
   size_t o_k0 = take(total * 4), o_v0 = take(total * 4), o_k1 = take(total * 4), o_v1 = take(total * 4);
   size_t o_tmp = take(sort_tmp);
-  size_t o_buck = take(nbuckets * sizeof(XYZZ<F>));
-  size_t o_heads = take(nthreads * sizeof(XYZZ<F>));
-  size_t o_hk = take(nthreads * 4);
-  size_t o_seg = take(size_t(p.nwin) * nseg * sizeof(XYZZ<F>));
-  size_t o_win = take(size_t(p.nwin) * sizeof(XYZZ<F>));
+  size_t o_buck = take(size_t(nbuck) * sizeof(P));
+  size_t nh1 = (nthreads + HCHUNK - 1) / HCHUNK;
+  size_t o_h0 = take(nthreads * sizeof(P)), o_hk0 = take(nthreads * 4);
+  size_t o_h1 = take(nh1 * sizeof(P)), o_hk1 = take(nh1 * 4);
+  size_t o_W = take(lvl_seg[0] * sizeof(P));           // W of the current level (reused)
+  size_t o_T0 = take(lvl_seg[0] * sizeof(P));          // T arrays ping-pong
+  size_t o_T1 = take((nlevels > 1 ? lvl_seg[1] : 1) * sizeof(P));
+  size_t nsum = lvl_seg[0] / 256 + 2;
+  size_t o_sum = take(nsum * sizeof(P) * 2);           // msm_sum_kernel ping-pong
+  size_t o_lvl = take(MSM_MAX_LEVELS * sizeof(P));
   cudaError_t e = ctx->msm_ws.reserve(off);
   if (e != cudaSuccess) return e;
   char* base = static_cast<char*>(ctx->msm_ws.p);
   uint32_t *k0 = (uint32_t*)(base + o_k0), *v0 = (uint32_t*)(base + o_v0);
   uint32_t *k1 = (uint32_t*)(base + o_k1), *v1 = (uint32_t*)(base + o_v1);
-  XYZZ<F>* buckets = (XYZZ<F>*)(base + o_buck);
-  XYZZ<F>* heads = (XYZZ<F>*)(base + o_heads);
-  uint32_t* head_keys = (uint32_t*)(base + o_hk);
-  XYZZ<F>* seg_out = (XYZZ<F>*)(base + o_seg);
-  XYZZ<F>* win_out = (XYZZ<F>*)(base + o_win);
+  P* buckets = (P*)(base + o_buck);
+  P* hp[2] = {(P*)(base + o_h0), (P*)(base + o_h1)};
+  uint32_t* hk[2] = {(uint32_t*)(base + o_hk0), (uint32_t*)(base + o_hk1)};
+  P* W = (P*)(base + o_W);
+  P* Tb[2] = {(P*)(base + o_T0), (P*)(base + o_T1)};
+  P* sum_buf[2] = {(P*)(base + o_sum), (P*)(base + o_sum) + nsum};
+  P* lvl_sums = (P*)(base + o_lvl);
 
   {
     ProfScope ps(ctx, PH0 + 0);
-    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, p.c, p.nwin, p.nbuck, p.sentinel, k0, v0);
+    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, sentinel, table_n, first, k0, v0);
     ctx->launches++;
   }
   {
     ProfScope ps(ctx, PH0 + 1);
-    e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, k0, k1, v0, v1, int(total), 0, p.key_bits, st);
+    e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, k0, k1, v0, v1, int(total), 0, key_bits, st);
     if (e != cudaSuccess) return e;
   }
-  cudaMemsetAsync(buckets, 0, nbuckets * sizeof(XYZZ<F>), st);
-  cudaMemsetAsync(head_keys, 0xff, nthreads * 4, st);
+  cudaMemsetAsync(buckets, 0, size_t(nbuck) * sizeof(P), st);
+  cudaMemsetAsync(hk[0], 0xff, nthreads * 4, st);
   {
     ProfScope ps(ctx, PH0 + 2);
     unsigned acc_blocks = unsigned((nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
-    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(
-        bases, k1, v1, total, p.chunk, p.sentinel, buckets, heads, head_keys);
+    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(table, k1, v1, total, int(chunk), sentinel,
+                                                                                  buckets, hp[0], hk[0]);
     ctx->launches++;
   }
   {
     ProfScope ps(ctx, PH0 + 3);
-    msm_heads_kernel<F><<<unsigned((nthreads + 63) / 64), 64, 0, st>>>(heads, head_keys, nthreads, p.sentinel, buckets);
-    size_t rthreads = size_t(p.nwin) * nseg;
-    msm_reduce_kernel<F><<<unsigned((rthreads + 31) / 32), 32, 0, st>>>(buckets, p.nwin, p.nbuck, p.seg, seg_out);
-    msm_window_sum_kernel<F, 64><<<p.nwin, 64, 0, st>>>(seg_out, nseg, win_out);
-    msm_final_kernel<F><<<1, 32, 0, st>>>(win_out, p.nwin, p.c, out_xyzz, out_affine);
-    ctx->launches += 4;
+    // heads, level by level (a level with <= 256 entries goes to the leader kernel)
+    size_t count = nthreads;
+    int cur = 0;
+    while (count > 256) {
+      size_t nt = (count + HCHUNK - 1) / HCHUNK;
+      cudaMemsetAsync(hk[cur ^ 1], 0xff, nt * 4, st);
+      msm_heads_level_kernel<F, HCHUNK><<<unsigned((nt + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets,
+                                                                                hp[cur ^ 1], hk[cur ^ 1]);
+      ctx->launches++;
+      count = nt;
+      cur ^= 1;
+    }
+    msm_heads_kernel<F><<<unsigned((count + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets);
+    ctx->launches++;
+    // bucket reduction, level by level
+    const P* in = buckets;
+    for (int l = 0; l < nlevels; l++) {
+      size_t nseg = lvl_seg[l];
+      P* Tout = Tb[l & 1];
+      msm_bucket_seg_kernel<F><<<unsigned((nseg + 63) / 64), 64, 0, st>>>(in, lvl_m[l], W, Tout, nseg);
+      ctx->launches++;
+      // sum of W[0..nseg) -> lvl_sums[l]
+      const P* src = W;
+      size_t cnt = nseg;
+      int sb = 0;
+      while (true) {
+        size_t nb = (cnt + 255) / 256;
+        P* dst = nb == 1 ? lvl_sums + l : sum_buf[sb];
+        msm_sum_kernel<F, 64, 256><<<unsigned(nb), 64, 0, st>>>(src, cnt, dst);
+        ctx->launches++;
+        if (nb == 1) break;
+        src = dst;
+        cnt = nb;
+        sb ^= 1;
+      }
+      in = Tout + 1;  // next level works on T[1..]
+    }
+    msm_final_kernel<F><<<1, 32, 0, st>>>(lvl_sums, nlevels, out_xyzz, out_affine);
+    ctx->launches++;
   }
   return cudaGetLastError();
 }

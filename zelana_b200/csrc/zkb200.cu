@@ -108,7 +108,7 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
 extern "C" const char* zkb_last_error(zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" unsigned long long zkb_launch_count(zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c) {
-  if (!ctx || c < 0 || c > 16 || (c > 0 && c < 2)) return ZKB_ERR_INVALID_ARG;
+  if (!ctx || c < 0 || c > 23 || (c > 0 && c < 2)) return ZKB_ERR_INVALID_ARG;
   ctx->msm_c = c;
   return ZKB_OK;
 }
