@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="0 = choose for ~10-30 s of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="msm_g1", choices=["msm_g1", "ntt", "msm_sweep"],
+                    help="msm_g1 = the contract line (default); ntt / msm_sweep = BASELINE.json configs 3 / 2 as extra sweeps")
+    ap.add_argument("--logs", default="", help="comma-separated log2 sizes for the sweeps")
     return ap.parse_args()
 
 
@@ -370,10 +373,86 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def measured_hbm_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_sweeps(args):
+    """BASELINE.json configs 2 and 3 as sweeps (not the contract line): one JSON line with a row per size."""
+    import numpy as np
+    import torch
+    import zelana_b200
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = zelana_b200.Context(0, stream=stream.cuda_stream)
+    peak_int = max(ctx.int32_peak(0)[0], ctx.int32_peak(1)[0])
+    hbm, hbm_src = measured_hbm_gbs()
+    rows = []
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / args.steps
+
+    if args.workload == "ntt":
+        logs = [int(x) for x in args.logs.split(",")] if args.logs else [16, 18, 20, 22, 24, 26]
+        for lg in logs:
+            n = 1 << lg
+            a = rand_fr_range(torch, 0xA77E0000 + lg, 0, n, dev)
+            b = torch.empty_like(a)
+            row = {"log_n": lg}
+            for name, inv, coset in (("ntt", False, False), ("intt", True, False), ("coset_ntt", False, True),
+                                     ("coset_intt", True, True)):
+                ms = timed(lambda: ctx.ntt_dev(a, b, lg, inverse=inv, coset=coset))
+                row[name + "_ms"] = ms
+                row[name + "_hbm_frac"] = 64.0 * n / (ms * 1e-3) / (hbm * 1e9)
+                row[name + "_int32_frac"] = (n / 2) * lg * 136.0 / (ms * 1e-3) / peak_int
+            rows.append(row)
+            del a, b
+        line = {"workload": "bn254_fr_ntt_sweep", "unit": "ms", "rows": rows, "steps": args.steps, "warmup": args.warmup,
+                "hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src, "int32_peak_tmul32": peak_int / 1e12,
+                "algorithmic_bytes": "64*n per transform", "algorithmic_mul32": "(n/2)*log2(n)*136 per transform",
+                "l2": "inputs larger than L2 from 2^22 up; smaller sizes are L2-resident and say so by exceeding the HBM roofline"}
+    else:
+        logs = [int(x) for x in args.logs.split(",")] if args.logs else [16, 18, 20, 22, 24, 26]
+        for lg in logs:
+            n = 1 << lg
+            k = rand_fr_range(torch, SEED_BASES, 0, n, dev)
+            bases = ctx.g1_bases_generate(k, n)
+            ctx.synchronize()
+            del k
+            sc = rand_fr_range(torch, SEED_SCALARS + lg, 0, n, dev)
+            out = torch.zeros(64, dtype=torch.uint8, device=dev)
+            ms = timed(lambda: ctx.msm_g1_dev(bases, sc, n, out_affine_dev=out))
+            rows.append({"log_n": lg, "ms": ms, "points_per_s": n / (ms * 1e-3),
+                         "int32_frac_normalised": MUL32_PER_POINT * n / (ms * 1e-3) / peak_int})
+            bases.free()
+            del sc
+        line = {"workload": "bn254_g1_msm_sweep", "unit": "ms", "rows": rows, "steps": args.steps, "warmup": args.warmup,
+                "int32_peak_tmul32": peak_int / 1e12, "normalisation": "21760 mul32 per point (SURVEY 8d)"}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "msm_g1":
+        run_sweeps(args)
     else:
         run_ours(args)
 

@@ -23,10 +23,11 @@
 //   4. msm_heads_level_kernel   heads are again a sorted list: the same chunking, 16 per thread, level after level
 //                               (a bucket holding millions of entries -- scalars 0/1 of real witnesses -- is
 //                               folded in log_16 steps), then msm_heads_kernel for the last <= 256.
-//   5. msm_bucket_seg_kernel    sum_b (b+1) B_b by segments of S buckets: W_s = local weighted sum, T_s = plain
-//                               sum; sum_b (b+1) B_b = sum_s W_s + S * R(T[1..]) -> recursion on the T array.
-//      msm_sum_kernel           tree sums of the W arrays.
-//   6. msm_final_kernel         Horner over the levels (log2 S doublings each), XYZZ -> affine -> canonical bytes.
+//   5. msm_bucket_seg_kernel    sum_b (b+1) B_b by segments of S = 32 buckets: W_s = local weighted sum, T_s = plain
+//                               sum; sum_b (b+1) B_b = sum_s W_s + S * sum_s s T_s.
+//      msm_plane_sum_kernel     sum_s s T_s = sum_y 2^y (sum of T_s over s with bit y set): log-depth tree sums per
+//                               bit plane (plus one plane for sum_s W_s), no scalar multiplications, no long chains.
+//   6. msm_final_kernel         Horner over the planes, XYZZ -> affine -> canonical bytes.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -42,7 +43,6 @@ static inline int ilog2_ceil(size_t n) {
 }
 
 constexpr int MSM_SEG_LOG = 5;   // bucket reduction: segments of 32
-constexpr int MSM_MAX_LEVELS = 8;
 
 static inline int msm_windows_for(int c) { return (255 + c - 1) / c; }  // nwin * c >= 255: the top digit absorbs the carry
 
@@ -277,13 +277,40 @@ msm_bucket_seg_kernel(const XYZZ<F>* __restrict__ in, size_t m, XYZZ<F>* __restr
   store_xyzz(T + s, run);
 }
 
-// out[blockIdx.x] = sum of in[blockIdx.x * PER .. +PER) (tree in shared memory); called until one point is left
+// Bit-plane sums.  Plane y < nplanes: out[y * gridDim.x + bx] = sum of T[s] over the block's 256 indices s with bit y of s
+// set; plane y == nplanes: the plain sum of W[s].  With P_y the plane totals,  sum_s s T[s] = sum_y 2^y P_y.
 template <class F, int THREADS, int PER>
-__global__ void __launch_bounds__(THREADS) msm_sum_kernel(const XYZZ<F>* __restrict__ in, size_t count, XYZZ<F>* __restrict__ out) {
+__global__ void __launch_bounds__(THREADS)
+msm_plane_sum_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ W, size_t count, int nplanes,
+                     XYZZ<F>* __restrict__ out) {
   __shared__ XYZZ<F> sh[THREADS];
+  const int y = blockIdx.y;
+  const XYZZ<F>* src = (y == nplanes) ? W : T;
   size_t base = size_t(blockIdx.x) * PER;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (size_t i = base + threadIdx.x; i < base + PER && i < count; i += THREADS) acc.add(load_xyzz(in + i));
+  for (size_t i = base + threadIdx.x; i < base + PER && i < count; i += THREADS)
+    if (y == nplanes || ((i >> y) & 1)) acc.add(load_xyzz(src + i));
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int stride = THREADS / 2; stride > 0; stride >>= 1) {
+    if (int(threadIdx.x) < stride) {
+      XYZZ<F> a = sh[threadIdx.x];
+      a.add(sh[threadIdx.x + stride]);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) store_xyzz(out + size_t(y) * gridDim.x + blockIdx.x, sh[0]);
+}
+
+// second stage: out[y] = sum of in[y * per_plane .. +per_plane)
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+msm_plane_fold_kernel(const XYZZ<F>* __restrict__ in, size_t per_plane, XYZZ<F>* __restrict__ out) {
+  __shared__ XYZZ<F> sh[THREADS];
+  const XYZZ<F>* src = in + size_t(blockIdx.x) * per_plane;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (size_t i = threadIdx.x; i < per_plane; i += THREADS) acc.add(load_xyzz(src + i));
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int stride = THREADS / 2; stride > 0; stride >>= 1) {
@@ -316,17 +343,20 @@ __device__ inline void store_affine_canonical<Fq2>(const Affine<Fq2>& a, uint32_
     for (int i = 0; i < 8; i++) out[8 * k + i] = v[k].v[i];
 }
 
-// level_sums[l] = sum_s W^(l)[s];  result = sum_l S^l level_sums[l]  (Horner, MSM_SEG_LOG doublings per level).
+// planes[y] = P_y for y < nplanes, planes[nplanes] = sum_s W[s]:
+//   result = sum_b (b+1) B_b = sum_s W[s] + S * sum_y 2^y P_y   (Horner over the planes, then MSM_SEG_LOG doublings).
 // Writes the XYZZ sum (Montgomery, for multi-GPU combining) and the canonical affine bytes.
 template <class F>
-__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ level_sums, int nlevels, XYZZ<F>* __restrict__ out_xyzz,
+__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ planes, int nplanes, XYZZ<F>* __restrict__ out_xyzz,
                                  uint32_t* __restrict__ out_affine) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<F> acc = load_xyzz(level_sums + (nlevels - 1));
-  for (int l = nlevels - 2; l >= 0; l--) {
-    for (int k = 0; k < MSM_SEG_LOG; k++) acc = acc.dbl();
-    acc.add(load_xyzz(level_sums + l));
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int y = nplanes - 1; y >= 0; y--) {
+    acc = acc.dbl();
+    acc.add(load_xyzz(planes + y));
   }
+  for (int k = 0; k < MSM_SEG_LOG; k++) acc = acc.dbl();
+  acc.add(load_xyzz(planes + nplanes));
   if (out_xyzz) store_xyzz(out_xyzz, acc);
   if (out_affine) store_affine_canonical<F>(acc.to_affine(), out_affine);
 }
@@ -383,14 +413,10 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   chunk = (chunk + 3) & ~size_t(3);
   const size_t nthreads = (total + chunk - 1) / chunk;
 
-  // bucket-reduction levels: m_0 = nbuck, m_{l+1} = ceil(m_l / S) - 1 (the T array without its first entry)
-  size_t lvl_m[MSM_MAX_LEVELS], lvl_seg[MSM_MAX_LEVELS];
-  int nlevels = 0;
-  for (size_t m = nbuck; m > 0 && nlevels < MSM_MAX_LEVELS; nlevels++) {
-    lvl_m[nlevels] = m;
-    lvl_seg[nlevels] = (m + S - 1) / S;
-    m = lvl_seg[nlevels] - 1;
-  }
+  // bucket reduction: segments of S buckets, then bit-plane sums over the nseg segment totals
+  const size_t nseg = (size_t(nbuck) + S - 1) / S;
+  const int nplanes = nseg > 1 ? ilog2_ceil(nseg) : 0;
+  const size_t plane_blocks = (nseg + 255) / 256;
 
   size_t sort_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -407,12 +433,10 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   size_t nh1 = (nthreads + HCHUNK - 1) / HCHUNK;
   size_t o_h0 = take(nthreads * sizeof(P)), o_hk0 = take(nthreads * 4);
   size_t o_h1 = take(nh1 * sizeof(P)), o_hk1 = take(nh1 * 4);
-  size_t o_W = take(lvl_seg[0] * sizeof(P));           // W of the current level (reused)
-  size_t o_T0 = take(lvl_seg[0] * sizeof(P));          // T arrays ping-pong
-  size_t o_T1 = take((nlevels > 1 ? lvl_seg[1] : 1) * sizeof(P));
-  size_t nsum = lvl_seg[0] / 256 + 2;
-  size_t o_sum = take(nsum * sizeof(P) * 2);           // msm_sum_kernel ping-pong
-  size_t o_lvl = take(MSM_MAX_LEVELS * sizeof(P));
+  size_t o_W = take(nseg * sizeof(P));
+  size_t o_T = take(nseg * sizeof(P));
+  size_t o_part = take(size_t(nplanes + 1) * plane_blocks * sizeof(P));
+  size_t o_planes = take(size_t(nplanes + 1) * sizeof(P));
   cudaError_t e = ctx->msm_ws.reserve(off);
   if (e != cudaSuccess) return e;
   char* base = static_cast<char*>(ctx->msm_ws.p);
@@ -422,9 +446,9 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   P* hp[2] = {(P*)(base + o_h0), (P*)(base + o_h1)};
   uint32_t* hk[2] = {(uint32_t*)(base + o_hk0), (uint32_t*)(base + o_hk1)};
   P* W = (P*)(base + o_W);
-  P* Tb[2] = {(P*)(base + o_T0), (P*)(base + o_T1)};
-  P* sum_buf[2] = {(P*)(base + o_sum), (P*)(base + o_sum) + nsum};
-  P* lvl_sums = (P*)(base + o_lvl);
+  P* Tt = (P*)(base + o_T);
+  P* part = (P*)(base + o_part);
+  P* planes = (P*)(base + o_planes);
 
   {
     ProfScope ps(ctx, PH0 + 0);
@@ -461,31 +485,12 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
     }
     msm_heads_kernel<F><<<unsigned((count + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets);
     ctx->launches++;
-    // bucket reduction, level by level
-    const P* in = buckets;
-    for (int l = 0; l < nlevels; l++) {
-      size_t nseg = lvl_seg[l];
-      P* Tout = Tb[l & 1];
-      msm_bucket_seg_kernel<F><<<unsigned((nseg + 63) / 64), 64, 0, st>>>(in, lvl_m[l], W, Tout, nseg);
-      ctx->launches++;
-      // sum of W[0..nseg) -> lvl_sums[l]
-      const P* src = W;
-      size_t cnt = nseg;
-      int sb = 0;
-      while (true) {
-        size_t nb = (cnt + 255) / 256;
-        P* dst = nb == 1 ? lvl_sums + l : sum_buf[sb];
-        msm_sum_kernel<F, 64, 256><<<unsigned(nb), 64, 0, st>>>(src, cnt, dst);
-        ctx->launches++;
-        if (nb == 1) break;
-        src = dst;
-        cnt = nb;
-        sb ^= 1;
-      }
-      in = Tout + 1;  // next level works on T[1..]
-    }
-    msm_final_kernel<F><<<1, 32, 0, st>>>(lvl_sums, nlevels, out_xyzz, out_affine);
-    ctx->launches++;
+    // bucket reduction
+    msm_bucket_seg_kernel<F><<<unsigned((nseg + 63) / 64), 64, 0, st>>>(buckets, nbuck, W, Tt, nseg);
+    msm_plane_sum_kernel<F, 64, 256><<<dim3(unsigned(plane_blocks), unsigned(nplanes + 1)), 64, 0, st>>>(Tt, W, nseg, nplanes, part);
+    msm_plane_fold_kernel<F, 64><<<unsigned(nplanes + 1), 64, 0, st>>>(part, plane_blocks, planes);
+    msm_final_kernel<F><<<1, 32, 0, st>>>(planes, nplanes, out_xyzz, out_affine);
+    ctx->launches += 4;
   }
   return cudaGetLastError();
 }
