@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="0 = choose for ~10-30 s of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="msm_g1", choices=["msm_g1", "ntt", "msm_sweep"],
+    ap.add_argument("--workload", default="msm_g1", choices=["msm_g1", "ntt", "msm_sweep", "prove"],
                     help="msm_g1 = the contract line (default); ntt / msm_sweep = BASELINE.json configs 3 / 2 as extra sweeps")
     ap.add_argument("--logs", default="", help="comma-separated log2 sizes for the sweeps")
     return ap.parse_args()
@@ -173,7 +173,10 @@ def run_reference(args):
         return
     import numpy as np
     from oracle import cpu as orc
-    threads = orc.max_threads()
+    try:
+        threads = len(os.sched_getaffinity(0))      # torchrun exports OMP_NUM_THREADS=1: ask the OS, not OpenMP
+    except AttributeError:
+        threads = os.cpu_count() or 1
     total = args.steps + args.warmup
     lg = args.cpu_sample_log_n or choose_cpu_sample(orc, np, threads, budget_s=150.0 / max(total, 1))
     lg = min(lg, args.log_n)
@@ -200,7 +203,7 @@ def run_reference(args):
         "e2e": {"value": ms_full, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -366,11 +369,133 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": launches, "roofline": roof, "phase_ms_per_step": phase_ms,
             "cpu_baseline": cpu, "clocks": clocks, "result": result_hex,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     bases.free()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def mimc_r1cs_numpy(np, num_perm, seed, rounds=91):
+    """Synthetic R1CS shaped like forge/circuits/zelana_lib/src/poseidon.nr:30-46 (MiMC-7: 4 constraints per round), built
+    with numpy index arithmetic (tests/helpers.py::mimc7_chain is the small, loop-built twin checked against the oracle).
+    -> (num_instance, num_witness, (A, B, C) CSR triples, z as uint8[nv, 32])."""
+    import random
+    R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+    rnd = random.Random(seed)
+    consts = [rnd.randrange(R) for _ in range(rounds)]
+    x0, key = rnd.randrange(R), rnd.randrange(R)
+    G = num_perm * rounds
+    nv = 4 + 4 * G
+    z = np.zeros((nv, 32), dtype=np.uint8)
+
+    def put(i, v):
+        z[i] = np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint8)
+
+    put(0, 1); put(2, x0); put(3, key)
+    x = x0
+    for g in range(G):
+        t = (x + key + consts[g % rounds]) % R
+        t2 = t * t % R
+        t4 = t2 * t2 % R
+        t6 = t4 * t2 % R
+        x = t6 * t % R
+        b = 4 + 4 * g
+        put(b, t2); put(b + 1, t4); put(b + 2, t6); put(b + 3, x)
+    put(1, x)
+    g = np.arange(G, dtype=np.int64)
+    base = 4 + 4 * g
+    xi = np.where(g == 0, 2, base - 1)
+    one = np.zeros(32, dtype=np.uint8); one[0] = 1
+    cbytes = np.stack([np.frombuffer(c.to_bytes(32, "little"), dtype=np.uint8) for c in consts])[g % rounds]   # [G, 32]
+    ki = np.full(G, 3, dtype=np.int64)
+    zero = np.zeros(G, dtype=np.int64)
+
+    def assemble(cols_per_row, coeff_per_row, last_col):
+        """cols_per_row: list (4 rows of the group) of lists of column arrays; coeff: same shape, None = 1."""
+        counts = [len(r) for r in cols_per_row]
+        per_group = sum(counts)
+        col = np.empty((G, per_group), dtype=np.uint32)
+        co = np.zeros((G, per_group, 32), dtype=np.uint8)
+        k = 0
+        for r, cs in zip(cols_per_row, coeff_per_row):
+            for c_arr, cf in zip(r, cs):
+                col[:, k] = c_arr
+                if cf is None:
+                    co[:, k, 0] = 1
+                else:
+                    co[:, k] = cf
+                k += 1
+        rp_group = np.concatenate([[0], np.cumsum(counts)])[:4]
+        row_ptr = (np.arange(G, dtype=np.uint64)[:, None] * per_group + rp_group[None, :].astype(np.uint64)).reshape(-1)
+        row_ptr = np.concatenate([row_ptr, np.array([G * per_group, G * per_group + 1], dtype=np.uint64)])
+        col = np.concatenate([col.reshape(-1), np.array([last_col], dtype=np.uint32)])
+        co = np.concatenate([co.reshape(-1, 32), one[None, :]]).reshape(-1)
+        return row_ptr, col, co
+
+    lin, linc = [xi, ki, zero], [None, None, cbytes]
+    A = assemble([lin, [base], [base + 1], [base + 2]], [linc, [None], [None], [None]], int(4 + 4 * (G - 1) + 3))
+    B = assemble([lin, [base], [base], lin], [linc, [None], [None], linc], 0)
+    Cm = assemble([[base], [base + 1], [base + 2], [base + 3]], [[None]] * 4, 1)
+    return 2, nv - 2, (A, B, Cm), z
+
+
+def run_prove(args):
+    """BASELINE.json config 4: full Groth16 prove (7 NTTs + 4 G1 MSMs + 1 G2 MSM) of a forge-sized synthetic circuit."""
+    import numpy as np
+    import torch
+    import zelana_b200
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = zelana_b200.Context(0, stream=stream.cuda_stream)
+    lg = args.log_n if args.log_n != 24 else 21
+    num_perm = ((1 << lg) - 8) // (4 * 91)
+    t0 = time.perf_counter()
+    ni, nw, (A, B, Cm), z = mimc_r1cs_numpy(np, num_perm, seed=0xF0 + lg)
+    t_build = time.perf_counter() - t0
+    m = ctx.r1cs(ni, nw, A, B, Cm)
+    assert m.log_domain == lg, (m.log_domain, lg)
+    nv, n = ni + nw, 1 << lg
+    k_len = max(nv + 2, n - 1) + 8
+    k = rand_fr_range(torch, SEED_BASES, 0, k_len, dev)
+    t0 = time.perf_counter()
+    pk = ctx.proving_key_synthetic(nv, nw, n - 1, k, k_len)
+    ctx.synchronize()
+    t_key = time.perf_counter() - t0
+    del k
+    zt = torch.from_numpy(z).pin_memory()
+    z_np = zt.numpy().reshape(-1)
+    r = (123456789).to_bytes(32, "little")
+    sb = (987654321).to_bytes(32, "little")
+    for _ in range(args.warmup):
+        proof = ctx.prove(pk, m, z_np, r, sb)
+    ctx.profile(True)
+    ctx.profile_reset()
+    l0 = ctx.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        proof = ctx.prove(pk, m, z_np, r, sb)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    phases = {k2: v[0] / args.steps for k2, v in ctx.profile_read().items()}
+    line = {"workload": "groth16_prove_synthetic_mimc", "metric": "Groth16 proofs/s (forge-sized synthetic circuit)",
+            "value": 1e3 / ms, "unit": "proofs/s", "ms_per_proof": ms, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "config": {"log_domain": lg, "constraints": int(len(A[0]) - 1), "variables": int(nv), "mimc_permutations": num_perm,
+                       "key": "synthetic ([k_i]G points; timing-equivalent, proofs do not verify)",
+                       "through": "zkb_prove with host z (H2D inside the timed region)"},
+            "phase_ms_per_proof": phases, "gpu_launches": (ctx.launch_count() - l0) // max(args.steps, 1), "clocks": clocks,
+            "setup_s": {"r1cs_build_host": t_build, "key_generate_and_tables_gpu": t_key},
+            "proof_a": bytes(proof[0]).hex()[:32]}
+    emit(line)
+    ctx.close()
 
 
 def measured_hbm_gbs():
@@ -443,14 +568,55 @@ def run_sweeps(args):
             del sc
         line = {"workload": "bn254_g1_msm_sweep", "unit": "ms", "rows": rows, "steps": args.steps, "warmup": args.warmup,
                 "int32_peak_tmul32": peak_int / 1e12, "normalisation": "21760 mul32 per point (SURVEY 8d)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     ctx.close()
 
 
+class _CleanStdout:
+    """Everything any library prints to fd 1 (NCCL prints its version there) goes to stderr; only our JSON line reaches
+    the real stdout, so the driver always finds exactly one line to parse."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        self.out = os.fdopen(self.real, "w", closefd=False)
+        return self
+
+    def emit(self, obj):
+        self.out.write(json.dumps(obj) + "\n")
+        self.out.flush()
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+_OUT = None
+
+
+def emit(obj):
+    if _OUT is not None:
+        _OUT.emit(obj)
+    else:
+        print(json.dumps(obj), flush=True)
+
+
 def main():
+    global _OUT
     args = parse_args()
+    with _CleanStdout() as _OUT:
+        _main(args)
+    _OUT = None
+
+
+def _main(args):
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "prove":
+        run_prove(args)
     elif args.workload != "msm_g1":
         run_sweeps(args)
     else:

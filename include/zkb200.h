@@ -160,6 +160,10 @@ typedef struct {
 
 int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* desc, int validate, zkb_pk** out);
 void zkb_pk_free(zkb_pk* pk);
+/* BENCHMARK ONLY: a key of the given shape whose query points are [k_i] G for k_len >= max(num_vars + 2, h_len) + 4
+ * canonical Fr scalars in device memory (no trusted setup; proofs do not verify, timing is that of a real key). */
+int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev, size_t k_len,
+                     zkb_pk** out);
 
 /* Proof = (A in G1, B in G2, C in G1), canonical affine, A NOT negated (negation and flag bits are host-side
  * formatting: prover.rs:304-334 / ark-serialize).  r, s: 32 B canonical Fr, the prover's randomness

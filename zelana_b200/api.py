@@ -190,6 +190,14 @@ class Context:
     def proving_key(self, **parts):
         return ProvingKeyDev(self, **parts)
 
+    def proving_key_synthetic(self, num_vars, num_witness, h_len, k_dev, k_len):
+        """Benchmark-only key of the given shape (query points [k_i] G from device scalars); proofs do not verify."""
+        h = C.c_void_p()
+        self._check(self.lib.zkb_pk_synthetic(self.h, num_vars, num_witness, h_len, _devptr(k_dev), k_len, C.byref(h)))
+        pk = ProvingKeyDev.__new__(ProvingKeyDev)
+        pk.ctx, pk.h = self, h
+        return pk
+
     def witness_map(self, r1cs, z_bytes):
         pz, kz = _buf(z_bytes)
         n = 1 << r1cs.log_domain
@@ -281,13 +289,17 @@ class R1csMatrices:
     """Device-resident ConstraintMatrices (ark-relations): rows of (coeff, variable)."""
 
     def __init__(self, ctx, num_instance, num_witness, a, b, c):
-        assert len(a) == len(b) == len(c)
+        """a, b, c: rows of (coeff, variable) pairs, or prebuilt CSR triples (row_ptr u64, col u32, coeff u8[nnz*32])."""
         self.ctx = ctx
         keep = []
         d = R1csDesc()
-        d.num_constraints, d.num_instance, d.num_witness = len(a), num_instance, num_witness
-        for name, rows in (("a", a), ("b", b), ("c", c)):
-            rp, col, co = _csr_arrays(rows)
+        csr = [m if isinstance(m, tuple) else _csr_arrays(m) for m in (a, b, c)]
+        assert len(csr[0][0]) == len(csr[1][0]) == len(csr[2][0])
+        d.num_constraints, d.num_instance, d.num_witness = len(csr[0][0]) - 1, num_instance, num_witness
+        for name, (rp, col, co) in zip(("a", "b", "c"), csr):
+            rp = np.ascontiguousarray(rp, dtype=np.uint64)
+            col = np.ascontiguousarray(col, dtype=np.uint32)
+            co = np.ascontiguousarray(co, dtype=np.uint8).reshape(-1)
             keep += [rp, col, co]
             setattr(d, name, Csr(rp.ctypes.data, col.ctypes.data, co.ctypes.data))
         h = C.c_void_p()

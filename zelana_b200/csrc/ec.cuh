@@ -36,6 +36,10 @@ struct Fq2 {
     Fq d = (c0.sqr() + c1.sqr()).inverse();
     return {c0 * d, (c1 * d).neg()};
   }
+  __device__ Fq2 inverse_vartime() const {
+    Fq d = (c0.sqr() + c1.sqr()).inverse_vartime();
+    return {c0 * d, (c1 * d).neg()};
+  }
   __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
   __device__ __forceinline__ Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
 };
@@ -171,6 +175,15 @@ struct XYZZ {
         if ((k[i] >> bit) & 1u) r.add(*this);
       }
     return r;
+  }
+
+  // same with the variable-time inversion: single-thread tails only
+  __device__ Affine<F> to_affine_vartime() const {
+    if (is_inf()) return Affine<F>::inf();
+    F zi3 = zzz.inverse_vartime();
+    F zi = zi3 * zz;
+    F zi2 = zi.sqr();
+    return {x * zi2, y * zi3};
   }
 
   __device__ Affine<F> to_affine() const {

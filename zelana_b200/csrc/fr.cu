@@ -13,6 +13,7 @@ struct NttTables {
   Fr* mem = nullptr;  // one allocation
   PowTable fwd, inv, coset_pre, coset_inv_post;
   const Fr* ninv = nullptr;
+  const Fr* zinv = nullptr;  // (g^n - 1)^-1
 };
 
 struct FrState {
@@ -80,20 +81,20 @@ __global__ void csr_matvec_kernel(const uint64_t* __restrict__ row_ptr, const ui
   out[i] = acc;
 }
 
+// zinv = (g^n - 1)^-1, g = 5: the inverse of the vanishing polynomial on the coset (one thread, once per domain size)
+__global__ void qap_zinv_kernel(int logn, Fr* out) {
+  if (blockIdx.x || threadIdx.x) return;
+  Fr gn = fr_base(FRB_GEN);
+  for (int k = 0; k < logn; k++) gn = gn.sqr();
+  *out = (gn - Fr::one()).inverse_vartime();
+}
+
 // ab[i] = (a[i] * b[i] - c[i]) * zinv ; a is in Montgomery form, b and c canonical, zinv Montgomery -> canonical
 __global__ void qap_pointwise_kernel(const Fr* __restrict__ a, const Fr* __restrict__ b, const Fr* __restrict__ c,
-                                     int logn, size_t n, Fr* __restrict__ out) {
+                                     const Fr* __restrict__ zinv, size_t n, Fr* __restrict__ out) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  __shared__ Fr zinv_sh;
-  if (threadIdx.x == 0) {
-    // (g^n - 1)^-1, g = 5
-    Fr gn = fr_base(FRB_GEN);
-    for (int k = 0; k < logn; k++) gn = gn.sqr();
-    zinv_sh = (gn - Fr::one()).inverse();
-  }
-  __syncthreads();
   if (i >= n) return;
-  out[i] = (a[i] * b[i] - c[i]) * zinv_sh;
+  out[i] = (load_fr(a + i) * load_fr(b + i) - load_fr(c + i)) * ldg_fr(zinv);
 }
 
 // scalars for the folded MSMs (all canonical):
@@ -133,7 +134,7 @@ int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
   int lb = (logn + 1) / 2;
   uint32_t nlo = 1u << lb, nhi = 1u << (logn - lb);
   size_t per = size_t(nlo) + nhi;
-  CUDA_TRY(ctx, cudaMalloc(&t.mem, (4 * per + 1) * sizeof(Fr)));
+  CUDA_TRY(ctx, cudaMalloc(&t.mem, (4 * per + 2) * sizeof(Fr)));
   Fr* p = t.mem;
   unsigned long long wmult = 1ull << (28 - logn);
   auto gen = [&](Fr* lo, int base, unsigned long long mult, int sbase, unsigned long long sexp) {
@@ -155,8 +156,10 @@ int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
   Fr* ninv = p + 4 * per;
   // single constant n^-1 = (1/2)^logn: i = 0 gives base^0 = 1, times sbase^sexp
   fr_pow_table_kernel<<<1, 32, 0, ctx->stream>>>(ninv, 1, FRB_INV2, 1, 1, FRB_INV2, (unsigned long long)logn);
-  ctx->launches++;
+  qap_zinv_kernel<<<1, 32, 0, ctx->stream>>>(logn, ninv + 1);
+  ctx->launches += 2;
   t.ninv = ninv;
+  t.zinv = ninv + 1;
   CUDA_TRY(ctx, cudaGetLastError());
   auto ins = S->tables.emplace(logn, t);
   *out = &ins.first->second;
@@ -309,7 +312,9 @@ int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev
   }
   {
     ProfScope ps(ctx, PH_POINTWISE);
-    qap_pointwise_kernel<<<blocks_for(n, 128), 128, 0, st>>>(w.wa, w.wb, w.wc, lg, n, w.wa);
+    NttTables* T = nullptr;
+    ZKB_TRY(ensure_ntt_tables(ctx, state(ctx), lg, &T));
+    qap_pointwise_kernel<<<blocks_for(n, 128), 128, 0, st>>>(w.wa, w.wb, w.wc, T->zinv, n, w.wa);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
   }

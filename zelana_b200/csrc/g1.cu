@@ -44,7 +44,7 @@ __global__ void prove_assemble_c_kernel(const XYZZ<Fq>* A, const XYZZ<Fq>* B1, c
     acc.add(part[1]);
     acc.add(*L);
     acc.add(*H);
-    store_affine_canonical<Fq>(acc.to_affine(), out_c);
+    store_affine_canonical<Fq>(acc.to_affine_vartime(), out_c);
   }
 }
 

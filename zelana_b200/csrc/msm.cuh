@@ -20,14 +20,15 @@
 //                               in its chunk with XYZZ mixed additions (8M+2S) on gathered 64-byte affine points;
 //                               a run that starts inside the chunk is stored to its bucket, the run that was
 //                               already open at the chunk start goes to a per-thread "head" slot.
-//   4. msm_heads_level_kernel   heads are again a sorted list: the same chunking, 16 per thread, level after level
-//                               (a bucket holding millions of entries -- scalars 0/1 of real witnesses -- is
-//                               folded in log_16 steps), then msm_heads_kernel for the last <= 256.
+//   4. msm_heads_warp_kernel    heads are again a sorted list: one lane per head, warp-segmented scan (5 shuffle
+//                               steps), 32x shorter per level (a bucket holding millions of entries -- scalars 0/1 of
+//                               real witnesses -- is folded in log_32 steps).
 //   5. msm_bucket_seg_kernel    sum_b (b+1) B_b by segments of S = 32 buckets: W_s = local weighted sum, T_s = plain
 //                               sum; sum_b (b+1) B_b = sum_s W_s + S * sum_s s T_s.
-//      msm_plane_sum_kernel     sum_s s T_s = sum_y 2^y (sum of T_s over s with bit y set): log-depth tree sums per
-//                               bit plane (plus one plane for sum_s W_s), no scalar multiplications, no long chains.
-//   6. msm_final_kernel         Horner over the planes, XYZZ -> affine -> canonical bytes.
+//      msm_rowcol_kernel        s = 256 hi + lo:  sum_s s T_s = 256 sum_hi hi Row_hi + sum_lo lo Col_lo (tree sums).
+//      msm_plane_kernel         the two short weighted sums by bit planes: sum_i i A_i = sum_y 2^y (sum of A_i over i
+//                               with bit y set); no scalar multiplications, no long dependent chains.
+//   6. msm_final_kernel         one warp sums the planes with shuffles, XYZZ -> affine -> canonical bytes.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
@@ -42,7 +43,8 @@ static inline int ilog2_ceil(size_t n) {
   return l;
 }
 
-constexpr int MSM_SEG_LOG = 5;   // bucket reduction: segments of 32
+constexpr int MSM_SEG_LOG = 5;   // bucket reduction: segments of 32 buckets
+constexpr int MSM_COL_LOG = 8;   // segment totals viewed as rows x 256 columns
 
 static inline int msm_windows_for(int c) { return (255 + c - 1) / c; }  // nwin * c >= 255: the top digit absorbs the carry
 
@@ -205,57 +207,59 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------- 4. heads
-// One level: the (sorted) head list is chunked again, CHUNK per thread.  A run that starts inside the chunk is complete
-// up to the next level's heads and is ADDED to its bucket; the run open at the chunk start becomes a head of the next level.
-template <class F, int CHUNK>
-__global__ void __launch_bounds__(64)
-msm_heads_level_kernel(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, size_t count, uint32_t sentinel,
-                       XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ out, uint32_t* __restrict__ out_keys) {
-  size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  size_t start = t * CHUNK;
-  if (start >= count) return;
-  size_t end = start + CHUNK < count ? start + CHUNK : count;
-  uint32_t cur = in_keys[start];
-  if (cur >= sentinel) {
-    out_keys[t] = sentinel;
-    return;
-  }
-  bool first_run = true;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (size_t j = start; j < end; j++) {
-    acc.add(load_xyzz(in + j));
-    uint32_t k = (j + 1 < end) ? in_keys[j + 1] : sentinel;
-    if (k != cur) {
-      if (first_run) {
-        store_xyzz(out + t, acc);
-        out_keys[t] = cur;
-        first_run = false;
-      } else {
-        XYZZ<F> b = load_xyzz(buckets + cur);
-        b.add(acc);
-        store_xyzz(buckets + cur, b);
-      }
-      acc = XYZZ<F>::inf();
-      cur = k;
-      if (k >= sentinel) break;
-    }
-  }
+template <class F>
+__device__ __forceinline__ F shfl_up_field(const F& a, int d);
+template <>
+__device__ __forceinline__ Fq shfl_up_field<Fq>(const Fq& a, int d) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_up_sync(0xffffffffu, a.v[i], d);
+  return r;
+}
+template <>
+__device__ __forceinline__ Fq2 shfl_up_field<Fq2>(const Fq2& a, int d) {
+  return {shfl_up_field<Fq>(a.c0, d), shfl_up_field<Fq>(a.c1, d)};
+}
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_up_xyzz(const XYZZ<F>& p, int d) {
+  return {shfl_up_field<F>(p.x, d), shfl_up_field<F>(p.y, d), shfl_up_field<F>(p.zz, d), shfl_up_field<F>(p.zzz, d)};
 }
 
-// last level: one leader per distinct key folds its heads into the bucket
+// One level of head folding: the head list is sorted by key, one lane per head.  A warp does a segmented inclusive scan
+// (5 shuffle steps, one addition each) so the last lane of every run holds the run's sum.  A run that starts inside the warp
+// is ADDED to its bucket; the run that is open at lane 0 becomes a head of the next level (or, when `last`, also goes to
+// its bucket).  Each level shrinks the list 32x with a latency of five additions.
 template <class F>
-__global__ void msm_heads_kernel(const XYZZ<F>* __restrict__ heads, const uint32_t* __restrict__ head_keys,
-                                 size_t nthreads, uint32_t sentinel, XYZZ<F>* __restrict__ buckets) {
-  size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= nthreads) return;
-  uint32_t k = head_keys[t];
-  if (k >= sentinel) return;
-  if (t > 0 && head_keys[t - 1] == k) return;  // not the leader of this bucket's heads
-  XYZZ<F> acc = load_xyzz(heads + t);
-  for (size_t u = t + 1; u < nthreads && head_keys[u] == k; u++) acc.add(load_xyzz(heads + u));
-  XYZZ<F> b = load_xyzz(buckets + k);
-  b.add(acc);
-  store_xyzz(buckets + k, b);
+__global__ void __launch_bounds__(64)
+msm_heads_warp_kernel(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict__ in_keys, size_t count, uint32_t sentinel,
+                      XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ out, uint32_t* __restrict__ out_keys, int last) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t warp = i >> 5;
+  if ((warp << 5) >= count) return;  // whole warp beyond the list (grid rounding)
+  const int lane = threadIdx.x & 31;
+  uint32_t key = i < count ? in_keys[i] : sentinel;
+  if (key > sentinel) key = sentinel;
+  XYZZ<F> val = (i < count && key < sentinel) ? load_xyzz(in + i) : XYZZ<F>::inf();
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    XYZZ<F> o = shfl_up_xyzz(val, d);
+    uint32_t ok = __shfl_up_sync(0xffffffffu, key, d);
+    if (lane >= d && ok == key && key < sentinel) val.add(o);
+  }
+  uint32_t next_key = __shfl_down_sync(0xffffffffu, key, 1);
+  uint32_t key0 = __shfl_sync(0xffffffffu, key, 0);
+  bool run_end = (lane == 31) || next_key != key;
+  if (key < sentinel && run_end) {
+    if (key == key0 && !last) {
+      store_xyzz(out + warp, val);
+      out_keys[warp] = key;
+    } else {
+      XYZZ<F> b = load_xyzz(buckets + key);
+      b.add(val);
+      store_xyzz(buckets + key, b);
+    }
+  }
+  if (lane == 0 && key >= sentinel && !last) out_keys[warp] = sentinel;
 }
 
 // ------------------------------------------------------------------------------------------- 5. bucket reduction
@@ -277,19 +281,9 @@ msm_bucket_seg_kernel(const XYZZ<F>* __restrict__ in, size_t m, XYZZ<F>* __restr
   store_xyzz(T + s, run);
 }
 
-// Bit-plane sums.  Plane y < nplanes: out[y * gridDim.x + bx] = sum of T[s] over the block's 256 indices s with bit y of s
-// set; plane y == nplanes: the plain sum of W[s].  With P_y the plane totals,  sum_s s T[s] = sum_y 2^y P_y.
-template <class F, int THREADS, int PER>
-__global__ void __launch_bounds__(THREADS)
-msm_plane_sum_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ W, size_t count, int nplanes,
-                     XYZZ<F>* __restrict__ out) {
-  __shared__ XYZZ<F> sh[THREADS];
-  const int y = blockIdx.y;
-  const XYZZ<F>* src = (y == nplanes) ? W : T;
-  size_t base = size_t(blockIdx.x) * PER;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (size_t i = base + threadIdx.x; i < base + PER && i < count; i += THREADS)
-    if (y == nplanes || ((i >> y) & 1)) acc.add(load_xyzz(src + i));
+// Block tree sum helper: every thread contributes `acc`; thread 0 returns the total.
+template <class F, int THREADS>
+__device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sh) {
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int stride = THREADS / 2; stride > 0; stride >>= 1) {
@@ -300,28 +294,54 @@ msm_plane_sum_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ 
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_xyzz(out + size_t(y) * gridDim.x + blockIdx.x, sh[0]);
+  return sh[0];
 }
 
-// second stage: out[y] = sum of in[y * per_plane .. +per_plane)
+// sum_s s T[s] with s = hi * C + lo (C = 2^MSM_COL_LOG columns) = C * sum_hi hi * Row[hi] + sum_lo lo * Col[lo].
+// blocks [0, rows): Row[hi] = sum_lo T[hi C + lo]; blocks [rows, 2 rows): WRow[hi] = sum_lo W[hi C + lo];
+// blocks [2 rows, 2 rows + C): Col[lo] = sum_hi T[hi C + lo].   out = Row[rows] | WRow[rows] | Col[C]
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-msm_plane_fold_kernel(const XYZZ<F>* __restrict__ in, size_t per_plane, XYZZ<F>* __restrict__ out) {
+msm_rowcol_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ W, size_t nseg, size_t rows, XYZZ<F>* __restrict__ out) {
   __shared__ XYZZ<F> sh[THREADS];
-  const XYZZ<F>* src = in + size_t(blockIdx.x) * per_plane;
+  constexpr size_t C = size_t(1) << MSM_COL_LOG;
+  const size_t b = blockIdx.x;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (size_t i = threadIdx.x; i < per_plane; i += THREADS) acc.add(load_xyzz(src + i));
-  sh[threadIdx.x] = acc;
-  __syncthreads();
-  for (int stride = THREADS / 2; stride > 0; stride >>= 1) {
-    if (int(threadIdx.x) < stride) {
-      XYZZ<F> a = sh[threadIdx.x];
-      a.add(sh[threadIdx.x + stride]);
-      sh[threadIdx.x] = a;
-    }
-    __syncthreads();
+  if (b < 2 * rows) {
+    const XYZZ<F>* src = b < rows ? T : W;
+    size_t hi = b < rows ? b : b - rows;
+    for (size_t lo = threadIdx.x; lo < C; lo += THREADS)
+      if (hi * C + lo < nseg) acc.add(load_xyzz(src + hi * C + lo));
+  } else {
+    size_t lo = b - 2 * rows;
+    for (size_t hi = threadIdx.x; hi < rows; hi += THREADS)
+      if (hi * C + lo < nseg) acc.add(load_xyzz(T + hi * C + lo));
   }
-  if (threadIdx.x == 0) store_xyzz(out + blockIdx.x, sh[0]);
+  XYZZ<F> tot = block_sum<F, THREADS>(acc, sh);
+  if (threadIdx.x == 0) store_xyzz(out + b, tot);
+}
+
+// Weighted sums of the short arrays by bit planes: block (y, a) with a in {0: Row, 1: Col}:
+//   out[a * 16 + y] = 2^y * sum_{i : bit y of i} A_a[i]       (y < 16; the 2^y by y doublings in thread 0)
+// and block (0, 2): out[32] = sum_i WRow[i].
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+msm_plane_kernel(const XYZZ<F>* __restrict__ rc, size_t rows, XYZZ<F>* __restrict__ out) {
+  __shared__ XYZZ<F> sh[THREADS];
+  constexpr size_t C = size_t(1) << MSM_COL_LOG;
+  const int y = blockIdx.x, a = blockIdx.y;
+  const XYZZ<F>* src = a == 0 ? rc : (a == 1 ? rc + 2 * rows : rc + rows);
+  const size_t cnt = a == 1 ? C : rows;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  if (a < 2 || y == 0)
+    for (size_t i = threadIdx.x; i < cnt; i += THREADS)
+      if (a == 2 || ((i >> y) & 1)) acc.add(load_xyzz(src + i));
+  XYZZ<F> tot = block_sum<F, THREADS>(acc, sh);
+  if (threadIdx.x == 0 && (a < 2 || y == 0)) {
+    if (a < 2)
+      for (int k = 0; k < y; k++) tot = tot.dbl();
+    store_xyzz(out + (a == 2 ? 32 : a * 16 + y), tot);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- 6. final
@@ -343,22 +363,32 @@ __device__ inline void store_affine_canonical<Fq2>(const Affine<Fq2>& a, uint32_
     for (int i = 0; i < 8; i++) out[8 * k + i] = v[k].v[i];
 }
 
-// planes[y] = P_y for y < nplanes, planes[nplanes] = sum_s W[s]:
-//   result = sum_b (b+1) B_b = sum_s W[s] + S * sum_y 2^y P_y   (Horner over the planes, then MSM_SEG_LOG doublings).
-// Writes the XYZZ sum (Montgomery, for multi-GPU combining) and the canonical affine bytes.
+// planes[0..16) = 2^y RowPlane_y, planes[16..32) = 2^y ColPlane_y, planes[32] = sum W:
+//   result = sum_b (b+1) B_b = sum W + S * (C * sum_y planes[y] + sum_y planes[16 + y]).
+// One warp: lanes tree-sum the two groups with shuffles, lane 0 finishes.  Writes the XYZZ sum (Montgomery, for multi-GPU
+// combining) and the canonical affine bytes.
 template <class F>
-__global__ void msm_final_kernel(const XYZZ<F>* __restrict__ planes, int nplanes, XYZZ<F>* __restrict__ out_xyzz,
-                                 uint32_t* __restrict__ out_affine) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (int y = nplanes - 1; y >= 0; y--) {
-    acc = acc.dbl();
-    acc.add(load_xyzz(planes + y));
+__global__ void __launch_bounds__(32)
+msm_final_kernel(const XYZZ<F>* __restrict__ planes, int row_planes, int col_planes, XYZZ<F>* __restrict__ out_xyzz,
+                 uint32_t* __restrict__ out_affine) {
+  const int lane = threadIdx.x;
+  const int y = lane & 15, grp = lane >> 4;
+  XYZZ<F> v = XYZZ<F>::inf();
+  if (y < (grp == 0 ? row_planes : col_planes)) v = load_xyzz(planes + grp * 16 + y);
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {  // after the loop lanes 15 and 31 hold their group's sum
+    XYZZ<F> o = shfl_up_xyzz(v, d);
+    if (y >= d) v.add(o);
   }
+  XYZZ<F> row_total = shfl_up_xyzz(v, 16);  // lane 31 receives the row-group total held by lane 15
+  if (lane != 31) return;
+  XYZZ<F> acc = row_total;             // sum_y 2^y RowPlane_y
+  for (int k = 0; k < MSM_COL_LOG; k++) acc = acc.dbl();
+  acc.add(v);                          // + column part
   for (int k = 0; k < MSM_SEG_LOG; k++) acc = acc.dbl();
-  acc.add(load_xyzz(planes + nplanes));
+  acc.add(load_xyzz(planes + 32));
   if (out_xyzz) store_xyzz(out_xyzz, acc);
-  if (out_affine) store_affine_canonical<F>(acc.to_affine(), out_affine);
+  if (out_affine) store_affine_canonical<F>(acc.to_affine_vartime(), out_affine);
 }
 
 // sum of k XYZZ points (multi-GPU combine: one partial per rank) -> canonical affine
@@ -367,7 +397,7 @@ __global__ void msm_combine_kernel(const XYZZ<F>* __restrict__ parts, int k, uin
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   XYZZ<F> acc = XYZZ<F>::inf();
   for (int i = 0; i < k; i++) acc.add(load_xyzz(parts + i));
-  store_affine_canonical<F>(acc.to_affine(), out_affine);
+  store_affine_canonical<F>(acc.to_affine_vartime(), out_affine);
 }
 
 // ------------------------------------------------------------------------------------------- driver
@@ -392,7 +422,6 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
-  constexpr int HCHUNK = 16;
   constexpr int S = 1 << MSM_SEG_LOG;
   cudaStream_t st = ctx->stream;
   if (n == 0) {
@@ -406,17 +435,20 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   const int key_bits = ilog2_ceil(size_t(nbuck) + 1);
   const size_t total = size_t(nwin) * n;
   if (total >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
-  // ~8 waves of accumulate threads, chunks of 32..1024 entries
+  // Equal chunks of the sorted list, one per thread, sized so that the threads fill a WHOLE number k of resident waves
+  // (no partial last wave) with ~512 entries each: few heads (one per thread), no tail.
   size_t resident = size_t(ctx->sm_count) * T::THREADS_PER_SM;
-  size_t chunk = (total + resident * 8 - 1) / (resident * 8);
-  chunk = chunk < 32 ? 32 : (chunk > 1024 ? 1024 : chunk);
-  chunk = (chunk + 3) & ~size_t(3);
+  size_t waves = (total + resident * 256) / (resident * 512);
+  if (waves < 1) waves = 1;
+  size_t chunk = (total + waves * resident - 1) / (waves * resident);
+  chunk = chunk < 16 ? 16 : chunk;
   const size_t nthreads = (total + chunk - 1) / chunk;
 
-  // bucket reduction: segments of S buckets, then bit-plane sums over the nseg segment totals
+  // bucket reduction: segments of S buckets, then row / column sums of the nseg segment totals and their bit planes
   const size_t nseg = (size_t(nbuck) + S - 1) / S;
-  const int nplanes = nseg > 1 ? ilog2_ceil(nseg) : 0;
-  const size_t plane_blocks = (nseg + 255) / 256;
+  const size_t rows = (nseg + (size_t(1) << MSM_COL_LOG) - 1) >> MSM_COL_LOG;
+  const int row_planes = rows > 1 ? ilog2_ceil(rows) : 0;
+  const int col_planes = nseg > 1 ? (nseg >= (size_t(1) << MSM_COL_LOG) ? MSM_COL_LOG : ilog2_ceil(nseg)) : 0;
 
   size_t sort_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -430,13 +462,13 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   size_t o_k0 = take(total * 4), o_v0 = take(total * 4), o_k1 = take(total * 4), o_v1 = take(total * 4);
   size_t o_tmp = take(sort_tmp);
   size_t o_buck = take(size_t(nbuck) * sizeof(P));
-  size_t nh1 = (nthreads + HCHUNK - 1) / HCHUNK;
+  size_t nh1 = (nthreads + 31) / 32;
   size_t o_h0 = take(nthreads * sizeof(P)), o_hk0 = take(nthreads * 4);
   size_t o_h1 = take(nh1 * sizeof(P)), o_hk1 = take(nh1 * 4);
   size_t o_W = take(nseg * sizeof(P));
   size_t o_T = take(nseg * sizeof(P));
-  size_t o_part = take(size_t(nplanes + 1) * plane_blocks * sizeof(P));
-  size_t o_planes = take(size_t(nplanes + 1) * sizeof(P));
+  size_t o_part = take((2 * rows + (size_t(1) << MSM_COL_LOG)) * sizeof(P));
+  size_t o_planes = take(33 * sizeof(P));
   cudaError_t e = ctx->msm_ws.reserve(off);
   if (e != cudaSuccess) return e;
   char* base = static_cast<char*>(ctx->msm_ws.p);
@@ -471,25 +503,24 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   }
   {
     ProfScope ps(ctx, PH0 + 3);
-    // heads, level by level (a level with <= 256 entries goes to the leader kernel)
+    // heads: 32x per level; the last level (<= 32 heads) folds everything into the buckets
     size_t count = nthreads;
     int cur = 0;
-    while (count > 256) {
-      size_t nt = (count + HCHUNK - 1) / HCHUNK;
-      cudaMemsetAsync(hk[cur ^ 1], 0xff, nt * 4, st);
-      msm_heads_level_kernel<F, HCHUNK><<<unsigned((nt + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets,
-                                                                                hp[cur ^ 1], hk[cur ^ 1]);
+    while (true) {
+      int last = count <= 32 ? 1 : 0;
+      size_t nw = (count + 31) / 32;
+      msm_heads_warp_kernel<F><<<unsigned((nw * 32 + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets, hp[cur ^ 1],
+                                                                          hk[cur ^ 1], last);
       ctx->launches++;
-      count = nt;
+      if (last) break;
+      count = nw;
       cur ^= 1;
     }
-    msm_heads_kernel<F><<<unsigned((count + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets);
-    ctx->launches++;
     // bucket reduction
     msm_bucket_seg_kernel<F><<<unsigned((nseg + 63) / 64), 64, 0, st>>>(buckets, nbuck, W, Tt, nseg);
-    msm_plane_sum_kernel<F, 64, 256><<<dim3(unsigned(plane_blocks), unsigned(nplanes + 1)), 64, 0, st>>>(Tt, W, nseg, nplanes, part);
-    msm_plane_fold_kernel<F, 64><<<unsigned(nplanes + 1), 64, 0, st>>>(part, plane_blocks, planes);
-    msm_final_kernel<F><<<1, 32, 0, st>>>(planes, nplanes, out_xyzz, out_affine);
+    msm_rowcol_kernel<F, 64><<<unsigned(2 * rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, nseg, rows, part);
+    msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, rows, planes);
+    msm_final_kernel<F><<<1, 32, 0, st>>>(planes, row_planes, col_planes, out_xyzz, out_affine);
     ctx->launches += 4;
   }
   return cudaGetLastError();

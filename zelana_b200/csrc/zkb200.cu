@@ -435,6 +435,37 @@ extern "C" int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, zkb
   return ZKB_OK;
 }
 
+// Benchmark-only key: every query vector is [k_i] G for caller-supplied device scalars, so that a forge-sized key
+//  can be fabricated in seconds on the GPU.  Proofs made with it do not verify -- the timing
+// of zkb_prove does not depend on which curve points the key holds; correctness is covered by the real-key tests.
+extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev,
+                                size_t k_len, zkb_pk** out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || !k_dev || num_vars < 1 || num_witness > num_vars - 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_synthetic: bad argument");
+  size_t need = num_vars + 2 > h_len ? num_vars + 2 : h_len;
+  if (k_len < need + 4) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_synthetic: need %zu scalars, got %zu", need + 4, k_len);
+  *out = nullptr;
+  ZKB_TRY(set_device(ctx));
+  zkb_pk* pk = new (std::nothrow) zkb_pk();
+  if (!pk) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_synthetic: host allocation failed");
+  pk->device = ctx->device;
+  pk->nv = num_vars;
+  pk->nw = num_witness;
+  pk->nh = h_len;
+  const char* k = static_cast<const char*>(k_dev);
+  int s = bases_generate_impl<Fq>(ctx, k, num_vars + 2, &pk->a_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 32, num_vars + 2, &pk->b1_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq2>(ctx, k + 64, num_vars + 2, &pk->b2_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 96, num_witness + 1, &pk->l_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 128, h_len, &pk->h);
+  if (s != ZKB_OK) {
+    zkb_pk_free(pk);
+    return s;
+  }
+  *out = pk;
+  return ZKB_OK;
+}
+
 extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
                          const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
