@@ -292,3 +292,127 @@ def test_prove_shape_errors(ctx, mimc_setup):
     with pytest.raises(zelana_b200.ZkbError) as e:
         ctx.prove(dpk, m_sq, fr_bytes(zsq), fr_bytes([1]), fr_bytes([1]))
     assert e.value.code == -6
+
+
+# ----------------------------------------------------------------------------- mid / full size against the C++ restatement
+def _rand_fr_np(n, seed):
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    a = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    a[:, 7] %= 0x30644E72
+    return a
+
+
+def test_msm_g1_2p16_matches_cpp_oracle_and_witness_like(ctx):
+    """Random (not arithmetic-progression) bases generated on the GPU, read back, and summed by oracle/cpu_oracle.cpp."""
+    import numpy as np
+    import torch
+    from oracle import cpu as orc
+    n = 1 << 16
+    k = _rand_fr_np(n, 1)
+    bases = ctx.g1_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+    cb = orc.G1Bases.from_raw(bases.read())
+    s = _rand_fr_np(n, 2)
+    assert ctx.msm_g1(bases, s) == cb.msm(s)
+    # witness-like scalars: 50% zero, 25% one, a hot bucket of 2^14 equal small scalars, the rest uniform
+    w = s.copy()
+    r = np.random.RandomState(3).rand(n)
+    w[r < 0.5] = 0
+    one = np.zeros(8, dtype=np.uint32); one[0] = 1
+    w[(r >= 0.5) & (r < 0.75)] = one
+    w[: 1 << 14] = 0
+    w[: 1 << 14, 0] = 7
+    assert ctx.msm_g1(bases, w) == cb.msm(w)
+    # sub-range with an offset
+    assert ctx.msm_g1(bases, s[1000:30000], offset=1000) == cb.msm(s[1000:30000], off=1000)
+
+
+def test_msm_g2_2p13_matches_cpp_oracle(ctx):
+    import numpy as np
+    import torch
+    from oracle import cpu as orc
+    n = 1 << 13
+    k = _rand_fr_np(n, 4)
+    bases = ctx.g2_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+    s = _rand_fr_np(n, 5)
+    assert ctx.msm_g2(bases, s) == orc.msm_g2(bases.read(), s)
+
+
+def test_msm_g1_2p22_known_dlog(ctx):
+    """Full-pipeline check at 2^22 (c = 21/22 tables): sum s_i [k_i]G == [sum k_i s_i]G, exact integers on the host."""
+    import numpy as np
+    import torch
+    n = 1 << 22
+    k = _rand_fr_np(n, 6)
+    s = _rand_fr_np(n, 7)
+    bases = ctx.g1_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+    out = ctx.msm_g1(bases, s)
+
+    def ints(a):  # [n, 8] u32 -> python ints
+        b = a.astype(np.uint64)
+        lo = b[:, 0] | (b[:, 1] << np.uint64(32))
+        parts = [b[:, 2 * j] | (b[:, 2 * j + 1] << np.uint64(32)) for j in range(4)]
+        return [int(p0) | (int(p1) << 64) | (int(p2) << 128) | (int(p3) << 192)
+                for p0, p1, p2, p3 in zip(*[p.tolist() for p in parts])]
+
+    acc = 0
+    for a, b in zip(ints(k), ints(s)):
+        acc += a * b
+    assert out == bn.g1_to_raw(bn.G1.mul(bn.G1_GEN, acc % R))
+
+
+@pytest.mark.parametrize("log_n", [14, 18])
+def test_ntt_matches_cpp_oracle(ctx, log_n):
+    from oracle import cpu as orc
+    a = _rand_fr_np(1 << log_n, 10 + log_n)
+    for inv in (False, True):
+        for coset in (False, True):
+            assert ctx.ntt(a, log_n, inverse=inv, coset=coset) == orc.ntt(a, log_n, inverse=inv, coset=coset)
+
+
+def test_ntt_roundtrip_2p24(ctx):
+    import numpy as np
+    a = _rand_fr_np(1 << 24, 99)
+    data = a.tobytes()
+    f = ctx.ntt(data, 24, coset=True)
+    assert f != data
+    assert ctx.ntt(f, 24, inverse=True, coset=True) == data
+
+
+def test_prove_2p13_matches_cpp_oracle(ctx):
+    """Full prove on a 2^13-constraint MiMC circuit (the L2-dummy domain size): the key is a set of random
+    curve points generated on the GPU (no trusted setup needed to compare two provers), loaded into BOTH provers."""
+    import importlib.util
+    import os
+    import numpy as np
+    import torch
+    from conftest import ROOT
+    from oracle import cpu as orc
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ni, nw, (A, B, Cm), z = bench.mimc_r1cs_numpy(np, num_perm=22, seed=77)       # 8009 constraints -> domain 2^13
+    nv, n = ni + nw, 1 << 13
+    m = ctx.r1cs(ni, nw, A, B, Cm)
+    assert m.log_domain == 13
+
+    def g1(cnt, seed):
+        b = ctx.g1_bases_generate(torch.from_numpy(_rand_fr_np(cnt, seed).view(np.int32)).cuda(), cnt)
+        return b.read()
+
+    def g2(cnt, seed):
+        b = ctx.g2_bases_generate(torch.from_numpy(_rand_fr_np(cnt, seed).view(np.int32)).cuda(), cnt)
+        return b.read()
+
+    parts = dict(alpha_g1=g1(1, 20), beta_g1=g1(1, 21), beta_g2=g2(1, 22), delta_g1=g1(1, 23), delta_g2=g2(1, 24),
+                 a_query=g1(nv, 25), b_g1_query=g1(nv, 26), b_g2_query=g2(nv, 27), h_query=g1(n - 1, 28), l_query=g1(nw, 29))
+    dpk = ctx.proving_key(**parts)
+    cpk = orc.ProvingKey(**parts)
+    cm = orc.R1cs(ni, nw, csr=(A, B, Cm))
+    zb = z.reshape(-1)
+    h_gpu = ctx.witness_map(m, zb)
+    assert h_gpu == orc.witness_map(cm, zb)
+    assert h_gpu[-32:] == bytes(32)
+    for r, s in ((0x1234567, 0x7654321), (R - 5, 3)):
+        got = ctx.prove(dpk, m, zb, fr_bytes([r]), fr_bytes([s]))
+        assert got == orc.prove(cpk, cm, zb, fr_bytes([r]), fr_bytes([s]))
