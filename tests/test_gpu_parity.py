@@ -416,3 +416,26 @@ def test_prove_2p13_matches_cpp_oracle(ctx):
     for r, s in ((0x1234567, 0x7654321), (R - 5, 3)):
         got = ctx.prove(dpk, m, zb, fr_bytes([r]), fr_bytes([s]))
         assert got == orc.prove(cpk, cm, zb, fr_bytes([r]), fr_bytes([s]))
+
+
+def test_msm_g1_host_sliced_path_2p21(ctx):
+    """zkb_msm_g1 with >= 2^20 host scalars takes the sliced path (upload overlapped with accumulation, one bucket array per
+    slice, merged before the reduction): same bytes as the device-resident path and as the C++ restatement."""
+    import numpy as np
+    import torch
+    from oracle import cpu as orc
+    n = (1 << 21) + 12345          # ragged: the last slice is shorter
+    k = _rand_fr_np(n, 31)
+    s = _rand_fr_np(n, 32)
+    s[: 1 << 12] = 0
+    bases = ctx.g1_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+    out = ctx.msm_g1(bases, s)
+    sd = torch.from_numpy(s.view(np.int32)).cuda()
+    od = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    ctx.msm_g1_dev(bases, sd, n, out_affine_dev=od)
+    ctx.synchronize()
+    assert out == bytes(od.cpu().numpy())
+    m = 1 << 18
+    assert ctx.msm_g1(bases, s[:m]) == orc.G1Bases.from_raw(bases.read(0, m)).msm(s[:m])
+    # twice in a row on the same context (slice buffers and events are reused)
+    assert ctx.msm_g1(bases, s) == out

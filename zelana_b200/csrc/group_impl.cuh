@@ -350,8 +350,20 @@ int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t 
   ZKB_TRY(set_device(ctx));
   CUDA_TRY(ctx, ctx->scal.reserve(n * 32 + 32));
   CUDA_TRY(ctx, ctx->res.reserve(512));
-  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  ZKB_TRY((msm_dev_impl<F>(ctx, bases, offset, ctx->scal.p, n, ctx->res.p, nullptr)));
+  if (n >= (size_t(1) << 20) && ctx->msm_slices > 1) {
+    // large: upload in slices on a second stream and accumulate each slice while the next one is in flight
+    if (!bases || offset + n > bases->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
+    if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
+    cudaError_t e = msm_run_host_sliced<F>(ctx, bases->p, bases->n, bases->c, bases->nwin, offset, scalars_host,
+                                           ctx->scal.as<uint32_t>(), n, ctx->msm_slices, nullptr, ctx->res.as<uint32_t>());
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run_host_sliced: %s", cudaGetErrorString(e));
+    }
+  } else {
+    if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKB_TRY((msm_dev_impl<F>(ctx, bases, offset, ctx->scal.p, n, ctx->res.p, nullptr)));
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;

@@ -18,6 +18,8 @@
 #include "../../include/zkb200.h"
 #include "ec.cuh"
 
+constexpr int ZKB_MAX_SLICES = 8;
+
 namespace zkb {
 
 struct DevBuf {
@@ -79,6 +81,9 @@ struct zkb_ctx {
   std::string err;
   unsigned long long launches = 0;
   int msm_c = 0;
+  int msm_slices = 4;                             // host-scalar MSMs >= 2^20: upload slices (env ZKB_MSM_SLICES, 1..8)
+  cudaStream_t copy_stream = nullptr;             // H2D slices of a host-scalar MSM, overlapped with compute
+  cudaEvent_t copy_done[8] = {nullptr};
   zkb::Prof prof;
   zkb::DevBuf msm_ws;                             // MSM scratch (keys, sort space, buckets)
   zkb::DevBuf scal, res, tmp0, tmp1, tmp2, flag;  // staging

@@ -414,90 +414,109 @@ struct MsmTraits<Fq2> {
   static constexpr int THREADS_PER_SM = 256;
 };
 
-// table: device, Montgomery affine, nwin x table_n (window-major).  The MSM covers bases [first, first + n).
-// scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
+// buckets[b] += extra[k][b] for k < nextra (slices of a pipelined MSM accumulate into separate bucket arrays)
 template <class F>
-cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
-                    const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+__global__ void __launch_bounds__(64)
+msm_bucket_merge_kernel(XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ extra, size_t nbuck, int nextra) {
+  size_t b = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (b >= nbuck) return;
+  XYZZ<F> acc = load_xyzz(buckets + b);
+  for (int k = 0; k < nextra; k++) acc.add(load_xyzz(extra + size_t(k) * nbuck + b));
+  store_xyzz(buckets + b, acc);
+}
+
+// Workspace layout of one MSM whose entries arrive in up to `nslices` slices of at most `n_slice` points each.
+template <class F>
+struct MsmLayout {
+  using P = XYZZ<F>;
+  int c = 0, nwin = 0, nslices = 1, key_bits = 0, row_planes = 0, col_planes = 0;
+  uint32_t nbuck = 0, sentinel = 0;
+  size_t n_slice = 0, total = 0, chunk = 0, nthreads = 0, nseg = 0, rows = 0, sort_tmp = 0, bytes = 0;
+  size_t o_k0, o_v0, o_k1, o_v1, o_tmp, o_buck, o_h0, o_hk0, o_h1, o_hk1, o_W, o_T, o_part, o_planes;
+};
+
+template <class F>
+static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, int nslices, cudaStream_t st) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
-  constexpr int PH0 = GroupOf<F>::PH0;
   constexpr int S = 1 << MSM_SEG_LOG;
-  cudaStream_t st = ctx->stream;
-  if (n == 0) {
-    // empty sum = infinity = all-zero encoding
-    if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(P), st);
-    if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>), st);
-    return cudaGetLastError();
-  }
-  const uint32_t nbuck = 1u << (c - 1);
-  const uint32_t sentinel = nbuck;
-  const int key_bits = ilog2_ceil(size_t(nbuck) + 1);
-  const size_t total = size_t(nwin) * n;
-  if (total >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
-  // Equal chunks of the sorted list, one per thread, sized so that the threads fill a WHOLE number k of resident waves
+  MsmLayout<F> L;
+  L.c = c;
+  L.nwin = nwin;
+  L.nslices = nslices;
+  L.n_slice = n_slice;
+  L.nbuck = 1u << (c - 1);
+  L.sentinel = L.nbuck;
+  L.key_bits = ilog2_ceil(size_t(L.nbuck) + 1);
+  L.total = size_t(nwin) * n_slice;
+  // Equal chunks of the sorted list, one per thread, sized so that the threads fill a WHOLE number of resident waves
   // (no partial last wave) with ~512 entries each: few heads (one per thread), no tail.
-  size_t resident = size_t(ctx->sm_count) * T::THREADS_PER_SM;
-  size_t waves = (total + resident * 256) / (resident * 512);
+  size_t resident = size_t(sm_count) * T::THREADS_PER_SM;
+  size_t waves = (L.total + resident * 256) / (resident * 512);
   if (waves < 1) waves = 1;
-  size_t chunk = (total + waves * resident - 1) / (waves * resident);
-  chunk = chunk < 16 ? 16 : chunk;
-  const size_t nthreads = (total + chunk - 1) / chunk;
-
+  L.chunk = (L.total + waves * resident - 1) / (waves * resident);
+  if (L.chunk < 16) L.chunk = 16;
+  L.nthreads = (L.total + L.chunk - 1) / L.chunk;
   // bucket reduction: segments of S buckets, then row / column sums of the nseg segment totals and their bit planes
-  const size_t nseg = (size_t(nbuck) + S - 1) / S;
-  const size_t rows = (nseg + (size_t(1) << MSM_COL_LOG) - 1) >> MSM_COL_LOG;
-  const int row_planes = rows > 1 ? ilog2_ceil(rows) : 0;
-  const int col_planes = nseg > 1 ? (nseg >= (size_t(1) << MSM_COL_LOG) ? MSM_COL_LOG : ilog2_ceil(nseg)) : 0;
-
-  size_t sort_tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, int(total), 0, key_bits, st);
+  L.nseg = (size_t(L.nbuck) + S - 1) / S;
+  L.rows = (L.nseg + (size_t(1) << MSM_COL_LOG) - 1) >> MSM_COL_LOG;
+  L.row_planes = L.rows > 1 ? ilog2_ceil(L.rows) : 0;
+  L.col_planes = L.nseg > 1 ? (L.nseg >= (size_t(1) << MSM_COL_LOG) ? MSM_COL_LOG : ilog2_ceil(L.nseg)) : 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, L.sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, int(L.total), 0, L.key_bits, st);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off += align_up(bytes);
     return o;
   };
-  size_t o_k0 = take(total * 4), o_v0 = take(total * 4), o_k1 = take(total * 4), o_v1 = take(total * 4);
-  size_t o_tmp = take(sort_tmp);
-  size_t o_buck = take(size_t(nbuck) * sizeof(P));
-  size_t nh1 = (nthreads + 31) / 32;
-  size_t o_h0 = take(nthreads * sizeof(P)), o_hk0 = take(nthreads * 4);
-  size_t o_h1 = take(nh1 * sizeof(P)), o_hk1 = take(nh1 * 4);
-  size_t o_W = take(nseg * sizeof(P));
-  size_t o_T = take(nseg * sizeof(P));
-  size_t o_part = take((2 * rows + (size_t(1) << MSM_COL_LOG)) * sizeof(P));
-  size_t o_planes = take(33 * sizeof(P));
-  cudaError_t e = ctx->msm_ws.reserve(off);
-  if (e != cudaSuccess) return e;
-  char* base = static_cast<char*>(ctx->msm_ws.p);
-  uint32_t *k0 = (uint32_t*)(base + o_k0), *v0 = (uint32_t*)(base + o_v0);
-  uint32_t *k1 = (uint32_t*)(base + o_k1), *v1 = (uint32_t*)(base + o_v1);
-  P* buckets = (P*)(base + o_buck);
-  P* hp[2] = {(P*)(base + o_h0), (P*)(base + o_h1)};
-  uint32_t* hk[2] = {(uint32_t*)(base + o_hk0), (uint32_t*)(base + o_hk1)};
-  P* W = (P*)(base + o_W);
-  P* Tt = (P*)(base + o_T);
-  P* part = (P*)(base + o_part);
-  P* planes = (P*)(base + o_planes);
+  L.o_k0 = take(L.total * 4), L.o_v0 = take(L.total * 4), L.o_k1 = take(L.total * 4), L.o_v1 = take(L.total * 4);
+  L.o_tmp = take(L.sort_tmp);
+  L.o_buck = take(size_t(L.nbuck) * sizeof(P) * nslices);
+  size_t nh1 = (L.nthreads + 31) / 32;
+  L.o_h0 = take(L.nthreads * sizeof(P)), L.o_hk0 = take(L.nthreads * 4);
+  L.o_h1 = take(nh1 * sizeof(P)), L.o_hk1 = take(nh1 * 4);
+  L.o_W = take(L.nseg * sizeof(P));
+  L.o_T = take(L.nseg * sizeof(P));
+  L.o_part = take((2 * L.rows + (size_t(1) << MSM_COL_LOG)) * sizeof(P));
+  L.o_planes = take(33 * sizeof(P));
+  L.bytes = off;
+  return L;
+}
 
+// Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE) -> bucket array `slice`.
+template <class F>
+cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affine<F>* table, size_t table_n, size_t first,
+                                 const uint32_t* scalars, size_t n, int slice) {
+  using T = MsmTraits<F>;
+  using P = XYZZ<F>;
+  constexpr int PH0 = GroupOf<F>::PH0;
+  cudaStream_t st = ctx->stream;
+  char* base = static_cast<char*>(ctx->msm_ws.p);
+  uint32_t *k0 = (uint32_t*)(base + L.o_k0), *v0 = (uint32_t*)(base + L.o_v0);
+  uint32_t *k1 = (uint32_t*)(base + L.o_k1), *v1 = (uint32_t*)(base + L.o_v1);
+  P* buckets = (P*)(base + L.o_buck) + size_t(slice) * L.nbuck;
+  P* hp[2] = {(P*)(base + L.o_h0), (P*)(base + L.o_h1)};
+  uint32_t* hk[2] = {(uint32_t*)(base + L.o_hk0), (uint32_t*)(base + L.o_hk1)};
+  const size_t total = size_t(L.nwin) * n;
+  const size_t nthreads = (total + L.chunk - 1) / L.chunk;
   {
     ProfScope ps(ctx, PH0 + 0);
-    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, c, nwin, sentinel, table_n, first, k0, v0);
+    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, L.c, L.nwin, L.sentinel, table_n, first, k0, v0);
     ctx->launches++;
   }
   {
     ProfScope ps(ctx, PH0 + 1);
-    e = cub::DeviceRadixSort::SortPairs(base + o_tmp, sort_tmp, k0, k1, v0, v1, int(total), 0, key_bits, st);
+    size_t tmp = L.sort_tmp;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.o_tmp, tmp, k0, k1, v0, v1, int(total), 0, L.key_bits, st);
     if (e != cudaSuccess) return e;
   }
-  cudaMemsetAsync(buckets, 0, size_t(nbuck) * sizeof(P), st);
+  cudaMemsetAsync(buckets, 0, size_t(L.nbuck) * sizeof(P), st);
   cudaMemsetAsync(hk[0], 0xff, nthreads * 4, st);
   {
     ProfScope ps(ctx, PH0 + 2);
     unsigned acc_blocks = unsigned((nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
-    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(table, k1, v1, total, int(chunk), sentinel,
+    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(table, k1, v1, total, int(L.chunk), L.sentinel,
                                                                                   buckets, hp[0], hk[0]);
     ctx->launches++;
   }
@@ -509,21 +528,102 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
     while (true) {
       int last = count <= 32 ? 1 : 0;
       size_t nw = (count + 31) / 32;
-      msm_heads_warp_kernel<F><<<unsigned((nw * 32 + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, sentinel, buckets, hp[cur ^ 1],
-                                                                          hk[cur ^ 1], last);
+      msm_heads_warp_kernel<F><<<unsigned((nw * 32 + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, L.sentinel, buckets,
+                                                                          hp[cur ^ 1], hk[cur ^ 1], last);
       ctx->launches++;
       if (last) break;
       count = nw;
       cur ^= 1;
     }
-    // bucket reduction
-    msm_bucket_seg_kernel<F><<<unsigned((nseg + 63) / 64), 64, 0, st>>>(buckets, nbuck, W, Tt, nseg);
-    msm_rowcol_kernel<F, 64><<<unsigned(2 * rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, nseg, rows, part);
-    msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, rows, planes);
-    msm_final_kernel<F><<<1, 32, 0, st>>>(planes, row_planes, col_planes, out_xyzz, out_affine);
-    ctx->launches += 4;
   }
   return cudaGetLastError();
+}
+
+// Stages 5-6: (merge the slices' bucket arrays,) reduce the buckets, write the results.
+template <class F>
+cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, int nslices_used, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+  using P = XYZZ<F>;
+  constexpr int PH0 = GroupOf<F>::PH0;
+  cudaStream_t st = ctx->stream;
+  char* base = static_cast<char*>(ctx->msm_ws.p);
+  P* buckets = (P*)(base + L.o_buck);
+  P* W = (P*)(base + L.o_W);
+  P* Tt = (P*)(base + L.o_T);
+  P* part = (P*)(base + L.o_part);
+  P* planes = (P*)(base + L.o_planes);
+  ProfScope ps(ctx, PH0 + 3);
+  if (nslices_used > 1) {
+    msm_bucket_merge_kernel<F><<<unsigned((size_t(L.nbuck) + 63) / 64), 64, 0, st>>>(buckets, buckets + L.nbuck, L.nbuck, nslices_used - 1);
+    ctx->launches++;
+  }
+  msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg);
+  msm_rowcol_kernel<F, 64><<<unsigned(2 * L.rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
+  msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, L.rows, planes);
+  msm_final_kernel<F><<<1, 32, 0, st>>>(planes, L.row_planes, L.col_planes, out_xyzz, out_affine);
+  ctx->launches += 4;
+  return cudaGetLastError();
+}
+
+// table: device, Montgomery affine, nwin x table_n (window-major).  The MSM covers bases [first, first + n).
+// scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
+template <class F>
+cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
+                    const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    // empty sum = infinity = all-zero encoding
+    if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(XYZZ<F>), st);
+    if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>), st);
+    return cudaGetLastError();
+  }
+  if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1, st);
+  cudaError_t e = ctx->msm_ws.reserve(L.bytes);
+  if (e != cudaSuccess) return e;
+  e = msm_accumulate_slice<F>(ctx, L, table, table_n, first, scalars, n, 0);
+  if (e != cudaSuccess) return e;
+  return msm_reduce<F>(ctx, L, 1, out_xyzz, out_affine);
+}
+
+// Host-scalar MSM pipelined against the PCIe copy: the scalars go up in `nslices` slices on a second stream; slice k is
+// decomposed, sorted and accumulated (into its own bucket array) while slice k+1 is still in flight.
+template <class F>
+cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
+                                const uint8_t* scalars_host, uint32_t* scalars_dev, size_t n, int nslices,
+                                XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+  if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
+  const size_t per = (n + nslices - 1) / nslices;
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, per, nslices, ctx->stream);
+  cudaError_t e = ctx->msm_ws.reserve(L.bytes);
+  if (e != cudaSuccess) return e;
+  if (!ctx->copy_stream) {
+    e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    for (int k = 0; k < ZKB_MAX_SLICES; k++) {
+      e = cudaEventCreateWithFlags(&ctx->copy_done[k], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  // the copy stream must not overwrite scalars_dev while earlier work on the compute stream still reads it
+  cudaEventRecord(ctx->copy_done[ZKB_MAX_SLICES - 1], ctx->stream);
+  cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[ZKB_MAX_SLICES - 1], 0);
+  int used = 0;
+  for (int k = 0; k < nslices; k++) {
+    size_t lo = size_t(k) * per;
+    if (lo >= n) break;
+    size_t cnt = lo + per <= n ? per : n - lo;
+    cudaMemcpyAsync(scalars_dev + lo * 8, scalars_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+    cudaEventRecord(ctx->copy_done[k], ctx->copy_stream);
+    used++;
+  }
+  for (int k = 0; k < used; k++) {
+    size_t lo = size_t(k) * per;
+    size_t cnt = lo + per <= n ? per : n - lo;
+    cudaStreamWaitEvent(ctx->stream, ctx->copy_done[k], 0);
+    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, k);
+    if (e != cudaSuccess) return e;
+  }
+  return msm_reduce<F>(ctx, L, used, out_xyzz, out_affine);
 }
 
 }  // namespace zkb

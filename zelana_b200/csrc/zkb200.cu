@@ -3,6 +3,8 @@
 // g1.cu, g2.cu); the host code here only moves bytes, sizes workspaces and orders launches.
 #include "internal.h"
 
+#include <cstdlib>
+
 using namespace zkb;
 
 // =============================================================================================== helpers
@@ -57,6 +59,10 @@ extern "C" int zkb_ctx_create(int device, zkb_ctx** out) {
   }
   ctx->own_stream = true;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* sl = getenv("ZKB_MSM_SLICES")) {
+    int v = atoi(sl);
+    if (v >= 1 && v <= ZKB_MAX_SLICES - 1) ctx->msm_slices = v;
+  }
   *out = ctx;
   return ZKB_OK;
 }
@@ -101,6 +107,12 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
     cudaEventDestroy(sp.b);
   }
   for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (int k = 0; k < ZKB_MAX_SLICES; k++)
+      if (ctx->copy_done[k]) cudaEventDestroy(ctx->copy_done[k]);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
