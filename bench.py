@@ -328,7 +328,7 @@ def run_ours(args):
         t_acc = acc_ms / acc_spans * 1e-3
         achieved = MUL32_PER_POINT * shard / t_acc
         roof = {"bound": "int32_mul", "kernel": "msm_accumulate_kernel<Fq>", "achieved": achieved / 1e12, "peak": peak / 1e12,
-                "unit": "Tmul32/s", "frac": achieved / peak, "traffic": None,
+                "unit": "Tmul32/s", "frac": achieved / peak, "traffic": accumulate_traffic(args.log_n, world),
                 "kernel_ms": t_acc * 1e3,
                 "peak_source": "measured live: zkb_bench_int32_peak (mad.wide.u32 %.2f, lo/hi pairs %.2f Tmul32/s)" % (
                     peak_wide / 1e12, peak_pair / 1e12),
@@ -496,6 +496,16 @@ def run_prove(args):
             "proof_a": bytes(proof[0]).hex()[:32]}
     emit(line)
     ctx.close()
+
+
+def accumulate_traffic(log_n, world):
+    """DRAM bytes per launch of the accumulate kernel from the committed ncu --set full capture (2^24, 1 GPU only)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")) as f:
+            t = json.load(f)
+        return t["dram_bytes_per_launch"] if (log_n == 24 and world == 1) else None
+    except Exception:
+        return None
 
 
 def measured_hbm_gbs():

@@ -83,8 +83,9 @@ struct XYZZ {
     return r;
   }
 
-  // dbl-2008-s-1, a = 0
-  __device__ __forceinline__ XYZZ dbl() const {
+  // dbl-2008-s-1, a = 0.  Not inlined (like add below): both are used only by the cold reduction / table kernels, where a call
+  // costs ~1 % and inlining them at every site multiplies the compile time of the G2 instantiation.
+  __device__ __noinline__ XYZZ dbl() const {
     if (is_inf() || y.is_zero()) return inf();
     F U = y.dbl();
     F V = U.sqr();
@@ -127,7 +128,7 @@ struct XYZZ {
   }
 
   // this += q: add-2008-s, 12M + 2S
-  __device__ __forceinline__ void add(const XYZZ& q) {
+  __device__ __noinline__ void add(const XYZZ& q) {
     if (q.is_inf()) return;
     if (is_inf()) {
       *this = q;

@@ -81,7 +81,7 @@ struct zkb_ctx {
   std::string err;
   unsigned long long launches = 0;
   int msm_c = 0;
-  int msm_slices = 4;                             // host-scalar MSMs >= 2^20: upload slices (env ZKB_MSM_SLICES, 1..8)
+  int msm_slices = 3;                             // host-scalar MSMs >= 2^20: upload slices (env ZKB_MSM_SLICES, 1..8)
   cudaStream_t copy_stream = nullptr;             // H2D slices of a host-scalar MSM, overlapped with compute
   cudaEvent_t copy_done[8] = {nullptr};
   zkb::Prof prof;

@@ -450,10 +450,11 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   L.key_bits = ilog2_ceil(size_t(L.nbuck) + 1);
   L.total = size_t(nwin) * n_slice;
   // Equal chunks of the sorted list, one per thread, sized so that the threads fill a WHOLE number of resident waves
-  // (no partial last wave) with ~512 entries each: few heads (one per thread), no tail.
+  // (no partial last wave): at least 4 waves so that the block scheduler evens out per-thread variance, ~512 entries per
+  // thread when the list is long (few heads: one per thread).
   size_t resident = size_t(sm_count) * T::THREADS_PER_SM;
   size_t waves = (L.total + resident * 256) / (resident * 512);
-  if (waves < 1) waves = 1;
+  if (waves < 4) waves = 4;
   L.chunk = (L.total + waves * resident - 1) / (waves * resident);
   if (L.chunk < 16) L.chunk = 16;
   L.nthreads = (L.total + L.chunk - 1) / L.chunk;
@@ -592,7 +593,26 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
                                 const uint8_t* scalars_host, uint32_t* scalars_dev, size_t n, int nslices,
                                 XYZZ<F>* out_xyzz, uint32_t* out_affine) {
   if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
-  const size_t per = (n + nslices - 1) / nslices;
+  // Slice k+1 is three times slice k: accumulating a point takes ~4x longer than copying its scalar, so every upload after
+  // the (small) first one hides behind the previous slice's compute.
+  if (nslices > ZKB_MAX_SLICES - 1) nslices = ZKB_MAX_SLICES - 1;
+  size_t bound[ZKB_MAX_SLICES + 1];
+  {
+    double wsum = 0, w = 1;
+    for (int k = 0; k < nslices; k++, w *= 3) wsum += w;
+    double acc = 0;
+    w = 1;
+    bound[0] = 0;
+    for (int k = 0; k < nslices; k++, w *= 3) {
+      acc += w;
+      size_t b = size_t(double(n) * acc / wsum);
+      b = (b + 255) & ~size_t(255);
+      bound[k + 1] = (k == nslices - 1 || b > n) ? n : b;
+    }
+  }
+  size_t per = 0;
+  for (int k = 0; k < nslices; k++)
+    if (bound[k + 1] - bound[k] > per) per = bound[k + 1] - bound[k];
   MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, per, nslices, ctx->stream);
   cudaError_t e = ctx->msm_ws.reserve(L.bytes);
   if (e != cudaSuccess) return e;
@@ -607,21 +627,19 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
   // the copy stream must not overwrite scalars_dev while earlier work on the compute stream still reads it
   cudaEventRecord(ctx->copy_done[ZKB_MAX_SLICES - 1], ctx->stream);
   cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done[ZKB_MAX_SLICES - 1], 0);
+  for (int k = 0; k < nslices; k++) {
+    size_t lo = bound[k], cnt = bound[k + 1] - bound[k];
+    if (cnt) cudaMemcpyAsync(scalars_dev + lo * 8, scalars_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
+    cudaEventRecord(ctx->copy_done[k], ctx->copy_stream);
+  }
   int used = 0;
   for (int k = 0; k < nslices; k++) {
-    size_t lo = size_t(k) * per;
-    if (lo >= n) break;
-    size_t cnt = lo + per <= n ? per : n - lo;
-    cudaMemcpyAsync(scalars_dev + lo * 8, scalars_host + lo * 32, cnt * 32, cudaMemcpyHostToDevice, ctx->copy_stream);
-    cudaEventRecord(ctx->copy_done[k], ctx->copy_stream);
-    used++;
-  }
-  for (int k = 0; k < used; k++) {
-    size_t lo = size_t(k) * per;
-    size_t cnt = lo + per <= n ? per : n - lo;
+    size_t lo = bound[k], cnt = bound[k + 1] - bound[k];
     cudaStreamWaitEvent(ctx->stream, ctx->copy_done[k], 0);
-    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, k);
+    if (!cnt) continue;
+    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, used);
     if (e != cudaSuccess) return e;
+    used++;
   }
   return msm_reduce<F>(ctx, L, used, out_xyzz, out_affine);
 }
