@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="msm_g1", choices=["msm_g1", "ntt", "msm_sweep", "prove"],
                     help="msm_g1 = the contract line (default); ntt / msm_sweep = BASELINE.json configs 3 / 2 as extra sweeps")
+    ap.add_argument("--concurrency", type=int, default=1, help="prove workload: contexts (host threads + streams) per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="prove workload: independent proofs per step over all GPUs (0 = one)")
     ap.add_argument("--logs", default="", help="comma-separated log2 sizes for the sweeps")
     return ap.parse_args()
 
@@ -441,15 +443,26 @@ def mimc_r1cs_numpy(np, num_perm, seed, rounds=91):
 
 
 def run_prove(args):
-    """BASELINE.json config 4: full Groth16 prove (7 NTTs + 4 G1 MSMs + 1 G2 MSM) of a forge-sized synthetic circuit."""
+    """BASELINE.json configs 4 and 5: full Groth16 proves (7 NTTs + 4 G1 MSMs + 1 G2 MSM each) of a synthetic MiMC circuit:
+    --log-n 21 = forge-sized (config 4, default); --log-n 13 --batch 64 = "batch of independent L2-sized proofs", one proof
+    per GPU at a time per context, proofs sharded over the ranks with no communication (config 5)."""
     import numpy as np
     import torch
+    import torch.distributed as dist
     import zelana_b200
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    ctx = zelana_b200.Context(0, stream=stream.cuda_stream)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K = max(1, args.concurrency)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
+    torch.cuda.set_stream(streams[0])
+    ctxs = [zelana_b200.Context(local, stream=st.cuda_stream) for st in streams]
+    ctx = ctxs[0]
     lg = args.log_n if args.log_n != 24 else 21
     num_perm = ((1 << lg) - 8) // (4 * 91)
     t0 = time.perf_counter()
@@ -467,35 +480,66 @@ def run_prove(args):
     del k
     zt = torch.from_numpy(z).pin_memory()
     z_np = zt.numpy().reshape(-1)
-    r = (123456789).to_bytes(32, "little")
-    sb = (987654321).to_bytes(32, "little")
+    batch = args.batch if args.batch > 0 else world * K
+    mine = [i for i in range(batch) if i % world == rank]          # proofs of this rank
+    rs = np.random.RandomState(7)
+    seeds = rs.randint(1, 1 << 62, size=(batch, 2), dtype=np.int64)  # (r, s) per proof, as StdRng(batch_id) would give
+
+    def prove_range(c, idxs, out):
+        for i in idxs:
+            out.append(c.prove(pk, m, z_np, int(seeds[i, 0]).to_bytes(32, "little"), int(seeds[i, 1]).to_bytes(32, "little")))
+
+    def step():
+        outs = [[] for _ in range(K)]
+        thr = [threading.Thread(target=prove_range, args=(ctxs[j], mine[j::K], outs[j])) for j in range(K)]
+        for t in thr:
+            t.start()
+        for t in thr:
+            t.join()
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(args.warmup):
-        proof = ctx.prove(pk, m, z_np, r, sb)
-    ctx.profile(True)
-    ctx.profile_reset()
-    l0 = ctx.launch_count()
-    sampler = ClockSampler(0)
+        outs = step()
+    if K == 1 and world == 1:
+        ctx.profile(True)
+        ctx.profile_reset()
+    l0 = sum(c.launch_count() for c in ctxs)
+    sampler = ClockSampler(local)
     sampler.start()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    barrier()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        proof = ctx.prove(pk, m, z_np, r, sb)
-    e1.record(stream)
-    torch.cuda.synchronize()
+        outs = step()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.steps
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
-    phases = {k2: v[0] / args.steps for k2, v in ctx.profile_read().items()}
-    line = {"workload": "groth16_prove_synthetic_mimc", "metric": "Groth16 proofs/s (forge-sized synthetic circuit)",
-            "value": 1e3 / ms, "unit": "proofs/s", "ms_per_proof": ms, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "config": {"log_domain": lg, "constraints": int(len(A[0]) - 1), "variables": int(nv), "mimc_permutations": num_perm,
-                       "key": "synthetic ([k_i]G points; timing-equivalent, proofs do not verify)",
-                       "through": "zkb_prove with host z (H2D inside the timed region)"},
-            "phase_ms_per_proof": phases, "gpu_launches": (ctx.launch_count() - l0) // max(args.steps, 1), "clocks": clocks,
-            "setup_s": {"r1cs_build_host": t_build, "key_generate_and_tables_gpu": t_key},
-            "proof_a": bytes(proof[0]).hex()[:32]}
-    emit(line)
-    ctx.close()
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    phases = {k2: v[0] / args.steps / max(len(mine), 1) for k2, v in ctx.profile_read().items()} if (K == 1 and world == 1) else None
+    launches = (sum(c.launch_count() for c in ctxs) - l0) // max(args.steps, 1)
+    if rank == 0:
+        line = {"workload": "groth16_prove_synthetic_mimc", "metric": "Groth16 proofs/s (synthetic MiMC circuit, domain 2^%d)" % lg,
+                "value": batch / dt, "unit": "proofs/s", "ms_per_step": dt * 1e3, "ms_per_proof_per_context": dt * 1e3 / max(len(mine[0::K]), 1),
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "scaling": "weak" if args.batch == 0 else "strong",
+                "config": {"log_domain": lg, "constraints": int(len(A[0]) - 1), "variables": int(nv), "mimc_permutations": num_perm,
+                           "proofs_per_step": batch, "contexts_per_gpu": K,
+                           "key": "synthetic ([k_i]G points; timing-equivalent, proofs do not verify)",
+                           "through": "zkb_prove with host z (H2D inside the timed region); wall clock around the batch, max over ranks"},
+                "phase_ms_per_proof": phases, "gpu_launches": launches, "clocks": clocks,
+                "setup_s": {"r1cs_build_host": t_build, "key_generate_and_tables_gpu": t_key},
+                "proof_a": bytes(outs[0][0][0]).hex()[:32] if outs[0] else None}
+        emit(line)
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def accumulate_traffic(log_n, world):
@@ -572,8 +616,21 @@ def run_sweeps(args):
             sc = rand_fr_range(torch, SEED_SCALARS + lg, 0, n, dev)
             out = torch.zeros(64, dtype=torch.uint8, device=dev)
             ms = timed(lambda: ctx.msm_g1_dev(bases, sc, n, out_affine_dev=out))
-            rows.append({"log_n": lg, "ms": ms, "points_per_s": n / (ms * 1e-3),
-                         "int32_frac_normalised": MUL32_PER_POINT * n / (ms * 1e-3) / peak_int})
+            row = {"log_n": lg, "ms": ms, "points_per_s": n / (ms * 1e-3),
+                   "int32_frac_normalised": MUL32_PER_POINT * n / (ms * 1e-3) / peak_int}
+            if lg >= 20:
+                # witness-like scalars: 50 % zero, 25 % one, 25 % uniform -- one bucket holds a quarter of the points
+                g = torch.Generator(device=dev)
+                g.manual_seed(0x717 + lg)
+                u = torch.rand(n, device=dev, generator=g)
+                wl = sc.clone()
+                wl[u < 0.5] = 0
+                one = torch.zeros(8, dtype=torch.int32, device=dev)
+                one[0] = 1
+                wl[(u >= 0.5) & (u < 0.75)] = one
+                row["witness_like_ms"] = timed(lambda: ctx.msm_g1_dev(bases, wl, n, out_affine_dev=out))
+                del wl, u
+            rows.append(row)
             bases.free()
             del sc
         line = {"workload": "bn254_g1_msm_sweep", "unit": "ms", "rows": rows, "steps": args.steps, "warmup": args.warmup,

@@ -86,8 +86,11 @@ struct zkb_ctx {
   cudaEvent_t copy_done[8] = {nullptr};
   zkb::Prof prof;
   zkb::DevBuf msm_ws;                             // MSM scratch (keys, sort space, buckets)
+  zkb::DevBuf msm_ws2;                            // second MSM scratch: the G2 MSM of a prove runs on aux_stream
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_inputs = nullptr, ev_aux_done = nullptr;
   zkb::DevBuf scal, res, tmp0, tmp1, tmp2, flag;  // staging
-  zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzl, prs, ppts;  // prove scratch
+  zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzb, pzl, prs, ppts;  // prove scratch
   void* fr_state = nullptr;                       // NTT tables, owned by fr.cu
   void* g1_table = nullptr;                       // fixed-base tables, owned by g1.cu / g2.cu
   void* g2_table = nullptr;

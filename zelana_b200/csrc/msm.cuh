@@ -24,7 +24,7 @@
 //                               steps), 32x shorter per level (a bucket holding millions of entries -- scalars 0/1 of
 //                               real witnesses -- is folded in log_32 steps).
 //   5. msm_bucket_seg_kernel    sum_b (b+1) B_b by segments of S = 32 buckets: W_s = local weighted sum, T_s = plain
-//                               sum; sum_b (b+1) B_b = sum_s W_s + S * sum_s s T_s.
+//                               sum; sum_b (b+1) B_b = sum_s W_s + S * sum_s s T_s.  (S shrinks when there are few buckets.)
 //      msm_rowcol_kernel        s = 256 hi + lo:  sum_s s T_s = 256 sum_hi hi Row_hi + sum_lo lo Col_lo (tree sums).
 //      msm_plane_kernel         the two short weighted sums by bit planes: sum_i i A_i = sum_y 2^y (sum of A_i over i
 //                               with bit y set); no scalar multiplications, no long dependent chains.
@@ -43,7 +43,7 @@ static inline int ilog2_ceil(size_t n) {
   return l;
 }
 
-constexpr int MSM_SEG_LOG = 5;   // bucket reduction: segments of 32 buckets
+constexpr int MSM_SEG_LOG_MAX = 5;  // bucket reduction: segments of up to 32 buckets (shorter when there are few buckets)
 constexpr int MSM_COL_LOG = 8;   // segment totals viewed as rows x 256 columns
 
 static inline int msm_windows_for(int c) { return (255 + c - 1) / c; }  // nwin * c >= 255: the top digit absorbs the carry
@@ -263,14 +263,15 @@ msm_heads_warp_kernel(const XYZZ<F>* __restrict__ in, const uint32_t* __restrict
 }
 
 // ------------------------------------------------------------------------------------------- 5. bucket reduction
-// R(A) = sum_{b < m} (b + 1) A[b].  Segment s of S = 2^MSM_SEG_LOG entries: W[s] = sum_i (i + 1) A[sS + i], T[s] = sum_i A[sS + i];
+// R(A) = sum_{b < m} (b + 1) A[b].  Segment s of S = 2^seg_log entries: W[s] = sum_i (i + 1) A[sS + i], T[s] = sum_i A[sS + i];
 // then R(A) = sum_s W[s] + S * R(T[1..]).
 template <class F>
 __global__ void __launch_bounds__(64)
-msm_bucket_seg_kernel(const XYZZ<F>* __restrict__ in, size_t m, XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ T, size_t nseg) {
+msm_bucket_seg_kernel(const XYZZ<F>* __restrict__ in, size_t m, XYZZ<F>* __restrict__ W, XYZZ<F>* __restrict__ T, size_t nseg,
+                      int seg_log) {
   size_t s = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
-  constexpr int S = 1 << MSM_SEG_LOG;
+  const int S = 1 << seg_log;
   size_t b0 = s * S;
   XYZZ<F> run = XYZZ<F>::inf(), w = XYZZ<F>::inf();
   for (int i = S - 1; i >= 0; i--) {
@@ -369,7 +370,7 @@ __device__ inline void store_affine_canonical<Fq2>(const Affine<Fq2>& a, uint32_
 // combining) and the canonical affine bytes.
 template <class F>
 __global__ void __launch_bounds__(32)
-msm_final_kernel(const XYZZ<F>* __restrict__ planes, int row_planes, int col_planes, XYZZ<F>* __restrict__ out_xyzz,
+msm_final_kernel(const XYZZ<F>* __restrict__ planes, int row_planes, int col_planes, int seg_log, XYZZ<F>* __restrict__ out_xyzz,
                  uint32_t* __restrict__ out_affine) {
   const int lane = threadIdx.x;
   const int y = lane & 15, grp = lane >> 4;
@@ -385,7 +386,7 @@ msm_final_kernel(const XYZZ<F>* __restrict__ planes, int row_planes, int col_pla
   XYZZ<F> acc = row_total;             // sum_y 2^y RowPlane_y
   for (int k = 0; k < MSM_COL_LOG; k++) acc = acc.dbl();
   acc.add(v);                          // + column part
-  for (int k = 0; k < MSM_SEG_LOG; k++) acc = acc.dbl();
+  for (int k = 0; k < seg_log; k++) acc = acc.dbl();
   acc.add(load_xyzz(planes + 32));
   if (out_xyzz) store_xyzz(out_xyzz, acc);
   if (out_affine) store_affine_canonical<F>(acc.to_affine_vartime(), out_affine);
@@ -429,7 +430,7 @@ msm_bucket_merge_kernel(XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict
 template <class F>
 struct MsmLayout {
   using P = XYZZ<F>;
-  int c = 0, nwin = 0, nslices = 1, key_bits = 0, row_planes = 0, col_planes = 0;
+  int c = 0, nwin = 0, nslices = 1, key_bits = 0, row_planes = 0, col_planes = 0, seg_log = 0;
   uint32_t nbuck = 0, sentinel = 0;
   size_t n_slice = 0, total = 0, chunk = 0, nthreads = 0, nseg = 0, rows = 0, sort_tmp = 0, bytes = 0;
   size_t o_k0, o_v0, o_k1, o_v1, o_tmp, o_buck, o_h0, o_hk0, o_h1, o_hk1, o_W, o_T, o_part, o_planes;
@@ -439,7 +440,6 @@ template <class F>
 static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, int nslices, cudaStream_t st) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
-  constexpr int S = 1 << MSM_SEG_LOG;
   MsmLayout<F> L;
   L.c = c;
   L.nwin = nwin;
@@ -459,6 +459,12 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   if (L.chunk < 16) L.chunk = 16;
   L.nthreads = (L.total + L.chunk - 1) / L.chunk;
   // bucket reduction: segments of S buckets, then row / column sums of the nseg segment totals and their bit planes
+  // enough segments to occupy the GPU (>= 2^13 threads) before making them long: with few buckets a 32-long segment is a
+  // 64-addition dependent chain on a handful of threads -- pure latency (it dominated small proofs)
+  L.seg_log = c - 1 - 13;
+  L.seg_log = L.seg_log < 1 ? 1 : (L.seg_log > MSM_SEG_LOG_MAX ? MSM_SEG_LOG_MAX : L.seg_log);
+  if (c - 1 < L.seg_log) L.seg_log = c - 1;
+  const size_t S = size_t(1) << L.seg_log;
   L.nseg = (size_t(L.nbuck) + S - 1) / S;
   L.rows = (L.nseg + (size_t(1) << MSM_COL_LOG) - 1) >> MSM_COL_LOG;
   L.row_planes = L.rows > 1 ? ilog2_ceil(L.rows) : 0;
@@ -557,10 +563,10 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, int nslices_used, XY
     msm_bucket_merge_kernel<F><<<unsigned((size_t(L.nbuck) + 63) / 64), 64, 0, st>>>(buckets, buckets + L.nbuck, L.nbuck, nslices_used - 1);
     ctx->launches++;
   }
-  msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg);
+  msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg, L.seg_log);
   msm_rowcol_kernel<F, 64><<<unsigned(2 * L.rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
   msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, L.rows, planes);
-  msm_final_kernel<F><<<1, 32, 0, st>>>(planes, L.row_planes, L.col_planes, out_xyzz, out_affine);
+  msm_final_kernel<F><<<1, 32, 0, st>>>(planes, L.row_planes, L.col_planes, L.seg_log, out_xyzz, out_affine);
   ctx->launches += 4;
   return cudaGetLastError();
 }

@@ -4,6 +4,7 @@
 #include "internal.h"
 
 #include <cstdlib>
+#include <utility>
 
 using namespace zkb;
 
@@ -96,6 +97,14 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->msm_ws.release();
+  ctx->msm_ws2.release();
+  ctx->pzb.release();
+  if (ctx->aux_stream) {
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamDestroy(ctx->aux_stream);
+    cudaEventDestroy(ctx->ev_inputs);
+    cudaEventDestroy(ctx->ev_aux_done);
+  }
   DevBuf* bufs[] = {&ctx->scal, &ctx->res, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->flag, &ctx->pz, &ctx->pzm, &ctx->pwa,
                     &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts};
   for (DevBuf* b : bufs) b->release();
@@ -350,6 +359,7 @@ static int reserve_prove_bufs(zkb_ctx* ctx, size_t n, size_t nv, size_t nw) {
   CUDA_TRY(ctx, ctx->pwc.reserve(n * 32));
   CUDA_TRY(ctx, ctx->ph.reserve(n * 32));
   CUDA_TRY(ctx, ctx->pza.reserve((nv + 2) * 32));
+  CUDA_TRY(ctx, ctx->pzb.reserve((nv + 3) * 32));
   CUDA_TRY(ctx, ctx->pzl.reserve((nw + 1) * 32));
   CUDA_TRY(ctx, ctx->prs.reserve(64));
   CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + 64 + 128 + 64));
@@ -496,17 +506,6 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
   CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
 
-  // h = witness_map_from_matrices
-  WitnessBufs w{z, ctx->pzm.as<Fr>(), ctx->pwa.as<Fr>(), ctx->pwb.as<Fr>(), ctx->pwc.as<Fr>()};
-  ZKB_TRY(witness_map_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, w, ctx->ph.as<Fr>()));
-
-  // scalar vectors of the folded MSMs
-  Fr* za = ctx->pza.as<Fr>();
-  Fr* zl = ctx->pzl.as<Fr>();
-  if (nv > 1) CUDA_TRY(ctx, cudaMemcpyAsync(za, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, st));
-  if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(zl, z + ni, nw * 32, cudaMemcpyDeviceToDevice, st));
-  ZKB_TRY(prove_tail_scalars(ctx, rs, rs + 1, za + (nv - 1), zl + nw));
-
   char* pts = static_cast<char*>(ctx->ppts.p);
   XYZZ<Fq>* pA = reinterpret_cast<XYZZ<Fq>*>(pts);
   XYZZ<Fq>* pB1 = pA + 1;
@@ -516,19 +515,67 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
   uint32_t* oB = oA + 16;
   uint32_t* oC = oB + 32;
 
-  // A = MSM(a_ext, z[1..] || 1 || 1 || r)
-  ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za, nv + 2, oA, pA)));
-  // H: msm_bigint truncates to the shorter of (h_query, h)
-  size_t hn = pk->nh < n ? pk->nh : n;
-  ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->h, 0, ctx->ph.p, hn, nullptr, pH)));
-  // L = MSM(l_query || delta_1, aux || -(r s))
-  ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl, nw + 1, nullptr, pL)));
-  // B: same scalars with s in the last slot
-  CUDA_TRY(ctx, cudaMemcpyAsync(za + (nv + 1), rs + 1, 32, cudaMemcpyDeviceToDevice, st));
-  ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, za, nv + 2, nullptr, pB1)));
-  ZKB_TRY((msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, za, nv + 2, oB, nullptr)));
-  // C = s A + r B1 + L + H
-  ZKB_TRY(prove_assemble_c(ctx, pA, pB1, pL, pH, rs, rs + 1, oC));
+  // B in G2 needs only z and s, not h: it runs on a second stream (own MSM scratch) next to the witness map and the G1
+  // MSMs, filling the SMs those leave idle in their sort / reduction phases.
+  if (!ctx->aux_stream) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_aux_done, cudaEventDisableTiming));
+  }
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, st));
+  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_inputs, 0));
+  {
+    std::swap(ctx->stream, ctx->aux_stream);
+    std::swap(ctx->msm_ws, ctx->msm_ws2);
+    Fr* zb = ctx->pzb.as<Fr>();  // z[1..] || 1 || 1 || s  (+ one scratch slot)
+    int rc = ZKB_OK;
+    if (nv > 1 && cudaMemcpyAsync(zb, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    if (rc == ZKB_OK) rc = prove_tail_scalars(ctx, rs + 1, rs + 1, zb + (nv - 1), zb + (nv + 2));
+    if (rc == ZKB_OK) rc = msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb, nv + 2, oB, nullptr);
+    if (rc == ZKB_OK && cudaEventRecord(ctx->ev_aux_done, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    std::swap(ctx->stream, ctx->aux_stream);
+    std::swap(ctx->msm_ws, ctx->msm_ws2);
+    if (rc != ZKB_OK) {
+      cudaGetLastError();
+      cudaStreamSynchronize(ctx->aux_stream);
+      if (rc == ZKB_ERR_CUDA) ctx->err = "zkb_prove: CUDA error while queueing the G2 MSM";
+      return rc;
+    }
+  }
+
+  // h = witness_map_from_matrices
+  WitnessBufs w{z, ctx->pzm.as<Fr>(), ctx->pwa.as<Fr>(), ctx->pwb.as<Fr>(), ctx->pwc.as<Fr>()};
+  int wrc = witness_map_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, w, ctx->ph.as<Fr>());
+
+  // scalar vectors of the folded G1 MSMs
+  Fr* za = ctx->pza.as<Fr>();
+  Fr* zl = ctx->pzl.as<Fr>();
+  auto g1_part = [&]() -> int {
+    ZKB_TRY(wrc);
+    if (nv > 1) CUDA_TRY(ctx, cudaMemcpyAsync(za, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, st));
+    if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(zl, z + ni, nw * 32, cudaMemcpyDeviceToDevice, st));
+    ZKB_TRY(prove_tail_scalars(ctx, rs, rs + 1, za + (nv - 1), zl + nw));
+    // A = MSM(a_ext, z[1..] || 1 || 1 || r)
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za, nv + 2, oA, pA)));
+    // H: msm_bigint truncates to the shorter of (h_query, h)
+    size_t hn = pk->nh < n ? pk->nh : n;
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->h, 0, ctx->ph.p, hn, nullptr, pH)));
+    // L = MSM(l_query || delta_1, aux || -(r s))
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl, nw + 1, nullptr, pL)));
+    // B1: same scalars with s in the last slot
+    CUDA_TRY(ctx, cudaMemcpyAsync(za + (nv + 1), rs + 1, 32, cudaMemcpyDeviceToDevice, st));
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, za, nv + 2, nullptr, pB1)));
+    // C = s A + r B1 + L + H
+    ZKB_TRY(prove_assemble_c(ctx, pA, pB1, pL, pH, rs, rs + 1, oC));
+    return ZKB_OK;
+  };
+  int grc = g1_part();
+  // join the G2 stream in every case before returning: its work reads buffers owned by this context
+  cudaStreamWaitEvent(st, ctx->ev_aux_done, 0);
+  if (grc != ZKB_OK) {
+    cudaStreamSynchronize(ctx->aux_stream);
+    return grc;
+  }
   CUDA_TRY(ctx, cudaMemcpyAsync(out_a, oA, 64, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_b, oB, 128, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_c, oC, 64, cudaMemcpyDeviceToHost, st));
