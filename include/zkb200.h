@@ -159,6 +159,11 @@ typedef struct {
 } zkb_pk_desc;
 
 int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* desc, int validate, zkb_pk** out);
+/* The key exactly as the reference stores it: `ProvingKey::<Bn254>::serialize_compressed` bytes (prover/src/bin/keygen.rs:100),
+ * i.e. what Groth16Prover::from_bytes / from_files reads (prover.rs:263-286).  Points are decompressed (square roots) and
+ * validated (on curve; G2 in the prime-order subgroup, as Validate::Yes does) on the GPU.  Errors: ZKB_ERR_SHAPE for a
+ * truncated / over-long buffer, ZKB_ERR_NOT_CANONICAL for a bad point (zkb_last_error says which). */
+int zkb_pk_load_compressed(zkb_ctx* ctx, const uint8_t* ark_bytes, size_t len, int validate, zkb_pk** out);
 void zkb_pk_free(zkb_pk* pk);
 /* BENCHMARK ONLY: a key of the given shape whose query points are [k_i] G for k_len >= max(num_vars + 2, h_len) + 4
  * canonical Fr scalars in device memory (no trusted setup; proofs do not verify, timing is that of a real key). */

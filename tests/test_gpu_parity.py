@@ -439,3 +439,78 @@ def test_msm_g1_host_sliced_path_2p21(ctx):
     assert ctx.msm_g1(bases, s[:m]) == orc.G1Bases.from_raw(bases.read(0, m)).msm(s[:m])
     # twice in a row on the same context (slice buffers and events are reused)
     assert ctx.msm_g1(bases, s) == out
+
+
+# ----------------------------------------------------------------------------- compressed key load (row a11)
+def test_pk_load_compressed_matches_uncompressed_and_oracle(ctx, mimc_setup):
+    """Groth16Prover::from_bytes path: the ark-serialize COMPRESSED ProvingKey is decompressed + validated on the GPU;
+    proofs made with it equal the oracle's.  The key holds infinity points (variables absent from B) and both y signs."""
+    from oracle import rng as orng
+    r1cs, z, pk = mimc_setup
+    blob = pk.serialize_compressed()
+    assert g16.ProvingKey.deserialize_compressed(blob).serialize_compressed() == blob
+    assert any(p is None for p in pk.b_g1_query)
+    m = ctx.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+    dpk = ctx.proving_key_compressed(blob)
+    rng = StdRng.seed_from_u64(3)
+    r, s = orng.rand_fr(rng), orng.rand_fr(rng)
+    got = ctx.prove(dpk, m, fr_bytes(z), fr_bytes([r]), fr_bytes([s]))
+    ref = g16.prove_with_rs(pk, r1cs, z, r, s)
+    assert got == (bn.g1_to_raw(ref.a), bn.g2_to_raw(ref.b), bn.g1_to_raw(ref.c))
+    assert g16.verify(pk.vk, [z[1]], ref)
+
+
+def test_pk_load_compressed_square_circuit_fixture(ctx):
+    """keygen -> serialize_compressed -> from_bytes -> prove: the reference's committed proof again, via the compressed key."""
+    import json, os
+    from conftest import REF_FIXTURES
+    from oracle import rng as orng
+    r1cs, z = g16.square_circuit(7)
+    rng = StdRng.seed_from_u64(42)
+    pk = g16.circuit_specific_setup(r1cs, rng)
+    r, s = orng.rand_fr(rng), orng.rand_fr(rng)
+    m = ctx.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+    a, b, c = ctx.prove(ctx.proving_key_compressed(pk.serialize_compressed()), m, fr_bytes(z), fr_bytes([r]), fr_bytes([s]))
+    proof = g16.Proof(bn.g1_from_raw(a), bn.g2_from_raw(b), bn.g1_from_raw(c))
+    pc = json.load(open(os.path.join(REF_FIXTURES, "proof_for_onchain.json")))["proof_components"]
+    assert proof.serialize_uncompressed() == bytes(pc["pi_a"]) + bytes(pc["pi_b"]) + bytes(pc["pi_c"])
+
+
+def test_pk_load_compressed_rejects_what_arkworks_rejects(ctx, mimc_setup):
+    import zelana_b200
+    _, _, pk = mimc_setup
+    blob = bytearray(pk.serialize_compressed())
+    vk_len = 32 + 64 * 3 + 8 + 32 * len(pk.vk.gamma_abc_g1)
+    a_off = vk_len + 64 + 8                      # first a_query point
+
+    def expect(buf, code, *, validate=True):
+        with pytest.raises(zelana_b200.ZkbError) as e:
+            ctx.proving_key_compressed(bytes(buf), validate=validate)
+        assert e.value.code == code, str(e.value)
+
+    expect(blob[:-1], -6)                        # truncated
+    expect(blob + b"\x00", -6)                   # trailing byte
+    bad = bytearray(blob); bad[a_off + 31] |= 0xC0
+    expect(bad, -5)                              # both flags set
+    bad = bytearray(blob); bad[a_off:a_off + 32] = (bn.P + 1).to_bytes(32, "little")
+    expect(bad, -5)                              # x >= p
+    x = 1
+    while bn.fq_sqrt((x ** 3 + 3) % bn.P) is not None:
+        x += 1
+    bad = bytearray(blob); bad[a_off:a_off + 32] = x.to_bytes(32, "little")
+    expect(bad, -5)                              # x^3 + 3 is not a square
+    # a G2 point on the twist but outside the prime-order subgroup (in b_g2_query[0])
+    b2_off = vk_len + 64 + 8 + 32 * len(pk.a_query) + 8 + 32 * len(pk.b_g1_query) + 8
+    xx = 1
+    while True:
+        cand = (xx, 0)
+        y = bn.f2_sqrt(bn.f2_add(bn.f2_mul(bn.f2_sqr(cand), cand), bn.B_G2))
+        if y is not None and not bn.g2_in_subgroup((cand, y)):
+            break
+        xx += 1
+    bad = bytearray(blob); bad[b2_off:b2_off + 64] = bn.g2_serialize((cand, y))
+    expect(bad, -5)                              # not in the subgroup
+    ctx.proving_key_compressed(bytes(bad), validate=False)   # Validate::No skips exactly that check
+    # gamma_abc is not used by the prover but is still validated
+    bad = bytearray(blob); bad[32 + 64 * 3 + 8:32 + 64 * 3 + 8 + 32] = x.to_bytes(32, "little")
+    expect(bad, -5)

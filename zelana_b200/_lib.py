@@ -81,6 +81,7 @@ SIGNATURES = {
     "zkb_r1cs_log_domain": (_I, [_P]),
     "zkb_witness_map": (_I, [_P, _P, _P, _P]),
     "zkb_pk_load": (_I, [_P, C.POINTER(PkDesc), _I, C.POINTER(_P)]),
+    "zkb_pk_load_compressed": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
     "zkb_pk_free": (None, [_P]),
     "zkb_pk_synthetic": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, C.POINTER(_P)]),
     "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),

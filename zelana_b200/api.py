@@ -190,6 +190,15 @@ class Context:
     def proving_key(self, **parts):
         return ProvingKeyDev(self, **parts)
 
+    def proving_key_compressed(self, ark_bytes, validate=True):
+        """ProvingKey::deserialize_compressed on the GPU: the bytes keygen wrote (prover/src/bin/keygen.rs:100)."""
+        p, keep = _buf(ark_bytes)
+        h = C.c_void_p()
+        self._check(self.lib.zkb_pk_load_compressed(self.h, p, len(keep), int(validate), C.byref(h)))
+        pk = ProvingKeyDev.__new__(ProvingKeyDev)
+        pk.ctx, pk.h = self, h
+        return pk
+
     def proving_key_synthetic(self, num_vars, num_witness, h_len, k_dev, k_len):
         """Benchmark-only key of the given shape (query points [k_i] G from device scalars); proofs do not verify."""
         h = C.c_void_p()

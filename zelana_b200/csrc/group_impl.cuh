@@ -78,6 +78,105 @@ __global__ void affine_export_kernel(const Affine<F>* in, uint32_t* out, size_t 
   store_affine_canonical<F>(in[i], out + i * (sizeof(Affine<F>) / 4));
 }
 
+// ---- ark-serialize COMPRESSED points (Groth16Prover::from_bytes -> ProvingKey::deserialize_compressed, prover.rs:263-277)
+// Fq: p = 3 mod 4, sqrt(a) = a^((p+1)/4).  Values in and out are in Montgomery form.
+__device__ inline bool fq_sqrt(const Fq& a, Fq& out) {
+  const uint32_t e[8] = {0xb61f3f52u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu};
+  out = a.pow_words(e);
+  return out.sqr() == a;
+}
+// "y is the larger of {y, -y}" on canonical integers: y > (p - 1) / 2
+__device__ inline bool fq_is_larger(const Fq& y_mont) {
+  const uint32_t h[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+  Fq y = y_mont.from_mont();
+  for (int i = 7; i >= 0; i--) {
+    if (y.v[i] > h[i]) return true;
+    if (y.v[i] < h[i]) return false;
+  }
+  return false;
+}
+// Fq2 square root, complex method (any root; the caller picks the sign)
+__device__ inline bool fq2_sqrt(const Fq2& a, Fq2& out) {
+  if (a.c1.is_zero()) {
+    Fq s;
+    if (fq_sqrt(a.c0, s)) {
+      out = {s, Fq::zero()};
+      return true;
+    }
+    if (fq_sqrt(a.c0.neg(), s)) {
+      out = {Fq::zero(), s};
+      return true;
+    }
+    return false;
+  }
+  Fq alpha;
+  if (!fq_sqrt(a.c0.sqr() + a.c1.sqr(), alpha)) return false;
+  Fq half;
+  const uint32_t hw[8] = {0x4f060572u, 0x87bee7d2u, 0x2f1c6ae5u, 0xd0fd2addu, 0xfcfd4f44u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
+  for (int i = 0; i < 8; i++) half.v[i] = hw[i];  // 1/2 in Montgomery form
+  Fq x0;
+  if (!fq_sqrt((a.c0 + alpha) * half, x0)) {
+    if (!fq_sqrt((a.c0 - alpha) * half, x0)) return false;
+  }
+  Fq x1 = a.c1 * x0.dbl().inverse();
+  out = {x0, x1};
+  return out.sqr() == a;
+}
+
+template <class F> struct Compressed;
+template <> struct Compressed<Fq> {
+  static constexpr int WORDS = 8;
+  static __device__ __forceinline__ bool load_x(const uint32_t* w, Fq& x) {
+    for (int i = 0; i < 8; i++) x.v[i] = w[i];
+    x.v[7] &= 0x3fffffffu;
+    return fp_is_canonical(x);
+  }
+  static __device__ __forceinline__ bool sqrt(const Fq& a, Fq& out) { return fq_sqrt(a, out); }
+  static __device__ __forceinline__ bool is_larger(const Fq& y) { return fq_is_larger(y); }
+  static constexpr bool SUBGROUP_CHECK = false;  // cofactor 1
+};
+template <> struct Compressed<Fq2> {
+  static constexpr int WORDS = 16;
+  static __device__ __forceinline__ bool load_x(const uint32_t* w, Fq2& x) {
+    for (int i = 0; i < 8; i++) { x.c0.v[i] = w[i]; x.c1.v[i] = w[8 + i]; }
+    x.c1.v[7] &= 0x3fffffffu;
+    return fp_is_canonical(x.c0) && fp_is_canonical(x.c1);
+  }
+  static __device__ __forceinline__ bool sqrt(const Fq2& a, Fq2& out) { return fq2_sqrt(a, out); }
+  // Fq2 ordering compares c1 first, then c0
+  static __device__ __forceinline__ bool is_larger(const Fq2& y) { return y.c1.is_zero() ? fq_is_larger(y.c0) : fq_is_larger(y.c1); }
+  static constexpr bool SUBGROUP_CHECK = true;
+};
+
+// x || flags (bit 7 of the last byte: y is the larger root, bit 6: infinity) -> Montgomery affine.
+// bad: 1 non-canonical x, 2 x not on the curve, 3 both flags set, 4 not in the prime-order subgroup.
+template <class F>
+__global__ void affine_decompress_kernel(const uint32_t* __restrict__ in, Affine<F>* __restrict__ out, size_t n, int validate,
+                                         int* bad) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  constexpr int W = Compressed<F>::WORDS;
+  const uint32_t* w = in + i * W;
+  const uint32_t flags = w[W - 1] >> 30;
+  if (flags == 3u) { atomicExch(bad, 3); return; }
+  if (flags & 1u) {  // infinity
+    out[i] = Affine<F>::inf();
+    return;
+  }
+  F x;
+  if (!Compressed<F>::load_x(w, x)) { atomicExch(bad, 1); return; }
+  x = x.to_mont();
+  F y;
+  if (!Compressed<F>::sqrt(x.sqr() * x + CurveB<F>::b(), y)) { atomicExch(bad, 2); return; }
+  if (Compressed<F>::is_larger(y) != bool(flags & 2u)) y = y.neg();
+  Affine<F> p{x, y};
+  if (validate && Compressed<F>::SUBGROUP_CHECK) {
+    const uint32_t r[8] = {FrCfg::M0, FrCfg::M1, FrCfg::M2, FrCfg::M3, FrCfg::M4, FrCfg::M5, FrCfg::M6, FrCfg::M7};
+    if (!XYZZ<F>::from_affine(p).mul_words(r).is_inf()) { atomicExch(bad, 4); return; }
+  }
+  out[i] = p;
+}
+
 template <class F>
 __global__ void scalar_mul_kernel(const Affine<F>* pts, const uint32_t* scalars, size_t n, uint32_t* out) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -211,6 +310,40 @@ int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, t
   if (n) {
     int s = import_points<F>(ctx, host, n, validate, h->p);
     if (s == ZKB_OK) s = build_window_tables<F>(ctx, h);
+    if (s != ZKB_OK) {
+      cudaFree(h->p);
+      delete h;
+      return s;
+    }
+  }
+  *out = h;
+  return ZKB_OK;
+}
+
+// Same from ark-serialize compressed encodings (32 B per G1 point, 64 B per G2 point).
+template <class F>
+int bases_load_compressed_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out) {
+  using H = typename GroupOf<F>::Bases;
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || (!host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_load_compressed: bad argument");
+  *out = nullptr;
+  ZKB_TRY(set_device(ctx));
+  H* h = nullptr;
+  ZKB_TRY(bases_alloc<F>(ctx, n, &h));
+  if (n) {
+    const size_t bytes = n * sizeof(Affine<F>) / 2;
+    int s = ZKB_OK;
+    auto run = [&]() -> int {
+      CUDA_TRY(ctx, ctx->tmp0.reserve(bytes));
+      ZKB_TRY(clear_flag(ctx));
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+      affine_decompress_kernel<F><<<blocks_for(n, 64), 64, 0, ctx->stream>>>(ctx->tmp0.as<uint32_t>(), h->p, n, validate, ctx->flag.as<int>());
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaGetLastError());
+      ZKB_TRY(check_flag(ctx, "compressed point"));
+      return build_window_tables<F>(ctx, h);
+    };
+    s = run();
     if (s != ZKB_OK) {
       cudaFree(h->p);
       delete h;
@@ -383,6 +516,7 @@ int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
 #define ZKB_INSTANTIATE_GROUP(F)                                                                                            \
   template int import_points<F>(zkb_ctx*, const uint8_t*, size_t, int, Affine<F>*);                                        \
   template int bases_load_impl<F>(zkb_ctx*, const uint8_t*, size_t, int, GroupOf<F>::Bases**);                              \
+  template int bases_load_compressed_impl<F>(zkb_ctx*, const uint8_t*, size_t, int, GroupOf<F>::Bases**);                   \
   template int bases_generate_impl<F>(zkb_ctx*, const void*, size_t, GroupOf<F>::Bases**);                                  \
   template int bases_read_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, size_t, uint8_t*);                            \
   template void bases_free_impl<F>(GroupOf<F>::Bases*);                                                                     \

@@ -167,6 +167,7 @@ template <> struct GroupOf<Fq2> { using Bases = zkb_g2_bases; static constexpr i
 // group_impl.cuh, instantiated for Fq in g1.cu and Fq2 in g2.cu
 template <class F> int import_points(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, Affine<F>* dst);
 template <class F> int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out);
+template <class F> int bases_load_compressed_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, typename GroupOf<F>::Bases** out);
 template <class F> int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename GroupOf<F>::Bases** out);
 template <class F> int bases_read_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* b, size_t offset, size_t n, uint8_t* out_host);
 template <class F> void bases_free_impl(typename GroupOf<F>::Bases* b);

@@ -4,6 +4,7 @@
 #include "internal.h"
 
 #include <cstdlib>
+#include <initializer_list>
 #include <utility>
 
 using namespace zkb;
@@ -17,6 +18,8 @@ int check_flag(zkb_ctx* ctx, const char* what) {
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   if (h == 1) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: field element >= modulus", what);
   if (h == 2) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: point not on curve", what);
+  if (h == 3) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: both the infinity and the sign flag are set", what);
+  if (h == 4) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: point not in the prime-order subgroup", what);
   return ZKB_OK;
 }
 
@@ -449,6 +452,109 @@ extern "C" int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, zkb
   if (s == ZKB_OK) s = load_ext<Fq2>(ctx, d->b_g2_query, d->b_g2_len, true, eb2, 2, validate, &pk->b2_ext);
   if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->l_query, d->l_len, false, el, 1, validate, &pk->l_ext);
   if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->h_query, d->h_len, false, nullptr, 0, validate, &pk->h);
+  if (s != ZKB_OK) {
+    zkb_pk_free(pk);
+    return s;
+  }
+  *out = pk;
+  return ZKB_OK;
+}
+
+// ProvingKey::<Bn254>::deserialize_compressed (Groth16Prover::from_bytes, prover.rs:263-277): ark-serialize layout
+//   vk { alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1: Vec<G1> }, beta_g1, delta_g1, a_query, b_g1_query,
+//   b_g2_query: Vec<G2>, h_query, l_query      (Vec<T> = u64 LE length || elements; G1 32 B, G2 64 B, flags in the top bits).
+// Every point is decompressed (square root, sign choice) and validated (on curve; G2: prime-order subgroup) on the GPU.
+extern "C" int zkb_pk_load_compressed(zkb_ctx* ctx, const uint8_t* bytes, size_t len, int validate, zkb_pk** out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!bytes || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_load_compressed: null argument");
+  *out = nullptr;
+  size_t off = 0;
+  auto need = [&](size_t k) { return off + k <= len; };
+  auto fixed = [&](size_t k, const uint8_t** p) {
+    if (!need(k)) return false;
+    *p = bytes + off;
+    off += k;
+    return true;
+  };
+  auto vec = [&](size_t elem, const uint8_t** p, size_t* count) {
+    if (!need(8)) return false;
+    uint64_t n64;
+    memcpy(&n64, bytes + off, 8);
+    off += 8;
+    if (n64 > (len - off) / elem) return false;
+    *p = bytes + off;
+    *count = size_t(n64);
+    off += size_t(n64) * elem;
+    return true;
+  };
+  const uint8_t *alpha, *beta2, *gamma2, *delta2, *abc, *beta1, *delta1, *aq, *b1q, *b2q, *hq, *lq;
+  size_t n_abc, n_a, n_b1, n_b2, n_h, n_l;
+  bool ok = fixed(32, &alpha) && fixed(64, &beta2) && fixed(64, &gamma2) && fixed(64, &delta2) && vec(32, &abc, &n_abc) &&
+            fixed(32, &beta1) && fixed(32, &delta1) && vec(32, &aq, &n_a) && vec(32, &b1q, &n_b1) && vec(64, &b2q, &n_b2) &&
+            vec(32, &hq, &n_h) && vec(32, &lq, &n_l);
+  if (!ok) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: truncated proving key (%zu bytes)", len);
+  if (off != len) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: %zu trailing bytes after the proving key", len - off);
+  if (n_a < 1 || n_b1 != n_a || n_b2 != n_a)
+    ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: a/b_g1/b_g2 query lengths %zu/%zu/%zu disagree", n_a, n_b1, n_b2);
+  if (n_l > n_a - 1) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: l_query longer than the witness");
+  ZKB_TRY(set_device(ctx));
+  zkb_pk* pk = new (std::nothrow) zkb_pk();
+  if (!pk) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_load_compressed: host allocation failed");
+  pk->device = ctx->device;
+  pk->nv = n_a;
+  pk->nw = n_l;
+  pk->nh = n_h;
+  // q[1..] || q[0] || extras (or q || extras), in compressed form
+  auto ext = [&](const uint8_t* q, size_t qlen, size_t elem, bool rotate, std::initializer_list<const uint8_t*> extra) {
+    std::vector<uint8_t> buf((qlen + extra.size()) * elem);
+    size_t o = 0;
+    if (rotate && qlen) {
+      memcpy(buf.data(), q + elem, (qlen - 1) * elem);
+      o = (qlen - 1) * elem;
+      memcpy(buf.data() + o, q, elem);
+      o += elem;
+    } else if (qlen) {
+      memcpy(buf.data(), q, qlen * elem);
+      o = qlen * elem;
+    }
+    for (const uint8_t* e : extra) {
+      memcpy(buf.data() + o, e, elem);
+      o += elem;
+    }
+    return buf;
+  };
+  int s = ZKB_OK;
+  try {
+    {
+      auto b = ext(aq, n_a, 32, true, {alpha, delta1});
+      s = bases_load_compressed_impl<Fq>(ctx, b.data(), n_a + 2, validate, &pk->a_ext);
+    }
+    if (s == ZKB_OK) {
+      auto b = ext(b1q, n_b1, 32, true, {beta1, delta1});
+      s = bases_load_compressed_impl<Fq>(ctx, b.data(), n_b1 + 2, validate, &pk->b1_ext);
+    }
+    if (s == ZKB_OK) {
+      auto b = ext(b2q, n_b2, 64, true, {beta2, delta2});
+      s = bases_load_compressed_impl<Fq2>(ctx, b.data(), n_b2 + 2, validate, &pk->b2_ext);
+    }
+    if (s == ZKB_OK) {
+      auto b = ext(lq, n_l, 32, false, {delta1});
+      s = bases_load_compressed_impl<Fq>(ctx, b.data(), n_l + 1, validate, &pk->l_ext);
+    }
+    if (s == ZKB_OK) s = bases_load_compressed_impl<Fq>(ctx, hq, n_h, validate, &pk->h);
+    // the prover never reads gamma_g2 / gamma_abc_g1, but deserialize_compressed validates them: so do we
+    if (s == ZKB_OK && validate) {
+      zkb_g2_bases* g2 = nullptr;
+      s = bases_load_compressed_impl<Fq2>(ctx, gamma2, 1, validate, &g2);
+      bases_free_impl<Fq2>(g2);
+      zkb_g1_bases* g1 = nullptr;
+      if (s == ZKB_OK) s = bases_load_compressed_impl<Fq>(ctx, abc, n_abc, validate, &g1);
+      bases_free_impl<Fq>(g1);
+    }
+  } catch (const std::bad_alloc&) {
+    zkb_pk_free(pk);
+    ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_load_compressed: host staging allocation failed");
+  }
   if (s != ZKB_OK) {
     zkb_pk_free(pk);
     return s;
