@@ -199,9 +199,11 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
       } else {
         store_xyzz(buckets + cur, acc);
       }
-      acc = XYZZ<F>::inf();
-      cur = k;
       if (!more) break;
+      // the next run starts inside this chunk: this thread owns bucket k.  It continues from the bucket's current content
+      // (zero = infinity after the memset; the earlier slices' sum when a host-scalar MSM is uploaded in slices).
+      acc = load_xyzz(buckets + k);
+      cur = k;
     }
   }
 }
@@ -415,17 +417,6 @@ struct MsmTraits<Fq2> {
   static constexpr int THREADS_PER_SM = 256;
 };
 
-// buckets[b] += extra[k][b] for k < nextra (slices of a pipelined MSM accumulate into separate bucket arrays)
-template <class F>
-__global__ void __launch_bounds__(64)
-msm_bucket_merge_kernel(XYZZ<F>* __restrict__ buckets, const XYZZ<F>* __restrict__ extra, size_t nbuck, int nextra) {
-  size_t b = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (b >= nbuck) return;
-  XYZZ<F> acc = load_xyzz(buckets + b);
-  for (int k = 0; k < nextra; k++) acc.add(load_xyzz(extra + size_t(k) * nbuck + b));
-  store_xyzz(buckets + b, acc);
-}
-
 // Workspace layout of one MSM whose entries arrive in up to `nslices` slices of at most `n_slice` points each.
 template <class F>
 struct MsmLayout {
@@ -479,7 +470,7 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   };
   L.o_k0 = take(L.total * 4), L.o_v0 = take(L.total * 4), L.o_k1 = take(L.total * 4), L.o_v1 = take(L.total * 4);
   L.o_tmp = take(L.sort_tmp);
-  L.o_buck = take(size_t(L.nbuck) * sizeof(P) * nslices);
+  L.o_buck = take(size_t(L.nbuck) * sizeof(P));
   size_t nh1 = (L.nthreads + 31) / 32;
   L.o_h0 = take(L.nthreads * sizeof(P)), L.o_hk0 = take(L.nthreads * 4);
   L.o_h1 = take(nh1 * sizeof(P)), L.o_hk1 = take(nh1 * 4);
@@ -491,10 +482,11 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   return L;
 }
 
-// Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE) -> bucket array `slice`.
+// Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE), accumulated into the
+// (shared) bucket array; `first_slice` clears it.
 template <class F>
 cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affine<F>* table, size_t table_n, size_t first,
-                                 const uint32_t* scalars, size_t n, int slice) {
+                                 const uint32_t* scalars, size_t n, bool first_slice) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
@@ -502,7 +494,7 @@ cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affi
   char* base = static_cast<char*>(ctx->msm_ws.p);
   uint32_t *k0 = (uint32_t*)(base + L.o_k0), *v0 = (uint32_t*)(base + L.o_v0);
   uint32_t *k1 = (uint32_t*)(base + L.o_k1), *v1 = (uint32_t*)(base + L.o_v1);
-  P* buckets = (P*)(base + L.o_buck) + size_t(slice) * L.nbuck;
+  P* buckets = (P*)(base + L.o_buck);
   P* hp[2] = {(P*)(base + L.o_h0), (P*)(base + L.o_h1)};
   uint32_t* hk[2] = {(uint32_t*)(base + L.o_hk0), (uint32_t*)(base + L.o_hk1)};
   const size_t total = size_t(L.nwin) * n;
@@ -518,7 +510,7 @@ cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affi
     cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.o_tmp, tmp, k0, k1, v0, v1, int(total), 0, L.key_bits, st);
     if (e != cudaSuccess) return e;
   }
-  cudaMemsetAsync(buckets, 0, size_t(L.nbuck) * sizeof(P), st);
+  if (first_slice) cudaMemsetAsync(buckets, 0, size_t(L.nbuck) * sizeof(P), st);
   cudaMemsetAsync(hk[0], 0xff, nthreads * 4, st);
   {
     ProfScope ps(ctx, PH0 + 2);
@@ -546,9 +538,9 @@ cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affi
   return cudaGetLastError();
 }
 
-// Stages 5-6: (merge the slices' bucket arrays,) reduce the buckets, write the results.
+// Stages 5-6: reduce the buckets, write the results.
 template <class F>
-cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, int nslices_used, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
   using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
   cudaStream_t st = ctx->stream;
@@ -559,10 +551,6 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, int nslices_used, XY
   P* part = (P*)(base + L.o_part);
   P* planes = (P*)(base + L.o_planes);
   ProfScope ps(ctx, PH0 + 3);
-  if (nslices_used > 1) {
-    msm_bucket_merge_kernel<F><<<unsigned((size_t(L.nbuck) + 63) / 64), 64, 0, st>>>(buckets, buckets + L.nbuck, L.nbuck, nslices_used - 1);
-    ctx->launches++;
-  }
   msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg, L.seg_log);
   msm_rowcol_kernel<F, 64><<<unsigned(2 * L.rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
   msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, L.rows, planes);
@@ -587,13 +575,13 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1, st);
   cudaError_t e = ctx->msm_ws.reserve(L.bytes);
   if (e != cudaSuccess) return e;
-  e = msm_accumulate_slice<F>(ctx, L, table, table_n, first, scalars, n, 0);
+  e = msm_accumulate_slice<F>(ctx, L, table, table_n, first, scalars, n, true);
   if (e != cudaSuccess) return e;
-  return msm_reduce<F>(ctx, L, 1, out_xyzz, out_affine);
+  return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
 }
 
 // Host-scalar MSM pipelined against the PCIe copy: the scalars go up in `nslices` slices on a second stream; slice k is
-// decomposed, sorted and accumulated (into its own bucket array) while slice k+1 is still in flight.
+// decomposed, sorted and accumulated (on top of the buckets the earlier slices left) while slice k+1 is still in flight.
 template <class F>
 cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
                                 const uint8_t* scalars_host, uint32_t* scalars_dev, size_t n, int nslices,
@@ -643,11 +631,12 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
     size_t lo = bound[k], cnt = bound[k + 1] - bound[k];
     cudaStreamWaitEvent(ctx->stream, ctx->copy_done[k], 0);
     if (!cnt) continue;
-    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, used);
+    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, used == 0);
     if (e != cudaSuccess) return e;
     used++;
   }
-  return msm_reduce<F>(ctx, L, used, out_xyzz, out_affine);
+  if (!used) cudaMemsetAsync(static_cast<char*>(ctx->msm_ws.p) + L.o_buck, 0, size_t(L.nbuck) * sizeof(XYZZ<F>), ctx->stream);
+  return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
 }
 
 }  // namespace zkb
