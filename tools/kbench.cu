@@ -90,6 +90,19 @@ __global__ void __launch_bounds__(THREADS, MINB) madd_reg_kernel(const uint32_t*
   if (s == 0xdeadbeefu) sink[0] = s;
 }
 
+// ---- E2b: G2 (Fq2) mixed addition at different register budgets
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) madd_g2_kernel(const uint32_t* seed, int iters, uint32_t* sink) {
+  XYZZ<Fq2> acc;
+  Affine<Fq2> p0, p1;
+  auto ld2 = [&](int o) { return Fq2{load_fq(seed + 8 * ((threadIdx.x + o) & 7)), load_fq(seed + 8 * ((threadIdx.x + o + 1) & 7))}; };
+  p0.x = ld2(0); p0.y = ld2(1); p1.x = ld2(2); p1.y = ld2(3);
+  acc.x = ld2(4); acc.y = ld2(5); acc.zz = ld2(6); acc.zzz = ld2(7);
+  for (int it = 0; it < iters; it++) acc.madd((it & 1) ? p1 : p0);
+  uint32_t s = acc.x.c0.v[0] ^ acc.y.c1.v[3] ^ acc.zz.c0.v[1] ^ acc.zzz.c1.v[2];
+  if (s == 0xdeadbeefu) sink[0] = s;
+}
+
 // ---- E3: accumulator resident in shared memory (one 128-byte slot per thread, word-interleaved across threads
 // so that lane l reads bank l: conflict-free), registers hold only the operands of the product in flight.
 template <int THREADS>
@@ -196,6 +209,8 @@ int main(int argc, char** argv) {
 #define MADDK(NACC, MINB) time_kernel("madd regs NACC=" #NACC " blocks/SM=" #MINB, madd_reg_kernel<NACC, 128, MINB>, 128, MINB, 0, IM, 10 * NACC, seed, sink)
   MADDK(1, 3); MADDK(1, 4); MADDK(1, 5); MADDK(1, 6); MADDK(1, 8);
   MADDK(2, 2); MADDK(2, 3); MADDK(2, 4);
+#define MADDG2(TH, MINB) time_kernel("madd G2 threads=" #TH " blocks/SM=" #MINB, madd_g2_kernel<TH, MINB>, TH, MINB, 0, 200, 28, seed, sink)
+  MADDG2(64, 2); MADDG2(64, 3); MADDG2(64, 4); MADDG2(64, 5); MADDG2(64, 6); MADDG2(64, 8); MADDG2(128, 2); MADDG2(128, 3); MADDG2(128, 4);
 #define MADDS(MINB) time_kernel("madd smem-acc blocks/SM=" #MINB, madd_smem_kernel<128, MINB>, 128, MINB, 128 * 128, IM, 10, seed, sink)
   MADDS(4); MADDS(5); MADDS(6); MADDS(8); MADDS(10); MADDS(12);
   return 0;

@@ -8,6 +8,7 @@ namespace zkb {
 namespace {
 
 constexpr int NTT_LRMAX = 8;
+constexpr int NTT_FULL_TABLE_LOG = 24;
 
 struct NttTables {
   Fr* mem = nullptr;  // one allocation
@@ -131,7 +132,10 @@ int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
     return ZKB_OK;
   }
   NttTables t;
-  int lb = (logn + 1) / 2;
+  // Up to 2^24 the power tables are FULL (one load per twiddle, 32 B x n per table: the transform is multiply-bound, so a
+  // table read is cheaper than the extra product of a two-level lookup); beyond that, two levels of ~sqrt(n) entries.
+  const bool full = logn <= NTT_FULL_TABLE_LOG;
+  int lb = full ? logn : (logn + 1) / 2;
   uint32_t nlo = 1u << lb, nhi = 1u << (logn - lb);
   size_t per = size_t(nlo) + nhi;
   CUDA_TRY(ctx, cudaMalloc(&t.mem, (4 * per + 2) * sizeof(Fr)));
@@ -139,14 +143,15 @@ int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
   unsigned long long wmult = 1ull << (28 - logn);
   auto gen = [&](Fr* lo, int base, unsigned long long mult, int sbase, unsigned long long sexp) {
     Fr* hi = lo + nlo;
-    fr_pow_table_kernel<<<blocks_for(nlo, 64), 64, 0, ctx->stream>>>(lo, nlo, base, mult, 1, 0, 0);
+    // full table: the constant factor is baked into every entry (hi has the single entry lo[0]'s value)
+    fr_pow_table_kernel<<<blocks_for(nlo, 64), 64, 0, ctx->stream>>>(lo, nlo, base, mult, 1, full ? sbase : 0, full ? sexp : 0);
     fr_pow_table_kernel<<<blocks_for(nhi, 64), 64, 0, ctx->stream>>>(hi, nhi, base, mult, 1ull << lb, sbase, sexp);
     ctx->launches += 2;
     PowTable pt;
     pt.lo = lo;
     pt.hi = hi;
     pt.lo_bits = lb;
-    pt.scaled = sexp ? 1 : 0;
+    pt.scaled = (sexp && !full) ? 1 : 0;
     return pt;
   };
   t.fwd = gen(p, FRB_ROOT, wmult, 0, 0);
