@@ -87,17 +87,38 @@ __device__ __forceinline__ void store_affine(Affine<F>* p, const Affine<F>& v) {
   for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++) dst[k] = src[k];
 }
 
-// table[j * n + i] = 2^(c j) * table[i] for 1 <= j < nwin (table[0..n) holds the bases).  One thread per base.
+// table[j * n + i] = 2^(c j) * table[i] for 1 <= j < nwin (table[0..n) holds the bases).  One thread per base: the doubling
+// chain stays in XYZZ, and the conversions back to affine share one inversion per group of up to 16 windows (Montgomery's
+// trick on the ZZZ coordinates, kept in local memory).
 template <class F>
 __global__ void __launch_bounds__(128) window_tables_kernel(Affine<F>* table, size_t n, int c, int nwin) {
+  constexpr int GROUP = 16;
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Affine<F> a = table[i];
-  for (int j = 1; j < nwin; j++) {
-    XYZZ<F> cur = XYZZ<F>::dbl_affine(a);
-    for (int k = 1; k < c; k++) cur = cur.dbl();
-    a = cur.to_affine();
-    store_affine(table + size_t(j) * n + i, a);
+  XYZZ<F> cur = XYZZ<F>::from_affine(table[i]);
+  XYZZ<F> pts[GROUP];
+  F prefix[GROUP];
+  for (int j0 = 1; j0 < nwin; j0 += GROUP) {
+    const int g = nwin - j0 < GROUP ? nwin - j0 : GROUP;
+    F pr = F::one();
+    for (int k = 0; k < g; k++) {
+      for (int d = 0; d < c; d++) cur = cur.dbl();
+      pts[k] = cur;
+      prefix[k] = pr;                       // product of the finite points' ZZZ before this one
+      if (!cur.is_inf()) pr = pr * cur.zzz;
+    }
+    F inv = pr.inverse();
+    for (int k = g - 1; k >= 0; k--) {
+      Affine<F> a = Affine<F>::inf();
+      if (!pts[k].is_inf()) {
+        F zi3 = inv * prefix[k];            // 1 / zzz_k
+        inv = inv * pts[k].zzz;
+        F zi = zi3 * pts[k].zz;             // zz / zzz = 1 / z
+        F zi2 = zi.sqr();
+        a = {pts[k].x * zi2, pts[k].y * zi3};
+      }
+      store_affine(table + size_t(j0 + k) * n + i, a);
+    }
   }
 }
 
