@@ -53,6 +53,7 @@ def parse_args():
                     help="msm_g1 = the contract line (default); ntt / msm_sweep = BASELINE.json configs 3 / 2 as extra sweeps")
     ap.add_argument("--concurrency", type=int, default=1, help="prove workload: contexts (host threads + streams) per GPU")
     ap.add_argument("--batch", type=int, default=0, help="prove workload: independent proofs per step over all GPUs (0 = one)")
+    ap.add_argument("--cpu-baseline-prove", action="store_true", help="prove workload: time the CPU restatement even for large circuits")
     ap.add_argument("--logs", default="", help="comma-separated log2 sizes for the sweeps")
     return ap.parse_args()
 
@@ -473,7 +474,7 @@ def run_prove(args):
     nv, n = ni + nw, 1 << lg
     # Small circuits: the key (random curve points generated on the GPU, read back) is loaded into BOTH provers, so the CPU
     # restatement's proof can be compared byte for byte; forge-sized: a device-only synthetic key.
-    with_cpu = rank == 0 and world == 1 and K == 1 and not args.no_cpu_baseline and lg <= 16
+    with_cpu = rank == 0 and world == 1 and K == 1 and not args.no_cpu_baseline and (lg <= 16 or args.cpu_baseline_prove)
     parts = None
     t0 = time.perf_counter()
     if with_cpu:
@@ -546,7 +547,7 @@ def run_prove(args):
         cpk = orc.ProvingKey(**parts)
         cm = orc.R1cs(ni, nw, csr=(A, B, Cm))
         rb, sb2 = int(seeds[mine[0], 0]).to_bytes(32, "little"), int(seeds[mine[0], 1]).to_bytes(32, "little")
-        reps = 3
+        reps = 3 if lg <= 16 else 1
         t0 = time.perf_counter()
         for _ in range(reps):
             cproof = orc.prove(cpk, cm, z_np, rb, sb2, threads=threads)
