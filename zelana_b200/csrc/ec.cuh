@@ -66,8 +66,9 @@ struct XYZZ {
     return {p.x, p.y, F::one(), F::one()};
   }
 
-  // 2 * affine (mdbl-2008-s-1, a = 0)
-  static __device__ __forceinline__ XYZZ dbl_affine(const Affine<F>& p) {
+  // 2 * affine (mdbl-2008-s-1, a = 0).  Not inlined: inside madd it is the (practically never taken) P == Q branch, and inlining
+  // its seven products there bloats the hot loop's code (instruction-fetch stalls, visible in the G2 accumulate profile).
+  static __device__ __noinline__ XYZZ dbl_affine(const Affine<F>& p) {
     if (p.is_inf() || p.y.is_zero()) return inf();
     F U = p.y.dbl();
     F V = U.sqr();
