@@ -176,6 +176,19 @@ int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h
 int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
               const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
 
+/* ---- one proof over several GPUs (MSMs sharded by contiguous range of the key's query vectors) ----------
+ * Rank `shard` of `world` loads its range of the key (zkb_pk_load_shard), runs zkb_prove_partial (witness map replicated,
+ * five MSMs over its range) and contributes ZKB_PROVE_PARTIAL_BYTES; the records are all-gathered (NCCL) and any rank
+ * finishes the proof with zkb_prove_combine.  world = 1 reproduces zkb_prove. */
+#define ZKB_PROVE_PARTIAL_BYTES 768 /* A, B1, L, H: 4 x 128 B ; B2: 256 B (opaque projective partial sums) */
+int zkb_pk_load_shard(zkb_ctx* ctx, const zkb_pk_desc* desc, int validate, int shard, int world, zkb_pk** out);
+int zkb_pk_synthetic_shard(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev, size_t k_len,
+                           int shard, int world, zkb_pk** out); /* BENCHMARK ONLY, as zkb_pk_synthetic */
+int zkb_prove_partial(zkb_ctx* ctx, const zkb_pk* pk_shard, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+                      const uint8_t s[32], void* out_partial_dev);
+int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int world, const uint8_t r[32], const uint8_t s[32],
+                      uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -514,3 +514,35 @@ def test_pk_load_compressed_rejects_what_arkworks_rejects(ctx, mimc_setup):
     # gamma_abc is not used by the prover but is still validated
     bad = bytearray(blob); bad[32 + 64 * 3 + 8:32 + 64 * 3 + 8 + 32] = x.to_bytes(32, "little")
     expect(bad, -5)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5])
+def test_sharded_prove_equals_prove(ctx, mimc_setup, world):
+    """One proof over `world` key shards (emulated sequentially on one GPU): partial records combined == zkb_prove == oracle.
+    The last shards hold the appended constant points (alpha, beta, delta); ragged ranges when world does not divide."""
+    import torch
+    from zelana_b200.api import PROVE_PARTIAL_BYTES
+    r1cs, z, pk = mimc_setup
+    m = ctx.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+    parts_host = pk_parts(pk)
+    r, s = 0x1234567890ABCDEF1234567, 0x7654321FEDCBA987654321
+    ref = g16.prove_with_rs(pk, r1cs, z, r, s)
+    expect = (bn.g1_to_raw(ref.a), bn.g2_to_raw(ref.b), bn.g1_to_raw(ref.c))
+    parts = torch.zeros(world * PROVE_PARTIAL_BYTES, dtype=torch.uint8, device="cuda")
+    for shard in range(world):
+        dpk = ctx.proving_key_shard(shard, world, **parts_host)
+        ctx.prove_partial(dpk, m, fr_bytes(z), fr_bytes([r]), fr_bytes([s]), parts[shard * PROVE_PARTIAL_BYTES:])
+        if world > 1:
+            import zelana_b200
+            with pytest.raises(zelana_b200.ZkbError):
+                ctx.prove(dpk, m, fr_bytes(z), fr_bytes([r]), fr_bytes([s]))   # a shard cannot make a whole proof
+        dpk.free()
+    assert ctx.prove_combine(parts, world, fr_bytes([r]), fr_bytes([s])) == expect
+    # r = 0 (arkworks skips B1) through the sharded path
+    parts.zero_()
+    for shard in range(world):
+        dpk = ctx.proving_key_shard(shard, world, **parts_host)
+        ctx.prove_partial(dpk, m, fr_bytes(z), fr_bytes([0]), fr_bytes([9]), parts[shard * PROVE_PARTIAL_BYTES:])
+        dpk.free()
+    ref0 = g16.prove_with_rs(pk, r1cs, z, 0, 9)
+    assert ctx.prove_combine(parts, world, fr_bytes([0]), fr_bytes([9])) == (bn.g1_to_raw(ref0.a), bn.g2_to_raw(ref0.b), bn.g1_to_raw(ref0.c))

@@ -85,6 +85,10 @@ SIGNATURES = {
     "zkb_pk_free": (None, [_P]),
     "zkb_pk_synthetic": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, C.POINTER(_P)]),
     "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "zkb_pk_load_shard": (_I, [_P, C.POINTER(PkDesc), _I, _I, _I, C.POINTER(_P)]),
+    "zkb_pk_synthetic_shard": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, _I, _I, C.POINTER(_P)]),
+    "zkb_prove_partial": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "zkb_prove_combine": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@ from ._lib import ZkbError, load_library, R1csDesc, PkDesc, Csr
 FR, FQ = 0, 1
 OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_NEG = range(5)
 G1_PARTIAL_BYTES, G2_PARTIAL_BYTES = 128, 256
+PROVE_PARTIAL_BYTES = 768
 
 
 def _buf(x):
@@ -199,10 +200,11 @@ class Context:
         pk.ctx, pk.h = self, h
         return pk
 
-    def proving_key_synthetic(self, num_vars, num_witness, h_len, k_dev, k_len):
-        """Benchmark-only key of the given shape (query points [k_i] G from device scalars); proofs do not verify."""
+    def proving_key_synthetic(self, num_vars, num_witness, h_len, k_dev, k_len, shard=0, world=1):
+        """Benchmark-only key (or key shard) of the given shape (query points [k_i] G from device scalars); proofs do not verify."""
         h = C.c_void_p()
-        self._check(self.lib.zkb_pk_synthetic(self.h, num_vars, num_witness, h_len, _devptr(k_dev), k_len, C.byref(h)))
+        self._check(self.lib.zkb_pk_synthetic_shard(self.h, num_vars, num_witness, h_len, _devptr(k_dev), k_len, shard, world,
+                                                    C.byref(h)))
         pk = ProvingKeyDev.__new__(ProvingKeyDev)
         pk.ctx, pk.h = self, h
         return pk
@@ -213,6 +215,27 @@ class Context:
         out = np.empty(n * 32, dtype=np.uint8)
         self._check(self.lib.zkb_witness_map(self.h, r1cs.h, pz, out.ctypes.data_as(C.c_void_p)))
         return out.tobytes()
+
+    def proving_key_shard(self, shard, world, **parts):
+        """Rank `shard` of `world`: only its contiguous range of every query vector is uploaded (zkb_pk_load_shard)."""
+        return ProvingKeyDev(self, shard=shard, world=world, **parts)
+
+    def prove_partial(self, pk, r1cs, z_bytes, r_bytes, s_bytes, out_partial_dev):
+        """This rank's share of a sharded proof -> PROVE_PARTIAL_BYTES at out_partial_dev (device memory)."""
+        pz, kz = _buf(z_bytes)
+        pr, kr = _buf(r_bytes)
+        ps, ks = _buf(s_bytes)
+        self._check(self.lib.zkb_prove_partial(self.h, pk.h, r1cs.h, pz, pr, ps, _devptr(out_partial_dev)))
+
+    def prove_combine(self, partials_dev, world, r_bytes, s_bytes):
+        pr, kr = _buf(r_bytes)
+        ps, ks = _buf(s_bytes)
+        oa = np.empty(64, dtype=np.uint8)
+        ob = np.empty(128, dtype=np.uint8)
+        oc = np.empty(64, dtype=np.uint8)
+        self._check(self.lib.zkb_prove_combine(self.h, _devptr(partials_dev), world, pr, ps, oa.ctypes.data_as(C.c_void_p),
+                                               ob.ctypes.data_as(C.c_void_p), oc.ctypes.data_as(C.c_void_p)))
+        return oa.tobytes(), ob.tobytes(), oc.tobytes()
 
     def prove(self, pk, r1cs, z_bytes, r_bytes, s_bytes):
         pz, kz = _buf(z_bytes)
@@ -333,7 +356,7 @@ class ProvingKeyDev:
     """Device-resident Groth16 proving key built from raw affine byte strings."""
 
     def __init__(self, ctx, alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2, a_query, b_g1_query, b_g2_query,
-                 h_query, l_query, validate=True):
+                 h_query, l_query, validate=True, shard=0, world=1):
         self.ctx = ctx
         keep = []
 
@@ -353,7 +376,7 @@ class ProvingKeyDev:
         d.h_query, d.h_len = ptr(h_query), len(h_query) // 64
         d.l_query, d.l_len = ptr(l_query), len(l_query) // 64
         h = C.c_void_p()
-        ctx._check(ctx.lib.zkb_pk_load(ctx.h, C.byref(d), int(validate), C.byref(h)))
+        ctx._check(ctx.lib.zkb_pk_load_shard(ctx.h, C.byref(d), int(validate), shard, world, C.byref(h)))
         self.h = h
 
     def free(self):

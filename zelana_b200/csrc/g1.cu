@@ -48,7 +48,44 @@ __global__ void prove_assemble_c_kernel(const XYZZ<Fq>* A, const XYZZ<Fq>* B1, c
   }
 }
 
+// parts: `world` records of `stride` bytes, each starting with the four G1 partial sums A, B1, L, H.
+__global__ void prove_combine_g1_kernel(const char* parts, int world, size_t stride, const uint32_t* r, const uint32_t* s,
+                                        uint32_t* out_a, uint32_t* out_c) {
+  __shared__ XYZZ<Fq> sum[4];
+  int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (lane == 0 && warp < 4) {
+    XYZZ<Fq> acc = XYZZ<Fq>::inf();
+    for (int k = 0; k < world; k++) acc.add(load_xyzz(reinterpret_cast<const XYZZ<Fq>*>(parts + size_t(k) * stride) + warp));
+    if (warp < 2) {  // s * A, r * B1
+      uint32_t e[8];
+      for (int j = 0; j < 8; j++) e[j] = warp == 0 ? s[j] : r[j];
+      if (warp == 0) store_affine_canonical<Fq>(acc.to_affine_vartime(), out_a);
+      acc = acc.mul_words(e);
+    }
+    sum[warp] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    XYZZ<Fq> acc = sum[0];
+    acc.add(sum[1]);
+    acc.add(sum[2]);
+    acc.add(sum[3]);
+    store_affine_canonical<Fq>(acc.to_affine_vartime(), out_c);
+  }
+}
+
 }  // namespace
+
+int prove_combine_g1(zkb_ctx* ctx, const void* parts, int world, size_t stride, const void* r_dev, const void* s_dev,
+                     void* out_a_dev, void* out_c_dev) {
+  ProfScope ps(ctx, PH_ASSEMBLE);
+  prove_combine_g1_kernel<<<1, 128, 0, ctx->stream>>>(static_cast<const char*>(parts), world, stride,
+                                                      static_cast<const uint32_t*>(r_dev), static_cast<const uint32_t*>(s_dev),
+                                                      static_cast<uint32_t*>(out_a_dev), static_cast<uint32_t*>(out_c_dev));
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
 
 int fq_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
   size_t bytes = n * 32;

@@ -185,6 +185,10 @@ int fq_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t
 // C = s*A + r*B1 + L + H (projective partial sums on device) -> canonical affine
 int prove_assemble_c(zkb_ctx* ctx, const void* pA, const void* pB1, const void* pL, const void* pH, const void* r_dev,
                      const void* s_dev, void* out_c_dev);
+// sharded prove: sum `world` partial records [A | B1 | L | H (XYZZ G1) | B2 (XYZZ G2)] and finish the proof (g1.cu / g2.cu)
+int prove_combine_g1(zkb_ctx* ctx, const void* parts, int world, size_t stride, const void* r_dev, const void* s_dev,
+                     void* out_a_dev, void* out_c_dev);
+int prove_combine_g2(zkb_ctx* ctx, const void* parts, int world, size_t stride, void* out_b_dev);
 
 // fr.cu
 struct CsrDev {
@@ -225,4 +229,8 @@ struct zkb_pk {
   //   l_ext  = l_query || delta_g1                                       scalars: aux   || -(r s)
   zkb_g1_bases *a_ext = nullptr, *b1_ext = nullptr, *l_ext = nullptr, *h = nullptr;
   zkb_g2_bases* b2_ext = nullptr;
+  // A shard of a key (zkb_pk_load_shard): the handles above hold only the range [off, off + len) of each extended vector;
+  // nv / nw / nh keep describing the WHOLE key.  Unsharded: offsets 0.
+  size_t off_a = 0, off_l = 0, off_h = 0;   // a_ext, b1_ext and b2_ext share off_a
+  int shard = 0, world = 1;
 };

@@ -365,7 +365,7 @@ static int reserve_prove_bufs(zkb_ctx* ctx, size_t n, size_t nv, size_t nw) {
   CUDA_TRY(ctx, ctx->pzb.reserve((nv + 3) * 32));
   CUDA_TRY(ctx, ctx->pzl.reserve((nw + 1) * 32));
   CUDA_TRY(ctx, ctx->prs.reserve(64));
-  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + 64 + 128 + 64));
+  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64));
   return ZKB_OK;
 }
 
@@ -388,7 +388,7 @@ namespace {
 
 template <class F>
 int load_ext(zkb_ctx* ctx, const uint8_t* q, size_t qlen, bool rotate_first, const uint8_t* const* extra, int nextra,
-             int validate, typename GroupOf<F>::Bases** out) {
+             int validate, size_t lo, size_t cnt, typename GroupOf<F>::Bases** out) {
   // host-side concatenation: q[1..] || q[0] || extra...   (or q || extra... when !rotate_first)
   const size_t sz = sizeof(Affine<F>);
   std::vector<uint8_t> buf;
@@ -411,7 +411,7 @@ int load_ext(zkb_ctx* ctx, const uint8_t* q, size_t qlen, bool rotate_first, con
     memcpy(buf.data() + o, extra[i], sz);
     o += sz;
   }
-  return bases_load_impl<F>(ctx, buf.data(), qlen + nextra, validate, out);
+  return bases_load_impl<F>(ctx, buf.data() + lo * sz, cnt, validate, out);  // [lo, lo + cnt) of the extended vector
 }
 
 }  // namespace
@@ -426,10 +426,20 @@ extern "C" void zkb_pk_free(zkb_pk* pk) {
   delete pk;
 }
 
-extern "C" int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, zkb_pk** out) {
+namespace {
+
+// contiguous split with the remainder on the lowest shards (zelana_b200/multi.py shard_range)
+void shard_span(size_t n, int shard, int world, size_t* lo, size_t* cnt) {
+  size_t base = n / world, rem = n % world;
+  *lo = size_t(shard) * base + (size_t(shard) < rem ? size_t(shard) : rem);
+  *cnt = base + (size_t(shard) < rem ? 1 : 0);
+}
+
+int pk_load_common(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, int shard, int world, zkb_pk** out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!d || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_load: null argument");
   *out = nullptr;
+  if (world < 1 || shard < 0 || shard >= world) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_load: shard %d of %d", shard, world);
   if (!d->alpha_g1 || !d->beta_g1 || !d->beta_g2 || !d->delta_g1 || !d->delta_g2 || !d->a_query || !d->b_g1_query ||
       !d->b_g2_query || (!d->h_query && d->h_len) || (!d->l_query && d->l_len))
     ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_load: null key component");
@@ -443,21 +453,38 @@ extern "C" int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, zkb
   pk->nv = d->a_len;
   pk->nw = d->l_len;
   pk->nh = d->h_len;
+  pk->shard = shard;
+  pk->world = world;
+  size_t cnt_a, cnt_l, cnt_h;
+  shard_span(d->a_len + 2, shard, world, &pk->off_a, &cnt_a);
+  shard_span(d->l_len + 1, shard, world, &pk->off_l, &cnt_l);
+  shard_span(d->h_len, shard, world, &pk->off_h, &cnt_h);
   const uint8_t* ea[2] = {d->alpha_g1, d->delta_g1};
   const uint8_t* eb1[2] = {d->beta_g1, d->delta_g1};
   const uint8_t* eb2[2] = {d->beta_g2, d->delta_g2};
   const uint8_t* el[1] = {d->delta_g1};
-  int s = load_ext<Fq>(ctx, d->a_query, d->a_len, true, ea, 2, validate, &pk->a_ext);
-  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->b_g1_query, d->b_g1_len, true, eb1, 2, validate, &pk->b1_ext);
-  if (s == ZKB_OK) s = load_ext<Fq2>(ctx, d->b_g2_query, d->b_g2_len, true, eb2, 2, validate, &pk->b2_ext);
-  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->l_query, d->l_len, false, el, 1, validate, &pk->l_ext);
-  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->h_query, d->h_len, false, nullptr, 0, validate, &pk->h);
+  int s = load_ext<Fq>(ctx, d->a_query, d->a_len, true, ea, 2, validate, pk->off_a, cnt_a, &pk->a_ext);
+  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->b_g1_query, d->b_g1_len, true, eb1, 2, validate, pk->off_a, cnt_a, &pk->b1_ext);
+  if (s == ZKB_OK) s = load_ext<Fq2>(ctx, d->b_g2_query, d->b_g2_len, true, eb2, 2, validate, pk->off_a, cnt_a, &pk->b2_ext);
+  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->l_query, d->l_len, false, el, 1, validate, pk->off_l, cnt_l, &pk->l_ext);
+  if (s == ZKB_OK) s = load_ext<Fq>(ctx, d->h_query, d->h_len, false, nullptr, 0, validate, pk->off_h, cnt_h, &pk->h);
   if (s != ZKB_OK) {
     zkb_pk_free(pk);
     return s;
   }
   *out = pk;
   return ZKB_OK;
+}
+
+}  // namespace
+
+extern "C" int zkb_pk_load(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, zkb_pk** out) {
+  return pk_load_common(ctx, d, validate, 0, 1, out);
+}
+
+// Shard `shard` of `world` of the same key: only the range shard_span(len) of every (extended) query vector is uploaded.
+extern "C" int zkb_pk_load_shard(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, int shard, int world, zkb_pk** out) {
+  return pk_load_common(ctx, d, validate, shard, world, out);
 }
 
 // ProvingKey::<Bn254>::deserialize_compressed (Groth16Prover::from_bytes, prover.rs:263-277): ark-serialize layout
@@ -566,10 +593,11 @@ extern "C" int zkb_pk_load_compressed(zkb_ctx* ctx, const uint8_t* bytes, size_t
 // Benchmark-only key: every query vector is [k_i] G for caller-supplied device scalars, so that a forge-sized key
 //  can be fabricated in seconds on the GPU.  Proofs made with it do not verify -- the timing
 // of zkb_prove does not depend on which curve points the key holds; correctness is covered by the real-key tests.
-extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev,
-                                size_t k_len, zkb_pk** out) {
+extern "C" int zkb_pk_synthetic_shard(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev,
+                                      size_t k_len, int shard, int world, zkb_pk** out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
-  if (!out || !k_dev || num_vars < 1 || num_witness > num_vars - 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_synthetic: bad argument");
+  if (!out || !k_dev || num_vars < 1 || num_witness > num_vars - 1 || world < 1 || shard < 0 || shard >= world)
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_pk_synthetic: bad argument");
   size_t need = num_vars + 2 > h_len ? num_vars + 2 : h_len;
   if (k_len < need + 4) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_synthetic: need %zu scalars, got %zu", need + 4, k_len);
   *out = nullptr;
@@ -580,12 +608,19 @@ extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witnes
   pk->nv = num_vars;
   pk->nw = num_witness;
   pk->nh = h_len;
+  pk->shard = shard;
+  pk->world = world;
+  size_t cnt_a, cnt_l, cnt_h;
+  shard_span(num_vars + 2, shard, world, &pk->off_a, &cnt_a);
+  shard_span(num_witness + 1, shard, world, &pk->off_l, &cnt_l);
+  shard_span(h_len, shard, world, &pk->off_h, &cnt_h);
+  // point i of the vector v is [k[i + v]] G, whatever the sharding
   const char* k = static_cast<const char*>(k_dev);
-  int s = bases_generate_impl<Fq>(ctx, k, num_vars + 2, &pk->a_ext);
-  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 32, num_vars + 2, &pk->b1_ext);
-  if (s == ZKB_OK) s = bases_generate_impl<Fq2>(ctx, k + 64, num_vars + 2, &pk->b2_ext);
-  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 96, num_witness + 1, &pk->l_ext);
-  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 128, h_len, &pk->h);
+  int s = bases_generate_impl<Fq>(ctx, k + 32 * pk->off_a, cnt_a, &pk->a_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 32 * (pk->off_a + 1), cnt_a, &pk->b1_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq2>(ctx, k + 32 * (pk->off_a + 2), cnt_a, &pk->b2_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 32 * (pk->off_l + 3), cnt_l, &pk->l_ext);
+  if (s == ZKB_OK) s = bases_generate_impl<Fq>(ctx, k + 32 * (pk->off_h + 4), cnt_h, &pk->h);
   if (s != ZKB_OK) {
     zkb_pk_free(pk);
     return s;
@@ -594,15 +629,42 @@ extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witnes
   return ZKB_OK;
 }
 
-extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
-                         const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {
-  if (!ctx) return ZKB_ERR_INVALID_ARG;
-  if (!pk || !m || !z_host || !r || !s || !out_a || !out_b || !out_c) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: null argument");
-  if (pk->device != ctx->device || m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: key/matrices on another device");
+extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h_len, const void* k_dev,
+                                size_t k_len, zkb_pk** out) {
+  return zkb_pk_synthetic_shard(ctx, num_vars, num_witness, h_len, k_dev, k_len, 0, 1, out);
+}
+
+namespace {
+
+struct ProveOut {
+  XYZZ<Fq>*pA, *pB1, *pL, *pH;
+  XYZZ<Fq2>* pB2;
+  uint32_t *oA, *oB, *oC;
+};
+
+ProveOut prove_out(zkb_ctx* ctx) {
+  char* pts = static_cast<char*>(ctx->ppts.p);
+  ProveOut o;
+  o.pA = reinterpret_cast<XYZZ<Fq>*>(pts);
+  o.pB1 = o.pA + 1;
+  o.pL = o.pA + 2;
+  o.pH = o.pA + 3;
+  o.pB2 = reinterpret_cast<XYZZ<Fq2>*>(pts + 4 * sizeof(XYZZ<Fq>));
+  o.oA = reinterpret_cast<uint32_t*>(pts + 4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>));
+  o.oB = o.oA + 16;
+  o.oC = o.oB + 32;
+  return o;
+}
+
+// Queues the whole prover for this key (or key shard) on the context's streams.  partial: every MSM leaves its projective
+// partial sum in ProveOut (A, B1, L, H, B2); otherwise A, B and C are finished to canonical affine bytes in oA, oB, oC.
+int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+                  const uint8_t s[32], bool partial, const char* who) {
+  if (pk->device != ctx->device || m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "%s: key/matrices on another device", who);
   const size_t nv = m->ni + m->nw, nw = m->nw, ni = m->ni;
   const size_t n = size_t(1) << m->log_domain;
-  if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove: key has %zu variables, circuit has %zu", pk->nv, nv);
-  if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove: l_query has %zu points, circuit has %zu witness variables", pk->nw, nw);
+  if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: key has %zu variables, circuit has %zu", who, pk->nv, nv);
+  if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: l_query has %zu points, circuit has %zu witness variables", who, pk->nw, nw);
   ZKB_TRY(set_device(ctx));
   cudaStream_t st = ctx->stream;
   ZKB_TRY(reserve_prove_bufs(ctx, n, nv, nw));
@@ -611,15 +673,8 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
   CUDA_TRY(ctx, cudaMemcpyAsync(z, z_host, nv * 32, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
-
-  char* pts = static_cast<char*>(ctx->ppts.p);
-  XYZZ<Fq>* pA = reinterpret_cast<XYZZ<Fq>*>(pts);
-  XYZZ<Fq>* pB1 = pA + 1;
-  XYZZ<Fq>* pL = pA + 2;
-  XYZZ<Fq>* pH = pA + 3;
-  uint32_t* oA = reinterpret_cast<uint32_t*>(pts + 4 * sizeof(XYZZ<Fq>));
-  uint32_t* oB = oA + 16;
-  uint32_t* oC = oB + 32;
+  ProveOut o = prove_out(ctx);
+  const size_t na = pk->a_ext->n;   // this shard's slice [off_a, off_a + na) of the nv + 2 extended scalars
 
   // B in G2 needs only z and s, not h: it runs on a second stream (own MSM scratch) next to the witness map and the G1
   // MSMs, filling the SMs those leave idle in their sort / reduction phases.
@@ -637,14 +692,15 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
     int rc = ZKB_OK;
     if (nv > 1 && cudaMemcpyAsync(zb, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
     if (rc == ZKB_OK) rc = prove_tail_scalars(ctx, rs + 1, rs + 1, zb + (nv - 1), zb + (nv + 2));
-    if (rc == ZKB_OK) rc = msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb, nv + 2, oB, nullptr);
+    if (rc == ZKB_OK)
+      rc = msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb + pk->off_a, na, partial ? nullptr : o.oB, partial ? o.pB2 : nullptr);
     if (rc == ZKB_OK && cudaEventRecord(ctx->ev_aux_done, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
     std::swap(ctx->stream, ctx->aux_stream);
     std::swap(ctx->msm_ws, ctx->msm_ws2);
     if (rc != ZKB_OK) {
       cudaGetLastError();
       cudaStreamSynchronize(ctx->aux_stream);
-      if (rc == ZKB_ERR_CUDA) ctx->err = "zkb_prove: CUDA error while queueing the G2 MSM";
+      if (rc == ZKB_ERR_CUDA) ctx->err = std::string(who) + ": CUDA error while queueing the G2 MSM";
       return rc;
     }
   }
@@ -662,17 +718,19 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
     if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(zl, z + ni, nw * 32, cudaMemcpyDeviceToDevice, st));
     ZKB_TRY(prove_tail_scalars(ctx, rs, rs + 1, za + (nv - 1), zl + nw));
     // A = MSM(a_ext, z[1..] || 1 || 1 || r)
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za, nv + 2, oA, pA)));
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za + pk->off_a, na, partial ? nullptr : o.oA, o.pA)));
     // H: msm_bigint truncates to the shorter of (h_query, h)
     size_t hn = pk->nh < n ? pk->nh : n;
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->h, 0, ctx->ph.p, hn, nullptr, pH)));
+    size_t hcnt = hn > pk->off_h ? hn - pk->off_h : 0;
+    if (hcnt > pk->h->n) hcnt = pk->h->n;
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->h, 0, ctx->ph.as<Fr>() + pk->off_h, hcnt, nullptr, o.pH)));
     // L = MSM(l_query || delta_1, aux || -(r s))
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl, nw + 1, nullptr, pL)));
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl + pk->off_l, pk->l_ext->n, nullptr, o.pL)));
     // B1: same scalars with s in the last slot
     CUDA_TRY(ctx, cudaMemcpyAsync(za + (nv + 1), rs + 1, 32, cudaMemcpyDeviceToDevice, st));
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, za, nv + 2, nullptr, pB1)));
+    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, za + pk->off_a, na, nullptr, o.pB1)));
     // C = s A + r B1 + L + H
-    ZKB_TRY(prove_assemble_c(ctx, pA, pB1, pL, pH, rs, rs + 1, oC));
+    if (!partial) ZKB_TRY(prove_assemble_c(ctx, o.pA, o.pB1, o.pL, o.pH, rs, rs + 1, o.oC));
     return ZKB_OK;
   };
   int grc = g1_part();
@@ -682,8 +740,54 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
     cudaStreamSynchronize(ctx->aux_stream);
     return grc;
   }
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_a, oA, 64, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_b, oB, 128, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_c, oC, 64, cudaMemcpyDeviceToHost, st));
+  return ZKB_OK;
+}
+
+}  // namespace
+
+extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+                         const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!pk || !m || !z_host || !r || !s || !out_a || !out_b || !out_c) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: null argument");
+  if (pk->world != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: this key is shard %d of %d (use zkb_prove_partial)", pk->shard, pk->world);
+  ZKB_TRY(prove_enqueue(ctx, pk, m, z_host, r, s, false, "zkb_prove"));
+  ProveOut o = prove_out(ctx);
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_a, o.oA, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_b, o.oB, 128, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_c, o.oC, 64, cudaMemcpyDeviceToHost, st));
   return check_flag(ctx, "witness assignment");
+}
+
+// One rank's share of a proof whose key is sharded over `world` GPUs: every rank runs the witness map (no
+// exchange) and the five MSMs over ITS range of the query vectors; out_partial_dev receives ZKB_PROVE_PARTIAL_BYTES.
+extern "C" int zkb_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+                                 const uint8_t s[32], void* out_partial_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!pk || !m || !z_host || !r || !s || !out_partial_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_partial: null argument");
+  ZKB_TRY(prove_enqueue(ctx, pk, m, z_host, r, s, true, "zkb_prove_partial"));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_partial_dev, ctx->ppts.p, ZKB_PROVE_PARTIAL_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
+  return check_flag(ctx, "witness assignment");
+}
+
+// partials_dev: `world` records of ZKB_PROVE_PARTIAL_BYTES (all-gathered) -> the proof.
+extern "C" int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int world, const uint8_t r[32], const uint8_t s[32],
+                                 uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!partials_dev || world < 1 || !r || !s || !out_a || !out_b || !out_c) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_combine: bad argument");
+  ZKB_TRY(set_device(ctx));
+  cudaStream_t st = ctx->stream;
+  CUDA_TRY(ctx, ctx->prs.reserve(64));
+  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64));
+  Fr* rs = ctx->prs.as<Fr>();
+  CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
+  ProveOut o = prove_out(ctx);
+  ZKB_TRY(prove_combine_g1(ctx, partials_dev, world, ZKB_PROVE_PARTIAL_BYTES, rs, rs + 1, o.oA, o.oC));
+  ZKB_TRY(prove_combine_g2(ctx, partials_dev, world, ZKB_PROVE_PARTIAL_BYTES, o.oB));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_a, o.oA, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_b, o.oB, 128, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_c, o.oC, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
 }

@@ -67,3 +67,27 @@ class ShardedMsm:
         else:
             dist.all_gather(chunks, part, group=self.pg)
         return self.engine.combine(self._parts, self.world)
+
+
+class ShardedProver:
+    """ONE Groth16 proof over the GPUs of a process group: rank r holds shard r of the proving key
+    (Context.proving_key_shard / zkb_pk_load_shard), runs the witness map (replicated: no exchange) and the five MSMs over
+    its range (zkb_prove_partial); the 768-byte partial records are all-gathered over NCCL and every rank finishes the
+    identical proof (zkb_prove_combine).  The full assignment z is host data every rank already has (same node)."""
+
+    def __init__(self, ctx, pk_shard, r1cs, process_group=None):
+        from .api import PROVE_PARTIAL_BYTES
+        self.ctx, self.pk, self.r1cs, self.pg = ctx, pk_shard, r1cs, process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.nbytes = PROVE_PARTIAL_BYTES
+        dev = torch.device("cuda", ctx.device)
+        self._part = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        self._parts = torch.zeros(self.world * self.nbytes, dtype=torch.uint8, device=dev)
+
+    def prove(self, z_bytes, r_bytes, s_bytes):
+        self.ctx.prove_partial(self.pk, self.r1cs, z_bytes, r_bytes, s_bytes, self._part)
+        if self.world == 1:
+            return self.ctx.prove_combine(self._part, 1, r_bytes, s_bytes)
+        dist.all_gather_into_tensor(self._parts, self._part, group=self.pg)
+        torch.cuda.current_stream().synchronize()
+        return self.ctx.prove_combine(self._parts, self.world, r_bytes, s_bytes)
