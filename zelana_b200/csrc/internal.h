@@ -86,9 +86,14 @@ struct zkb_ctx {
   cudaEvent_t copy_done[8] = {nullptr};
   zkb::Prof prof;
   zkb::DevBuf msm_ws;                             // MSM scratch (keys, sort space, buckets)
-  zkb::DevBuf msm_ws2;                            // second MSM scratch: the G2 MSM of a prove runs on aux_stream
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_inputs = nullptr, ev_aux_done = nullptr;
+  // a prove runs its MSMs side by side: B2, A, B1, L on four auxiliary lanes (own stream + MSM scratch), the witness map
+  // and H on the main stream
+  struct AuxLane {
+    cudaStream_t stream = nullptr;
+    zkb::DevBuf ws;
+    cudaEvent_t done = nullptr;
+  } aux[4];
+  cudaEvent_t ev_inputs = nullptr;
   zkb::DevBuf scal, res, tmp0, tmp1, tmp2, flag;  // staging
   zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzb, pzl, prs, ppts;  // prove scratch
   void* fr_state = nullptr;                       // NTT tables, owned by fr.cu

@@ -100,14 +100,16 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ctx->msm_ws.release();
-  ctx->msm_ws2.release();
   ctx->pzb.release();
-  if (ctx->aux_stream) {
-    cudaStreamSynchronize(ctx->aux_stream);
-    cudaStreamDestroy(ctx->aux_stream);
-    cudaEventDestroy(ctx->ev_inputs);
-    cudaEventDestroy(ctx->ev_aux_done);
+  for (auto& lane : ctx->aux) {
+    if (lane.stream) {
+      cudaStreamSynchronize(lane.stream);
+      cudaStreamDestroy(lane.stream);
+      cudaEventDestroy(lane.done);
+    }
+    lane.ws.release();
   }
+  if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
   DevBuf* bufs[] = {&ctx->scal, &ctx->res, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->flag, &ctx->pz, &ctx->pzm, &ctx->pwa,
                     &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts};
   for (DevBuf* b : bufs) b->release();
@@ -676,70 +678,73 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
   ProveOut o = prove_out(ctx);
   const size_t na = pk->a_ext->n;   // this shard's slice [off_a, off_a + na) of the nv + 2 extended scalars
 
-  // B in G2 needs only z and s, not h: it runs on a second stream (own MSM scratch) next to the witness map and the G1
-  // MSMs, filling the SMs those leave idle in their sort / reduction phases.
-  if (!ctx->aux_stream) {
-    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  // Scalar vectors of the folded MSMs (they depend on z, r, s only):
+  //   za = z[1..] || 1 || 1 || r   (A)        zb = z[1..] || 1 || 1 || s   (B1 and B2)        zl = aux || -(r s)   (L)
+  Fr* za = ctx->pza.as<Fr>();
+  Fr* zb = ctx->pzb.as<Fr>();
+  Fr* zl = ctx->pzl.as<Fr>();
+  if (nv > 1) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(za, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(zb, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, st));
+  }
+  if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(zl, z + ni, nw * 32, cudaMemcpyDeviceToDevice, st));
+  ZKB_TRY(prove_tail_scalars(ctx, rs, rs + 1, za + (nv - 1), zl + nw));
+  ZKB_TRY(prove_tail_scalars(ctx, rs + 1, rs + 1, zb + (nv - 1), zb + (nv + 2)));  // [1, 1, s]; the extra slot is scratch
+
+  // A, B1, B2 and L need only those vectors, not h: each runs on its own lane (stream + MSM scratch) next to the witness map
+  // and the H MSM of the main stream, so the latency-bound sort / reduction phases of one fill the SMs another leaves idle.
+  if (!ctx->ev_inputs) {
+    for (auto& lane : ctx->aux) {
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+      CUDA_TRY(ctx, cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
+    }
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming));
-    CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_aux_done, cudaEventDisableTiming));
   }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, st));
-  CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_inputs, 0));
-  {
-    std::swap(ctx->stream, ctx->aux_stream);
-    std::swap(ctx->msm_ws, ctx->msm_ws2);
-    Fr* zb = ctx->pzb.as<Fr>();  // z[1..] || 1 || 1 || s  (+ one scratch slot)
-    int rc = ZKB_OK;
-    if (nv > 1 && cudaMemcpyAsync(zb, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
-    if (rc == ZKB_OK) rc = prove_tail_scalars(ctx, rs + 1, rs + 1, zb + (nv - 1), zb + (nv + 2));
-    if (rc == ZKB_OK)
-      rc = msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb + pk->off_a, na, partial ? nullptr : o.oB, partial ? o.pB2 : nullptr);
-    if (rc == ZKB_OK && cudaEventRecord(ctx->ev_aux_done, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
-    std::swap(ctx->stream, ctx->aux_stream);
-    std::swap(ctx->msm_ws, ctx->msm_ws2);
-    if (rc != ZKB_OK) {
-      cudaGetLastError();
-      cudaStreamSynchronize(ctx->aux_stream);
-      if (rc == ZKB_ERR_CUDA) ctx->err = std::string(who) + ": CUDA error while queueing the G2 MSM";
-      return rc;
+  int lane_rc = ZKB_OK;
+  auto on_lane = [&](int idx, auto&& fn) {
+    auto& lane = ctx->aux[idx];
+    if (lane_rc != ZKB_OK) return;
+    if (cudaStreamWaitEvent(lane.stream, ctx->ev_inputs, 0) != cudaSuccess) {
+      lane_rc = ZKB_ERR_CUDA;
+      return;
     }
-  }
+    std::swap(ctx->stream, lane.stream);
+    std::swap(ctx->msm_ws, lane.ws);
+    int rc = fn();
+    if (rc == ZKB_OK && cudaEventRecord(lane.done, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    std::swap(ctx->stream, lane.stream);
+    std::swap(ctx->msm_ws, lane.ws);
+    if (rc != ZKB_OK) lane_rc = rc;
+  };
+  on_lane(0, [&] { return msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb + pk->off_a, na, partial ? nullptr : o.oB, partial ? o.pB2 : nullptr); });
+  on_lane(1, [&] { return msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za + pk->off_a, na, partial ? nullptr : o.oA, o.pA); });
+  on_lane(2, [&] { return msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, zb + pk->off_a, na, nullptr, o.pB1); });
+  on_lane(3, [&] { return msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl + pk->off_l, pk->l_ext->n, nullptr, o.pL); });
 
-  // h = witness_map_from_matrices
-  WitnessBufs w{z, ctx->pzm.as<Fr>(), ctx->pwa.as<Fr>(), ctx->pwb.as<Fr>(), ctx->pwc.as<Fr>()};
-  int wrc = witness_map_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, w, ctx->ph.as<Fr>());
-
-  // scalar vectors of the folded G1 MSMs
-  Fr* za = ctx->pza.as<Fr>();
-  Fr* zl = ctx->pzl.as<Fr>();
-  auto g1_part = [&]() -> int {
-    ZKB_TRY(wrc);
-    if (nv > 1) CUDA_TRY(ctx, cudaMemcpyAsync(za, z + 1, (nv - 1) * 32, cudaMemcpyDeviceToDevice, st));
-    if (nw) CUDA_TRY(ctx, cudaMemcpyAsync(zl, z + ni, nw * 32, cudaMemcpyDeviceToDevice, st));
-    ZKB_TRY(prove_tail_scalars(ctx, rs, rs + 1, za + (nv - 1), zl + nw));
-    // A = MSM(a_ext, z[1..] || 1 || 1 || r)
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za + pk->off_a, na, partial ? nullptr : o.oA, o.pA)));
-    // H: msm_bigint truncates to the shorter of (h_query, h)
+  // main stream: h = witness_map_from_matrices, then H = MSM(h_query, h) (msm_bigint truncates to the shorter of the two)
+  auto main_part = [&]() -> int {
+    WitnessBufs w{z, ctx->pzm.as<Fr>(), ctx->pwa.as<Fr>(), ctx->pwb.as<Fr>(), ctx->pwc.as<Fr>()};
+    ZKB_TRY(witness_map_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, w, ctx->ph.as<Fr>()));
     size_t hn = pk->nh < n ? pk->nh : n;
     size_t hcnt = hn > pk->off_h ? hn - pk->off_h : 0;
     if (hcnt > pk->h->n) hcnt = pk->h->n;
     ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->h, 0, ctx->ph.as<Fr>() + pk->off_h, hcnt, nullptr, o.pH)));
-    // L = MSM(l_query || delta_1, aux || -(r s))
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl + pk->off_l, pk->l_ext->n, nullptr, o.pL)));
-    // B1: same scalars with s in the last slot
-    CUDA_TRY(ctx, cudaMemcpyAsync(za + (nv + 1), rs + 1, 32, cudaMemcpyDeviceToDevice, st));
-    ZKB_TRY((msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, za + pk->off_a, na, nullptr, o.pB1)));
-    // C = s A + r B1 + L + H
-    if (!partial) ZKB_TRY(prove_assemble_c(ctx, o.pA, o.pB1, o.pL, o.pH, rs, rs + 1, o.oC));
     return ZKB_OK;
   };
-  int grc = g1_part();
-  // join the G2 stream in every case before returning: its work reads buffers owned by this context
-  cudaStreamWaitEvent(st, ctx->ev_aux_done, 0);
-  if (grc != ZKB_OK) {
-    cudaStreamSynchronize(ctx->aux_stream);
-    return grc;
+  int mrc = lane_rc == ZKB_OK ? main_part() : ZKB_OK;
+  // join every lane before anything else: their work reads buffers owned by this context
+  bool joined = true;
+  for (auto& lane : ctx->aux)
+    if (cudaStreamWaitEvent(st, lane.done, 0) != cudaSuccess) joined = false;
+  if (lane_rc != ZKB_OK || mrc != ZKB_OK || !joined) {
+    cudaGetLastError();
+    for (auto& lane : ctx->aux) cudaStreamSynchronize(lane.stream);
+    if (lane_rc == ZKB_ERR_CUDA || !joined) ctx->err = std::string(who) + ": CUDA error while queueing the MSM lanes";
+    return lane_rc != ZKB_OK ? lane_rc : (mrc != ZKB_OK ? mrc : ZKB_ERR_CUDA);
   }
+  // C = s A + r B1 + L + H
+  if (!partial) ZKB_TRY(prove_assemble_c(ctx, o.pA, o.pB1, o.pL, o.pH, rs, rs + 1, o.oC));
   return ZKB_OK;
 }
 
