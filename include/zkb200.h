@@ -176,6 +176,27 @@ int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h
 int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
               const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
 
+/* ---- trusted setup: ark-groth16 generate_parameters_with_qap (Groth16::circuit_specific_setup, keygen.rs:87-91) -------- */
+typedef struct {
+  uint8_t alpha[32], beta[32], gamma[32], delta[32], tau[32]; /* canonical Fr, the toxic waste (caller's RNG) */
+  uint8_t g1_generator[64];                                    /* the random generators arkworks draws (G1::rand, G2::rand) */
+  uint8_t g2_generator[128];
+} zkb_setup_params;
+
+typedef struct { /* caller-allocated host buffers, raw canonical affine (infinity = zeros) */
+  uint8_t *alpha_g1, *beta_g1, *delta_g1; /* 64 B each */
+  uint8_t *beta_g2, *gamma_g2, *delta_g2; /* 128 B each */
+  uint8_t* gamma_abc_g1;                  /* num_instance x 64 */
+  uint8_t* a_query;                       /* (num_instance + num_witness) x 64 */
+  uint8_t* b_g1_query;                    /* same */
+  uint8_t* b_g2_query;                    /* same x 128 */
+  uint8_t* h_query;                       /* (domain_size - 1) x 64 */
+  uint8_t* l_query;                       /* num_witness x 64 */
+} zkb_setup_out;
+
+/* Errors: ZKB_ERR_INVALID_ARG if tau is a domain element or gamma / delta is zero; ZKB_ERR_NOT_CANONICAL for values >= r. */
+int zkb_setup(zkb_ctx* ctx, const zkb_r1cs_desc* desc, const zkb_setup_params* params, const zkb_setup_out* out);
+
 /* ---- one proof over several GPUs (MSMs sharded by contiguous range of the key's query vectors) ----------
  * Rank `shard` of `world` loads its range of the key (zkb_pk_load_shard), runs zkb_prove_partial (witness map replicated,
  * five MSMs over its range) and contributes ZKB_PROVE_PARTIAL_BYTES; the records are all-gathered (NCCL) and any rank

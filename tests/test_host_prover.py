@@ -83,3 +83,81 @@ def test_groth16_prover_from_bytes_prove_matches_reference_flow():
         assert p.verification_key_hash() == blake3.blake3(pk.vk.serialize_compressed()).digest()
     finally:
         p.close()
+
+
+# ----------------------------------------------------------------------------- keygen host pieces (zelana_b200/keygen.py)
+def test_keygen_sampling_and_compression_match_oracle():
+    from zelana_b200 import keygen as kg
+    assert kg.B_G2 == bn.B_G2 and kg.G2_COFACTOR == bn.G2_COFACTOR
+    for seed in (0, 42, 9):
+        a, b = zp.StdRng.seed_from_u64(seed), orng.StdRng.seed_from_u64(seed)
+        for _ in range(4):
+            assert zp.fr_rand(a) == orng.rand_fr(b)
+        assert kg.g1_rand(a) == orng.rand_g1(b)
+        g2u = kg.g2_rand_uncleared(a)
+        assert bn.G2.mul(g2u, bn.G2_COFACTOR) == orng.rand_g2(b)      # the product clears the cofactor on the GPU
+        assert zp.fr_rand(a) == orng.rand_fr(b)                       # streams still aligned afterwards
+    g = bn.G1.mul(bn.G1_GEN, 12345)
+    for pt in (g, bn.G1.neg(g), None):
+        assert kg.g1_compress(bn.g1_to_raw(pt)) == bn.g1_serialize(pt)
+    h = bn.G2.mul(bn.G2_GEN, 777)
+    for pt in (h, bn.G2.neg(h), None):
+        assert kg.g2_compress(bn.g2_to_raw(pt)) == bn.g2_serialize(pt)
+
+
+@pytest.mark.gpu
+def test_gpu_keygen_reproduces_reference_vk_and_proof():
+    """keygen on the GPU with StdRng(42), as prover/src/snarkjs.rs:141-176 does for SquareCircuit: the verifying key equals
+    the reference's committed vk_snarkjs.json, the key bytes equal the oracle's, and proving with it on the same RNG stream
+    reproduces the committed proof."""
+    import zelana_b200
+    from zelana_b200 import keygen as kg
+    from helpers import fr_bytes
+    r1cs, z = g16.square_circuit(7)
+    ctx = zelana_b200.Context(0)
+    try:
+        rng = zp.StdRng.seed_from_u64(42)
+        pk_bytes, vk_bytes, _ = kg.circuit_specific_setup(ctx, r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c, rng)
+        orc_rng = orng.StdRng.seed_from_u64(42)
+        opk = g16.circuit_specific_setup(r1cs, orc_rng)
+        assert vk_bytes == opk.vk.serialize_compressed()
+        assert pk_bytes == opk.serialize_compressed()
+        v = json.load(open(os.path.join(REF_FIXTURES, "vk_snarkjs.json")))
+        vk = g16.VerifyingKey.deserialize_compressed(vk_bytes)
+        assert vk.alpha_g1 == (int(v["vk_alpha_1"][0]), int(v["vk_alpha_1"][1]))
+        assert [p for p in vk.gamma_abc_g1] == [(int(p[0]), int(p[1])) for p in v["IC"]]
+        # prove on the SAME stream (snarkjs.rs:156-159) from the GPU-made key
+        r, s = zp.fr_rand(rng), zp.fr_rand(rng)
+        m = ctx.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+        a, b, c = ctx.prove(ctx.proving_key_compressed(pk_bytes), m, fr_bytes(z), fr_bytes([r]), fr_bytes([s]))
+        proof = g16.Proof(bn.g1_from_raw(a), bn.g2_from_raw(b), bn.g1_from_raw(c))
+        pc = json.load(open(os.path.join(REF_FIXTURES, "proof_for_onchain.json")))["proof_components"]
+        assert proof.serialize_uncompressed() == bytes(pc["pi_a"]) + bytes(pc["pi_b"]) + bytes(pc["pi_c"])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_keygen_mimc_matches_oracle_and_proofs_verify():
+    import zelana_b200
+    from zelana_b200 import keygen as kg
+    from helpers import fr_bytes, mimc7_chain
+    r1cs, z = mimc7_chain(num_perm=2, seed=42, rounds=20)
+    ctx = zelana_b200.Context(0)
+    try:
+        pk_bytes, vk_bytes, _ = kg.circuit_specific_setup(ctx, r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c,
+                                                          zp.StdRng.seed_from_u64(0))          # keygen.rs:87: seed 0
+        opk = g16.circuit_specific_setup(r1cs, orng.StdRng.seed_from_u64(0))
+        assert pk_bytes == opk.serialize_compressed() and vk_bytes == opk.vk.serialize_compressed()
+        p = zp.Groth16Prover(ctx, ctx.proving_key_compressed(pk_bytes), vk_bytes)
+        m = p.circuit(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+        got = p.prove_assignment(zp.BatchPublicInputs(batch_id=5), m, fr_bytes(z))
+        ref = g16.prove(opk, r1cs, z, orng.StdRng.seed_from_u64(5))
+        assert got.proof_bytes == ref.to_solana_bytes()
+        assert g16.verify(g16.VerifyingKey.deserialize_compressed(vk_bytes), [z[1]], ref)
+        # a trapdoor inside the domain is refused
+        with pytest.raises(zelana_b200.ZkbError):
+            ctx.setup(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c, alpha=1, beta=2, gamma=3, delta=4, tau=1,
+                      g1_generator=bn.g1_to_raw(bn.G1_GEN), g2_generator=bn.g2_to_raw(bn.G2_GEN))
+    finally:
+        ctx.close()

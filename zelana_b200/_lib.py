@@ -34,6 +34,16 @@ class PkDesc(C.Structure):
                 ("l_query", C.c_void_p), ("l_len", C.c_size_t)]
 
 
+class SetupParams(C.Structure):
+    _fields_ = [("alpha", C.c_uint8 * 32), ("beta", C.c_uint8 * 32), ("gamma", C.c_uint8 * 32), ("delta", C.c_uint8 * 32),
+                ("tau", C.c_uint8 * 32), ("g1_generator", C.c_uint8 * 64), ("g2_generator", C.c_uint8 * 128)]
+
+
+class SetupOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("alpha_g1", "beta_g1", "delta_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1",
+                                          "a_query", "b_g1_query", "b_g2_query", "h_query", "l_query")]
+
+
 _P = C.c_void_p
 _SZ = C.c_size_t
 _I = C.c_int
@@ -85,6 +95,7 @@ SIGNATURES = {
     "zkb_pk_free": (None, [_P]),
     "zkb_pk_synthetic": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, C.POINTER(_P)]),
     "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "zkb_setup": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(SetupParams), C.POINTER(SetupOut)]),
     "zkb_pk_load_shard": (_I, [_P, C.POINTER(PkDesc), _I, _I, _I, C.POINTER(_P)]),
     "zkb_pk_synthetic_shard": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, _I, _I, C.POINTER(_P)]),
     "zkb_prove_partial": (_I, [_P, _P, _P, _P, _P, _P, _P]),

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import ZkbError, load_library, R1csDesc, PkDesc, Csr
+from ._lib import ZkbError, load_library, R1csDesc, PkDesc, Csr, SetupParams, SetupOut
 
 FR, FQ = 0, 1
 OP_ADD, OP_SUB, OP_MUL, OP_INV, OP_NEG = range(5)
@@ -208,6 +208,37 @@ class Context:
         pk = ProvingKeyDev.__new__(ProvingKeyDev)
         pk.ctx, pk.h = self, h
         return pk
+
+    def setup(self, num_instance, num_witness, a, b, c, *, alpha, beta, gamma, delta, tau, g1_generator, g2_generator):
+        """Groth16 parameter generation on the GPU (zkb_setup) from explicit toxic waste -> dict of raw affine byte strings."""
+        csr = [m if isinstance(m, tuple) else _csr_arrays(m) for m in (a, b, c)]
+        keep = []
+        d = R1csDesc()
+        d.num_constraints, d.num_instance, d.num_witness = len(csr[0][0]) - 1, num_instance, num_witness
+        for name, (rp, col, co) in zip(("a", "b", "c"), csr):
+            rp = np.ascontiguousarray(rp, dtype=np.uint64)
+            col = np.ascontiguousarray(col, dtype=np.uint32)
+            co = np.ascontiguousarray(co, dtype=np.uint8).reshape(-1)
+            keep += [rp, col, co]
+            setattr(d, name, Csr(rp.ctypes.data, col.ctypes.data, co.ctypes.data))
+        prm = SetupParams()
+        for name, v in (("alpha", alpha), ("beta", beta), ("gamma", gamma), ("delta", delta), ("tau", tau)):
+            getattr(prm, name)[:] = list(int(v).to_bytes(32, "little"))
+        prm.g1_generator[:] = list(g1_generator)
+        prm.g2_generator[:] = list(g2_generator)
+        nv = num_instance + num_witness
+        n = 1
+        while n < d.num_constraints + num_instance:
+            n <<= 1
+        sizes = {"alpha_g1": 64, "beta_g1": 64, "delta_g1": 64, "beta_g2": 128, "gamma_g2": 128, "delta_g2": 128,
+                 "gamma_abc_g1": 64 * num_instance, "a_query": 64 * nv, "b_g1_query": 64 * nv, "b_g2_query": 128 * nv,
+                 "h_query": 64 * (n - 1), "l_query": 64 * num_witness}
+        bufs = {k: np.zeros(max(v, 1), dtype=np.uint8) for k, v in sizes.items()}
+        out = SetupOut()
+        for k, arr in bufs.items():
+            setattr(out, k, arr.ctypes.data)
+        self._check(self.lib.zkb_setup(self.h, C.byref(d), C.byref(prm), C.byref(out)))
+        return {k: bufs[k][:sizes[k]].tobytes() for k in sizes}
 
     def witness_map(self, r1cs, z_bytes):
         pz, kz = _buf(z_bytes)

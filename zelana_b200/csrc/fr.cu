@@ -112,6 +112,72 @@ __global__ void prove_tail_scalars_kernel(const Fr* r, const Fr* s, Fr* za_tail,
   zl_tail[0] = rs.neg();
 }
 
+// ---- trusted setup (ark-groth16 generate_parameters_with_qap; prover/src/bin/keygen.rs:87-91) -----------------------------
+// consts (Montgomery): [0] tau, [1] alpha, [2] beta, [3] gamma^-1, [4] delta^-1, [5] zt = tau^n - 1, [6] zt / n, [7] zt / delta
+__global__ void setup_consts_kernel(const Fr* in /* canonical: tau, alpha, beta, gamma, delta */, int logn, Fr* c, int* bad) {
+  if (blockIdx.x || threadIdx.x) return;
+  Fr tau = in[0].to_mont(), gamma = in[3].to_mont(), delta = in[4].to_mont();
+  for (int i = 0; i < 5; i++)
+    if (!fr_is_canonical(in[i])) { atomicExch(bad, 1); return; }
+  Fr tn = tau;
+  for (int k = 0; k < logn; k++) tn = tn.sqr();
+  Fr zt = tn - Fr::one();
+  if (zt.is_zero() || gamma.is_zero() || delta.is_zero()) { atomicExch(bad, 5); return; }  // tau in the domain / zero trapdoor
+  Fr ninv = fr_base(FRB_INV2);
+  Fr nacc = Fr::one();
+  for (int k = 0; k < logn; k++) nacc = nacc * ninv;
+  Fr dinv = delta.inverse_vartime();
+  c[0] = tau;
+  c[1] = in[1].to_mont();
+  c[2] = in[2].to_mont();
+  c[3] = gamma.inverse_vartime();
+  c[4] = dinv;
+  c[5] = zt;
+  c[6] = zt * nacc;
+  c[7] = zt * dinv;
+}
+
+// u[i] = L_i(tau) = zt / n * omega^i / (tau - omega^i)     (Montgomery)
+__global__ void setup_lagrange_kernel(PowTable omega, const Fr* __restrict__ c, size_t n, Fr* __restrict__ u) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr w = i ? pow_lookup(omega, i) : Fr::one();
+  Fr d = ldg_fr(c + 0) - w;
+  store_fr(u + i, ldg_fr(c + 6) * w * d.inverse());
+}
+
+// Column j of the three matrices (CSC): a_j = sum_k A[k][j] u_k (+ u_{nc + j} for an instance column), b_j, c_j.
+// Outputs, all CANONICAL (they become fixed-base scalars): a_j, b_j, and (beta a_j + alpha b_j + c_j) / gamma for instance
+// columns (gamma_abc) or / delta for witness columns (l).
+struct CscDev {
+  const uint64_t* col_ptr;
+  const uint32_t* row;
+  const Fr* coeff;  // Montgomery
+};
+__device__ __forceinline__ Fr csc_dot(const CscDev& m, size_t j, const Fr* __restrict__ u) {
+  Fr acc = Fr::zero();
+  for (uint64_t k = m.col_ptr[j]; k < m.col_ptr[j + 1]; k++) acc = acc + ldg_fr(m.coeff + k) * ldg_fr(u + m.row[k]);
+  return acc;
+}
+__global__ void setup_columns_kernel(CscDev A, CscDev B, CscDev C, const Fr* __restrict__ u, const Fr* __restrict__ c, uint64_t nc,
+                                     uint64_t ni, size_t nv, Fr* __restrict__ a_out, Fr* __restrict__ b_out, Fr* __restrict__ abc_out) {
+  size_t j = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= nv) return;
+  Fr a = csc_dot(A, j, u), b = csc_dot(B, j, u), cc = csc_dot(C, j, u);
+  if (j < ni) a = a + ldg_fr(u + nc + j);
+  Fr abc = (ldg_fr(c + 2) * a + ldg_fr(c + 1) * b + cc) * ldg_fr(c + (j < ni ? 3 : 4));
+  store_fr(a_out + j, a.from_mont());
+  store_fr(b_out + j, b.from_mont());
+  store_fr(abc_out + j, abc.from_mont());
+}
+
+// h scalar i = tau^i * zt / delta, i < n - 1 (canonical); also the three constants alpha, beta, delta / gamma for the fixed points
+__global__ void setup_h_scalars_kernel(const Fr* __restrict__ c, size_t count, Fr* __restrict__ out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  store_fr(out + i, (fr_pow_u64(ldg_fr(c + 0), (unsigned long long)i) * ldg_fr(c + 7)).from_mont());
+}
+
 int ensure_wr(zkb_ctx* ctx, FrState* S) {
   if (S->wr_fwd) return ZKB_OK;
   const uint32_t cnt = 1u << (NTT_LRMAX - 1);
@@ -290,6 +356,27 @@ int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int
     logm -= lr;
   }
   if (npass == 1 && in == out) CUDA_TRY(ctx, cudaMemcpyAsync(out, scratch[0], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  return ZKB_OK;
+}
+
+// Setup scalars on the device.  in5: canonical tau, alpha, beta, gamma, delta (device).  Outputs (device, canonical):
+// a_out, b_out, abc_out (nv each), h_out (n - 1).  The CSC arrays are device pointers with Montgomery coefficients.
+int setup_scalars_dev(zkb_ctx* ctx, const uint64_t* const col_ptr[3], const uint32_t* const row[3], const Fr* const coeff[3],
+                      uint64_t nc, uint64_t ni, uint64_t nw, int logn, const Fr* in5, Fr* consts, Fr* u, Fr* a_out, Fr* b_out,
+                      Fr* abc_out, Fr* h_out) {
+  const size_t n = size_t(1) << logn, nv = ni + nw;
+  FrState* S = state(ctx);
+  NttTables* T = nullptr;
+  ZKB_TRY(ensure_ntt_tables(ctx, S, logn, &T));
+  ZKB_TRY(clear_flag(ctx));
+  cudaStream_t st = ctx->stream;
+  setup_consts_kernel<<<1, 32, 0, st>>>(in5, logn, consts, ctx->flag.as<int>());
+  setup_lagrange_kernel<<<blocks_for(n, 128), 128, 0, st>>>(T->fwd, consts, n, u);
+  CscDev A{col_ptr[0], row[0], coeff[0]}, B{col_ptr[1], row[1], coeff[1]}, C{col_ptr[2], row[2], coeff[2]};
+  setup_columns_kernel<<<blocks_for(nv, 128), 128, 0, st>>>(A, B, C, u, consts, nc, ni, nv, a_out, b_out, abc_out);
+  if (n > 1) setup_h_scalars_kernel<<<blocks_for(n - 1, 128), 128, 0, st>>>(consts, n - 1, h_out);
+  ctx->launches += 4;
+  CUDA_TRY(ctx, cudaGetLastError());
   return ZKB_OK;
 }
 

@@ -405,6 +405,41 @@ void fixed_table_free(zkb_ctx* ctx) {
   *slot = nullptr;
 }
 
+// Fixed-base batch multiplication by an ARBITRARY generator (the setup's random g1 / g2): window table for that point, one
+// thread per scalar, results exported as canonical affine bytes to the host.
+template <class F>
+int fixed_base_batch(zkb_ctx* ctx, const uint8_t* generator_raw, const void* scalars_dev, size_t n, uint8_t* out_host) {
+  if (n == 0) return ZKB_OK;
+  Affine<F>* table = nullptr;
+  Affine<F>* pts = nullptr;
+  uint32_t* raw = nullptr;
+  auto cleanup = [&]() {
+    if (table) cudaFree(table);
+    if (pts) cudaFree(pts);
+    if (raw) cudaFree(raw);
+  };
+  auto run = [&]() -> int {
+    CUDA_TRY(ctx, cudaMalloc(&table, 32 * 255 * sizeof(Affine<F>)));
+    CUDA_TRY(ctx, cudaMalloc(&pts, n * sizeof(Affine<F>)));
+    CUDA_TRY(ctx, cudaMalloc(&raw, n * sizeof(Affine<F>)));
+    CUDA_TRY(ctx, ctx->tmp1.reserve(sizeof(Affine<F>)));
+    ZKB_TRY(import_points<F>(ctx, generator_raw, 1, 1, ctx->tmp1.as<Affine<F>>()));
+    Affine<F> g;
+    CUDA_TRY(ctx, cudaMemcpy(&g, ctx->tmp1.p, sizeof(g), cudaMemcpyDeviceToHost));
+    fixed_base_table_kernel<F><<<blocks_for(32 * 255, 64), 64, 0, ctx->stream>>>(g, table);
+    fixed_base_mul_kernel<F><<<blocks_for(n, 64), 64, 0, ctx->stream>>>(table, static_cast<const uint32_t*>(scalars_dev), n, pts);
+    affine_export_kernel<F><<<blocks_for(n, 128), 128, 0, ctx->stream>>>(pts, raw, n);
+    ctx->launches += 3;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_host, raw, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKB_OK;
+  };
+  int s = run();
+  cleanup();
+  return s;
+}
+
 template <class F>
 int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename GroupOf<F>::Bases** out) {
   using H = typename GroupOf<F>::Bases;
@@ -525,6 +560,7 @@ int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
   template int msm_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, void*, void*);              \
   template int msm_host_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const uint8_t*, size_t, uint8_t*);              \
   template int msm_combine_impl<F>(zkb_ctx*, const void*, int, void*);                                                      \
-  template void fixed_table_free<F>(zkb_ctx*);
+  template void fixed_table_free<F>(zkb_ctx*);                                                                             \
+  template int fixed_base_batch<F>(zkb_ctx*, const uint8_t*, const void*, size_t, uint8_t*);
 
 }  // namespace zkb

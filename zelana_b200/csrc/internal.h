@@ -184,6 +184,8 @@ template <class F> int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Ba
                                      size_t n, uint8_t* out);
 template <class F> int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out);
 template <class F> void fixed_table_free(zkb_ctx* ctx);
+// out_host[i] = scalars_dev[i] * generator  (canonical 32 B scalars on the device; raw canonical affine out; zero -> infinity)
+template <class F> int fixed_base_batch(zkb_ctx* ctx, const uint8_t* generator_raw, const void* scalars_dev, size_t n, uint8_t* out_host);
 
 // g1.cu
 int fq_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
@@ -212,6 +214,9 @@ struct WitnessBufs {
 int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
                     int log_domain, const WitnessBufs& w, Fr* h_out);
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail);
+int setup_scalars_dev(zkb_ctx* ctx, const uint64_t* const col_ptr[3], const uint32_t* const row[3], const Fr* const coeff[3],
+                      uint64_t nc, uint64_t ni, uint64_t nw, int logn, const Fr* in5, Fr* consts, Fr* u, Fr* a_out, Fr* b_out,
+                      Fr* abc_out, Fr* h_out);
 
 }  // namespace zkb
 

@@ -636,6 +636,159 @@ extern "C" int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witnes
   return zkb_pk_synthetic_shard(ctx, num_vars, num_witness, h_len, k_dev, k_len, 0, 1, out);
 }
 
+// =============================================================================================== trusted setup
+namespace {
+
+// CSR (rows = constraints) -> CSC (columns = variables) on the host, coefficients kept as 32-byte canonical records
+struct CscHost {
+  std::vector<uint64_t> col_ptr;
+  std::vector<uint32_t> row;
+  std::vector<uint8_t> coeff;
+};
+
+int csr_to_csc(zkb_ctx* ctx, const zkb_csr& m, uint64_t nc, uint64_t nv, CscHost& out) {
+  if (!m.row_ptr) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_setup: null row_ptr");
+  const uint64_t nnz = m.row_ptr[nc];
+  if (nnz && (!m.col || !m.coeff)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_setup: null col/coeff");
+  out.col_ptr.assign(nv + 1, 0);
+  for (uint64_t k = 0; k < nnz; k++) {
+    if (m.col[k] >= nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_setup: column %u >= %llu variables", m.col[k], (unsigned long long)nv);
+    out.col_ptr[m.col[k] + 1]++;
+  }
+  for (uint64_t j = 0; j < nv; j++) out.col_ptr[j + 1] += out.col_ptr[j];
+  out.row.resize(nnz ? nnz : 1);
+  out.coeff.resize((nnz ? nnz : 1) * 32);
+  std::vector<uint64_t> cursor(out.col_ptr.begin(), out.col_ptr.end() - 1);
+  for (uint64_t i = 0; i < nc; i++) {
+    if (m.row_ptr[i + 1] < m.row_ptr[i]) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_setup: row_ptr not monotone at row %llu", (unsigned long long)i);
+    for (uint64_t k = m.row_ptr[i]; k < m.row_ptr[i + 1]; k++) {
+      uint64_t dst = cursor[m.col[k]]++;
+      out.row[dst] = uint32_t(i);
+      memcpy(&out.coeff[dst * 32], m.coeff + k * 32, 32);
+    }
+  }
+  return ZKB_OK;
+}
+
+}  // namespace
+
+// Groth16 parameter generation (ark-groth16 generate_parameters_with_qap, reached from prover/src/bin/keygen.rs:87-91 through
+// Groth16::circuit_specific_setup): Lagrange coefficients at tau, QAP column evaluations, then fixed-base batch multiplications
+// of the (random) generators -- all on the GPU.  The randomness (alpha, beta, gamma, delta, tau, g1, g2) is the caller's:
+// zelana_b200/keygen.py draws it from StdRng exactly as arkworks does.
+extern "C" int zkb_setup(zkb_ctx* ctx, const zkb_r1cs_desc* d, const zkb_setup_params* prm, const zkb_setup_out* o) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!d || !prm || !o) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_setup: null argument");
+  if (d->num_instance < 1) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_setup: num_instance must include the constant ONE");
+  if (!o->alpha_g1 || !o->beta_g1 || !o->delta_g1 || !o->beta_g2 || !o->gamma_g2 || !o->delta_g2 || !o->gamma_abc_g1 ||
+      !o->a_query || !o->b_g1_query || !o->b_g2_query || !o->h_query || (!o->l_query && d->num_witness))
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_setup: null output buffer");
+  const uint64_t nc = d->num_constraints, ni = d->num_instance, nw = d->num_witness, nv = ni + nw;
+  int lg = 0;
+  while ((uint64_t(1) << lg) < nc + ni) lg++;
+  if (lg > 28) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_setup: domain 2^%d exceeds Fr two-adicity 28", lg);
+  const size_t n = size_t(1) << lg;
+  ZKB_TRY(set_device(ctx));
+  cudaStream_t st = ctx->stream;
+
+  CscHost csc[3];
+  try {
+    ZKB_TRY(csr_to_csc(ctx, d->a, nc, nv, csc[0]));
+    ZKB_TRY(csr_to_csc(ctx, d->b, nc, nv, csc[1]));
+    ZKB_TRY(csr_to_csc(ctx, d->c, nc, nv, csc[2]));
+  } catch (const std::bad_alloc&) {
+    ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_setup: host allocation failed");
+  }
+  // device buffers, freed on every exit path
+  std::vector<void*> owned;
+  auto dmalloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 32) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    owned.push_back(p);
+    return p;
+  };
+  auto run = [&]() -> int {
+    const uint64_t* col_ptr[3];
+    const uint32_t* row[3];
+    const Fr* coeff[3];
+    for (int t = 0; t < 3; t++) {
+      size_t nnz = csc[t].col_ptr[nv];
+      uint64_t* cp = static_cast<uint64_t*>(dmalloc((nv + 1) * 8));
+      uint32_t* rw = static_cast<uint32_t*>(dmalloc(nnz * 4));
+      Fr* raw = static_cast<Fr*>(dmalloc(nnz * 32));
+      Fr* co = static_cast<Fr*>(dmalloc(nnz * 32));
+      if (!cp || !rw || !raw || !co) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_setup: device allocation failed");
+      CUDA_TRY(ctx, cudaMemcpyAsync(cp, csc[t].col_ptr.data(), (nv + 1) * 8, cudaMemcpyHostToDevice, st));
+      if (nnz) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(rw, csc[t].row.data(), nnz * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpyAsync(raw, csc[t].coeff.data(), nnz * 32, cudaMemcpyHostToDevice, st));
+        ZKB_TRY(clear_flag(ctx));
+        ZKB_TRY(fr_to_mont(ctx, raw, co, nnz));
+        ZKB_TRY(check_flag(ctx, "zkb_setup: matrix coefficient"));
+      }
+      col_ptr[t] = cp;
+      row[t] = rw;
+      coeff[t] = co;
+    }
+    Fr* in5 = static_cast<Fr*>(dmalloc(5 * 32));
+    Fr* consts = static_cast<Fr*>(dmalloc(8 * 32));
+    Fr* u = static_cast<Fr*>(dmalloc(n * 32));
+    Fr* a_s = static_cast<Fr*>(dmalloc(nv * 32));
+    Fr* b_s = static_cast<Fr*>(dmalloc(nv * 32));
+    Fr* abc_s = static_cast<Fr*>(dmalloc(nv * 32));
+    Fr* h_s = static_cast<Fr*>(dmalloc(n * 32));
+    Fr* k3 = static_cast<Fr*>(dmalloc(6 * 32));
+    if (!in5 || !consts || !u || !a_s || !b_s || !abc_s || !h_s || !k3) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_setup: device allocation failed");
+    uint8_t host5[5 * 32];
+    memcpy(host5, prm->tau, 32);
+    memcpy(host5 + 32, prm->alpha, 32);
+    memcpy(host5 + 64, prm->beta, 32);
+    memcpy(host5 + 96, prm->gamma, 32);
+    memcpy(host5 + 128, prm->delta, 32);
+    CUDA_TRY(ctx, cudaMemcpyAsync(in5, host5, sizeof(host5), cudaMemcpyHostToDevice, st));
+    ZKB_TRY(setup_scalars_dev(ctx, col_ptr, row, coeff, nc, ni, nw, lg, in5, consts, u, a_s, b_s, abc_s, h_s));
+    {
+      int h = 0;
+      CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      if (h == 1) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "zkb_setup: a trapdoor value is >= the Fr modulus");
+      if (h == 5) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_setup: tau lies in the evaluation domain, or gamma / delta is zero");
+    }
+    // fixed constants: [alpha, beta, delta] on g1 ; [beta, gamma, delta] on g2
+    uint8_t hostk[6 * 32];
+    memcpy(hostk, prm->alpha, 32);
+    memcpy(hostk + 32, prm->beta, 32);
+    memcpy(hostk + 64, prm->delta, 32);
+    memcpy(hostk + 96, prm->beta, 32);
+    memcpy(hostk + 128, prm->gamma, 32);
+    memcpy(hostk + 160, prm->delta, 32);
+    CUDA_TRY(ctx, cudaMemcpyAsync(k3, hostk, sizeof(hostk), cudaMemcpyHostToDevice, st));
+    uint8_t c1[3 * 64], c2[3 * 128];
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, k3, 3, c1));
+    ZKB_TRY(fixed_base_batch<Fq2>(ctx, prm->g2_generator, k3 + 3, 3, c2));
+    memcpy(o->alpha_g1, c1, 64);
+    memcpy(o->beta_g1, c1 + 64, 64);
+    memcpy(o->delta_g1, c1 + 128, 64);
+    memcpy(o->beta_g2, c2, 128);
+    memcpy(o->gamma_g2, c2 + 128, 128);
+    memcpy(o->delta_g2, c2 + 256, 128);
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, a_s, nv, o->a_query));
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, b_s, nv, o->b_g1_query));
+    ZKB_TRY(fixed_base_batch<Fq2>(ctx, prm->g2_generator, b_s, nv, o->b_g2_query));
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, abc_s, ni, o->gamma_abc_g1));
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, abc_s + ni, nw, o->l_query));
+    ZKB_TRY(fixed_base_batch<Fq>(ctx, prm->g1_generator, h_s, n - 1, o->h_query));
+    return ZKB_OK;
+  };
+  int rc = run();
+  cudaStreamSynchronize(st);
+  for (void* p : owned) cudaFree(p);
+  return rc;
+}
+
 namespace {
 
 struct ProveOut {
