@@ -546,3 +546,36 @@ def test_sharded_prove_equals_prove(ctx, mimc_setup, world):
         dpk.free()
     ref0 = g16.prove_with_rs(pk, r1cs, z, 0, 9)
     assert ctx.prove_combine(parts, world, fr_bytes([0]), fr_bytes([9])) == (bn.g1_to_raw(ref0.a), bn.g2_to_raw(ref0.b), bn.g1_to_raw(ref0.c))
+
+
+def test_l2_sized_keygen_prove_verify_end_to_end(ctx):
+    """The whole reference flow at the L2BlockCircuit::dummy() size (domain 2^13) with nothing but this library on the GPU:
+    keygen (seed 0, keygen.rs:87) -> compressed key bytes -> from_bytes -> prove(batch_id) -> the oracle's pairing check."""
+    import importlib.util
+    import os
+    import numpy as np
+    from conftest import ROOT
+    from oracle import cpu as orc
+    from zelana_b200 import keygen as kg
+    from zelana_b200 import prover as zp
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ni, nw, (A, B, Cm), z = bench.mimc_r1cs_numpy(np, num_perm=22, seed=78)
+    pk_bytes, vk_bytes, raw = kg.circuit_specific_setup(ctx, ni, nw, A, B, Cm, zp.StdRng.seed_from_u64(0))
+    vk = g16.VerifyingKey.deserialize_compressed(vk_bytes)
+    dpk = ctx.proving_key_compressed(pk_bytes)
+    m = ctx.r1cs(ni, nw, A, B, Cm)
+    zb = z.reshape(-1)
+    public = [int.from_bytes(z[1].tobytes(), "little")]
+    for batch_id in (0, 3):
+        rng = zp.StdRng.seed_from_u64(batch_id)
+        r, s = zp.fr_rand(rng), zp.fr_rand(rng)
+        a, b, c = ctx.prove(dpk, m, zb, fr_bytes([r]), fr_bytes([s]))
+        proof = g16.Proof(bn.g1_from_raw(a), bn.g2_from_raw(b), bn.g1_from_raw(c))
+        assert g16.verify(vk, public, proof)
+        assert not g16.verify(vk, [public[0] + 1], proof)
+        # and the C++ restatement proves the same bytes from the same (raw) key
+        cpk = orc.ProvingKey(**{k: raw[k] for k in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query",
+                                                    "b_g1_query", "b_g2_query", "h_query", "l_query")})
+        assert orc.prove(cpk, orc.R1cs(ni, nw, csr=(A, B, Cm)), zb, fr_bytes([r]), fr_bytes([s])) == (a, b, c)
