@@ -275,10 +275,14 @@ int bases_alloc(zkb_ctx* ctx, size_t n, typename GroupOf<F>::Bases** out) {
   if (c <= 0 || double(msm_windows_for(c)) * double(n) >= 2147483648.0)
     ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: no window width fits %zu points in %zu MB of free device memory", n, free_b >> 20);
   int nwin = msm_windows_for(c);
-  H* h = new (std::nothrow) H{ctx->device, nullptr, n, c, nwin};
+  H* h = new (std::nothrow) H{ctx->device, nullptr, n, c, nwin, nullptr};
   if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: host allocation failed");
   if (n) {
     cudaError_t e = cudaMalloc(&h->p, size_t(nwin) * n * sizeof(Affine<F>));
+    if (e == cudaSuccess) {
+      e = cudaMalloc(&h->inf_mask, n);
+      if (e != cudaSuccess) cudaFree(h->p);
+    }
     if (e != cudaSuccess) {
       cudaGetLastError();
       delete h;
@@ -291,7 +295,10 @@ int bases_alloc(zkb_ctx* ctx, size_t n, typename GroupOf<F>::Bases** out) {
 
 template <class F>
 int build_window_tables(zkb_ctx* ctx, typename GroupOf<F>::Bases* h) {
-  if (h->n == 0 || h->nwin <= 1) return ZKB_OK;
+  if (h->n == 0) return ZKB_OK;
+  inf_mask_kernel<F><<<blocks_for(h->n, 256), 256, 0, ctx->stream>>>(h->p, h->n, h->inf_mask);
+  ctx->launches++;
+  if (h->nwin <= 1) return ZKB_OK;
   window_tables_kernel<F><<<blocks_for(h->n, 128), 128, 0, ctx->stream>>>(h->p, h->n, h->c, h->nwin);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -312,6 +319,7 @@ int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, t
     if (s == ZKB_OK) s = build_window_tables<F>(ctx, h);
     if (s != ZKB_OK) {
       cudaFree(h->p);
+      cudaFree(h->inf_mask);
       delete h;
       return s;
     }
@@ -346,6 +354,7 @@ int bases_load_compressed_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int 
     s = run();
     if (s != ZKB_OK) {
       cudaFree(h->p);
+      cudaFree(h->inf_mask);
       delete h;
       return s;
     }
@@ -457,12 +466,14 @@ int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename Grou
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) {
       cudaFree(h->p);
+      cudaFree(h->inf_mask);
       delete h;
       ZKB_FAIL(ctx, ZKB_ERR_CUDA, "fixed_base_mul_kernel: %s", cudaGetErrorString(e2));
     }
     int s = build_window_tables<F>(ctx, h);
     if (s != ZKB_OK) {
       cudaFree(h->p);
+      cudaFree(h->inf_mask);
       delete h;
       return s;
     }
@@ -491,6 +502,7 @@ void bases_free_impl(typename GroupOf<F>::Bases* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   if (b->p) cudaFree(b->p);
+  if (b->inf_mask) cudaFree(b->inf_mask);
   delete b;
 }
 
@@ -501,7 +513,7 @@ int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t o
   if (!bases || offset + n > bases->n || (!scalars_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
   if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
   ZKB_TRY(set_device(ctx));
-  cudaError_t e = msm_run<F>(ctx, bases->p, bases->n, bases->c, bases->nwin, offset, static_cast<const uint32_t*>(scalars_dev), n,
+  cudaError_t e = msm_run<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset, static_cast<const uint32_t*>(scalars_dev), n,
                              static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -522,7 +534,7 @@ int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t 
     // large: upload in slices on a second stream and accumulate each slice while the next one is in flight
     if (!bases || offset + n > bases->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
     if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
-    cudaError_t e = msm_run_host_sliced<F>(ctx, bases->p, bases->n, bases->c, bases->nwin, offset, scalars_host,
+    cudaError_t e = msm_run_host_sliced<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset, scalars_host,
                                            ctx->scal.as<uint32_t>(), n, ctx->msm_slices, nullptr, ctx->res.as<uint32_t>());
     if (e != cudaSuccess) {
       cudaGetLastError();

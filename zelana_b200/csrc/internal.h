@@ -102,17 +102,21 @@ struct zkb_ctx {
 };
 
 // Device-resident bases with their window tables: p[j * n + i] = 2^(c j) * base_i, j < nwin (msm.cuh).
+// inf_mask[i] != 0: base i is the point at infinity (a variable absent from that query's matrix: half of b_query in
+// practice) -- the MSM drops its entries before the sort instead of carrying them as idle lanes through the accumulation.
 struct zkb_g1_bases {
   int device;
   zkb::Affine<zkb::Fq>* p;
   size_t n;
   int c, nwin;
+  uint8_t* inf_mask;
 };
 struct zkb_g2_bases {
   int device;
   zkb::Affine<zkb::Fq2>* p;
   size_t n;
   int c, nwin;
+  uint8_t* inf_mask;
 };
 
 namespace zkb {

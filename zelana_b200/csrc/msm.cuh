@@ -125,10 +125,24 @@ __global__ void __launch_bounds__(128) window_tables_kernel(Affine<F>* table, si
 // ------------------------------------------------------------------------------------------- 1. digits
 // scalars: n x 32 bytes canonical little-endian (NOT Montgomery): what msm_bigint receives.
 // entry (w, i): keys[w * n + i] = |digit| - 1 (sentinel for 0), vals[w * n + i] = (w * table_n + first + i) | neg << 31
+template <class F>
+__global__ void inf_mask_kernel(const Affine<F>* __restrict__ bases, size_t n, uint8_t* __restrict__ mask) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) mask[i] = load_affine(bases + i).is_inf() ? 1 : 0;
+}
+
 static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t sentinel,
-                                         size_t table_n, size_t first, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                         size_t table_n, size_t first, const uint8_t* __restrict__ inf_mask,
+                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (inf_mask && inf_mask[first + i]) {  // s * infinity = infinity: no entries
+    for (int w = 0; w < nwin; w++) {
+      keys[size_t(w) * n + i] = sentinel;
+      vals[size_t(w) * n + i] = 0;
+    }
+    return;
+  }
   const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * 8);
   uint4 lo = sp[0], hi = sp[1];
   uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
@@ -506,8 +520,8 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
 // Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE), accumulated into the
 // (shared) bucket array; `first_slice` clears it.
 template <class F>
-cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affine<F>* table, size_t table_n, size_t first,
-                                 const uint32_t* scalars, size_t n, bool first_slice) {
+cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask,
+                                 size_t first, const uint32_t* scalars, size_t n, bool first_slice) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
@@ -522,7 +536,7 @@ cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affi
   const size_t nthreads = (total + L.chunk - 1) / L.chunk;
   {
     ProfScope ps(ctx, PH0 + 0);
-    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, L.c, L.nwin, L.sentinel, table_n, first, k0, v0);
+    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, L.c, L.nwin, L.sentinel, table_n, first, inf_mask, k0, v0);
     ctx->launches++;
   }
   {
@@ -583,7 +597,7 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
 // table: device, Montgomery affine, nwin x table_n (window-major).  The MSM covers bases [first, first + n).
 // scalars: device, canonical LE.  out_xyzz / out_affine: device (either may be null).
 template <class F>
-cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
+cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask, int c, int nwin, size_t first,
                     const uint32_t* scalars, size_t n, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
   cudaStream_t st = ctx->stream;
   if (n == 0) {
@@ -596,7 +610,7 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
   MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1, st);
   cudaError_t e = ctx->msm_ws.reserve(L.bytes);
   if (e != cudaSuccess) return e;
-  e = msm_accumulate_slice<F>(ctx, L, table, table_n, first, scalars, n, true);
+  e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first, scalars, n, true);
   if (e != cudaSuccess) return e;
   return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
 }
@@ -604,7 +618,7 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c,
 // Host-scalar MSM pipelined against the PCIe copy: the scalars go up in `nslices` slices on a second stream; slice k is
 // decomposed, sorted and accumulated (on top of the buckets the earlier slices left) while slice k+1 is still in flight.
 template <class F>
-cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, int c, int nwin, size_t first,
+cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask, int c, int nwin, size_t first,
                                 const uint8_t* scalars_host, uint32_t* scalars_dev, size_t n, int nslices,
                                 XYZZ<F>* out_xyzz, uint32_t* out_affine) {
   if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
@@ -652,7 +666,7 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
     size_t lo = bound[k], cnt = bound[k + 1] - bound[k];
     cudaStreamWaitEvent(ctx->stream, ctx->copy_done[k], 0);
     if (!cnt) continue;
-    e = msm_accumulate_slice<F>(ctx, L, table, table_n, first + lo, scalars_dev + lo * 8, cnt, used == 0);
+    e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first + lo, scalars_dev + lo * 8, cnt, used == 0);
     if (e != cudaSuccess) return e;
     used++;
   }
