@@ -11,15 +11,18 @@
 //     and ALL windows share one set of 2^(c-1) buckets: no per-window bucket reduction, no Horner doublings,
 //     and c can grow to 22 (12 windows instead of 16) because the 2^21 buckets are reduced once, not 16 times.
 //   * one (key, value) entry per (point, window): key = |digit| - 1, value = table index | sign << 31;
-//     zero digits get the sentinel key and sort last.
-// Pipeline (all on one stream, no host synchronisation):
+//     zero digits -- and every digit of a base that is the point at infinity (half of a real b_query) -- get the
+//     sentinel key, sort last and never reach the accumulation.
+// Pipeline (all on one stream, no host synchronisation; a host-scalar MSM uploads in slices that run it per slice):
 //   1. msm_digits_kernel        canonical scalars -> signed c-bit digits -> entries.
 //   2. cub::DeviceRadixSort     entries by bucket.  Library sort, HBM-bound.
 //   3. msm_accumulate_kernel    the hot loop.  The sorted entry list is cut into equal chunks, one per thread, so
 //                               load balance does not depend on the scalar distribution.  A thread sums the runs
 //                               in its chunk with XYZZ mixed additions (8M+2S) on gathered 64-byte affine points;
-//                               a run that starts inside the chunk is stored to its bucket, the run that was
-//                               already open at the chunk start goes to a per-thread "head" slot.
+//                               a run that starts inside the chunk continues from the bucket's current content and is
+//                               stored back (so upload slices accumulate on top of each other), the run that was
+//                               already open at the chunk start goes to a per-thread "head" slot.  ncu: the fmaheavy
+//                               pipe (IMAD.WIDE.U32.X) is 90 % busy.
 //   4. msm_heads_warp_kernel    heads are again a sorted list: one lane per head, warp-segmented scan (5 shuffle
 //                               steps), 32x shorter per level (a bucket holding millions of entries -- scalars 0/1 of
 //                               real witnesses -- is folded in log_32 steps).
