@@ -210,6 +210,68 @@ int zkb_prove_partial(zkb_ctx* ctx, const zkb_pk* pk_shard, const zkb_r1cs* m, c
 int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int world, const uint8_t r[32], const uint8_t s[32],
                       uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
 
+/* ---- the L2 batch circuit on the host: prover/src/l2_circuit.rs (8f.3) ----------------------
+ * What `Groth16Prover::prove` (core/src/sequencer/settlement/prover.rs:350-425) does around the arkworks call, natively:
+ * build `L2BlockCircuit`, synthesise its constraints (l2_circuit.rs:179-505 over ark-r1cs-std / ark-crypto-primitives 0.5.0
+ * gadgets), seed StdRng with the batch id, draw (r, s), prove on the GPU, format the 256-byte Solana proof.
+ * Host-only functions (no zkb_ctx) report through zkb_l2_last_error() (thread-local). */
+typedef struct {              /* = BatchPublicInputs, prover.rs:48-63; roots are `Fr::from_le_bytes_mod_order` inputs */
+  uint8_t pre_state_root[32];
+  uint8_t post_state_root[32];
+  uint8_t pre_shielded_root[32];
+  uint8_t post_shielded_root[32];
+  uint8_t withdrawal_root[32];
+  uint8_t batch_hash[32];
+  uint64_t batch_id;
+} zkb_l2_public_inputs;
+
+typedef struct {              /* L2BlockCircuit's private witness, l2_circuit.rs:110-119 (prover.rs:357-404 fills it) */
+  const uint8_t* account_pks;       /* n_accounts x 32: initial_accounts keys (any order; folded in BTreeMap order) */
+  const uint64_t* account_balances; /* n_accounts */
+  size_t n_accounts;
+  const uint8_t* tx_senders;        /* n_txs x 32 */
+  const uint8_t* tx_recipients;     /* n_txs x 32 */
+  const uint64_t* tx_amounts;       /* n_txs */
+  size_t n_txs;
+  const uint8_t* commitments;       /* n_commitments x 32 (shielded_commitments) */
+  size_t n_commitments;
+  const uint8_t* wd_recipients;     /* n_withdrawals x 32 */
+  const uint64_t* wd_amounts;       /* n_withdrawals */
+  size_t n_withdrawals;
+} zkb_l2_witness;
+
+typedef struct zkb_l2_circuit zkb_l2_circuit; /* host: constraint matrices of ONE circuit shape (what a key is made for) */
+
+const char* zkb_l2_last_error(void);
+/* Structure pass = `generate_constraints` under SynthesisMode::Setup + `cs.finalize(); cs.to_matrices()`
+ * (OptimizationGoal::Constraints, as ark-groth16 sets).  Only the SHAPE of `shape` matters: the counts and which account
+ * each transfer debits / credits (keygen uses L2BlockCircuit::dummy(), l2_circuit.rs:147-170).
+ * ZKB_ERR_SHAPE: a transfer's sender is not an initial account (SynthesisError::AssignmentMissing, l2_circuit.rs:266). */
+int zkb_l2_circuit_create(const zkb_l2_witness* shape, zkb_l2_circuit** out);
+void zkb_l2_circuit_free(zkb_l2_circuit* c);
+/* Host CSR views (valid until zkb_l2_circuit_free) for zkb_r1cs_load / zkb_setup. */
+int zkb_l2_circuit_desc(const zkb_l2_circuit* c, zkb_r1cs_desc* out);
+/* Assignment pass = `generate_constraints` in prove mode: z_out = [1, 7 public inputs, witness..] as
+ * (num_instance + num_witness) x 32 B canonical.  Values only, no matrices.  ZKB_ERR_SHAPE if the witness does not have
+ * the circuit's shape.  Like the reference (release build: `debug_assert!(cs.is_satisfied())`), an unsatisfying witness is
+ * NOT an error here; use zkb_l2_circuit_is_satisfied. */
+int zkb_l2_circuit_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witness,
+                          uint8_t* z_out);
+/* `cs.is_satisfied()`: *satisfied = 1 iff (A z) o (B z) = C z; first_bad_row (may be NULL) = `cs.which_is_unsatisfied()`. */
+int zkb_l2_circuit_is_satisfied(const zkb_l2_circuit* c, const uint8_t* z, int* satisfied, uint64_t* first_bad_row);
+/* The six roots a satisfying batch carries, computed off-circuit with the native Poseidon sponge
+ * (prover/src/main.rs.bak:93-154 `calculate_new_root_offchain`, same folds for withdrawals / batch hash / commitments). */
+int zkb_l2_roots(const zkb_l2_witness* witness, uint64_t batch_id, const uint8_t pre_shielded_root[32],
+                 zkb_l2_public_inputs* out);
+/* Poseidon(get_poseidon_config()) of n <= 3 field elements (32 B LE, reduced mod r): fresh sponge, absorb, squeeze one. */
+int zkb_l2_poseidon_hash(const uint8_t* elems, size_t n, uint8_t out[32]);
+/* `StdRng::seed_from_u64(batch_id)` then `Fr::rand` twice (prover.rs:354 + ark-groth16 prove): canonical r, s. */
+int zkb_l2_prover_randomness(uint64_t batch_id, uint8_t r[32], uint8_t s[32]);
+/* `impl BatchProver for Groth16Prover { fn prove }` (prover.rs:350-425): proof_out = -A || B || C, 256 B
+ * (proof_to_solana_bytes, prover.rs:304-334).  m = zkb_r1cs_load(zkb_l2_circuit_desc(c)); pk = the key made for c. */
+int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c,
+                 const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witness, uint8_t proof_out[256]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,213 @@
+"""L2BlockCircuit (prover/src/l2_circuit.rs): the oracle restatement's own invariants, and the native synthesiser in
+libzkb200.so against it, bit for bit.  Host logic only -- no GPU needed.  (GPU: tests/test_gpu_parity.py::test_l2_*.)
+
+The reference pins nothing for this circuit except the instance count (l2_circuit.rs:512-541); the oracle is therefore
+"parity unpinned" against arkworks and these tests pin (a) its internal consistency and (b) product == oracle."""
+import ctypes as C
+import random
+
+import pytest
+
+from oracle import l2_circuit as O
+from oracle import rng as orng
+from oracle.bn254 import R
+
+from helpers import unpack32
+
+
+def _k(i):
+    return bytes([i]) * 32
+
+
+def _shapes():
+    """name -> (transactions, initial_accounts, commitments, withdrawals, batch_id)"""
+    rnd = random.Random(5)
+    rk = lambda: bytes(rnd.randrange(256) for _ in range(32))
+    a, b, c, d = rk(), rk(), rk(), rk()
+    return {
+        "dummy": ([(_k(1), _k(2), 100)], {_k(1): 1000, _k(2): 0}, [], [], 0),
+        "no_transfers": ([], {_k(9): 5}, [], [], 3),
+        "creates_recipient_and_spends_from_it": ([(a, b, 7), (b, c, 7), (a, a, 1)], {a: 50, d: 2 ** 63}, [], [], 11),
+        "commitments_and_withdrawals": ([(_k(1), _k(2), 1000)], {_k(2): 0, _k(1): 1000}, [rk(), bytes([255]) * 32],
+                                        [(rk(), 12345), (rk(), 0)], 2 ** 64 - 1),
+    }
+
+
+def _oracle_circuit(shape, satisfy=True):
+    txs, acc, com, wd, bid = shape
+    c = O.L2BlockCircuit(transactions=txs, initial_accounts=acc, shielded_commitments=com, withdrawals=wd, batch_id=bid,
+                         pre_shielded_root=bytes(range(32)))
+    return O.with_satisfying_roots(c) if satisfy else c
+
+
+def _product_circuit(shape, oc):
+    from zelana_b200 import l2_circuit as P
+    txs, acc, com, wd, bid = shape
+    return P.L2BlockCircuit(oc.pre_state_root, oc.post_state_root, oc.pre_shielded_root, oc.post_shielded_root,
+                            oc.withdrawal_root, oc.batch_hash, bid,
+                            [P.TransactionWitness(*t) for t in txs], dict(acc),
+                            [P.ShieldedCommitmentWitness(x) for x in com], [P.WithdrawalWitness(*x) for x in wd])
+
+
+def _rows(csr):
+    rp, col, co = csr
+    data = co.tobytes()
+    return [[(int.from_bytes(data[32 * k:32 * k + 32], "little"), int(col[k])) for k in range(int(rp[i]), int(rp[i + 1]))]
+            for i in range(len(rp) - 1)]
+
+
+# ----------------------------------------------------------------------------- oracle invariants
+def test_poseidon_parameters_have_the_generator_s_shape():
+    cfg = O.get_poseidon_config()
+    assert len(cfg.ark) == 64 and all(len(r) == 3 and all(0 <= x < R for x in r) for r in cfg.ark)
+    assert len({x for r in cfg.ark for x in r}) == 192
+    # Cauchy matrix 1 / (x_i + y_j): every 2x2 minor of the entrywise inverse has the rank-2 additive structure
+    inv = [[pow(v, -1, R) for v in row] for row in cfg.mds]
+    for i in range(2):
+        for j in range(2):
+            assert (inv[i][j] - inv[i + 1][j] - inv[i][j + 1] + inv[i + 1][j + 1]) % R == 0
+    # and it is invertible (MDS)
+    m = cfg.mds
+    det = (m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])
+           + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0])) % R
+    assert det != 0
+
+
+def test_grain_lfsr_is_the_80_bit_register_of_the_poseidon_paper():
+    g = O.GrainLFSR(False, 254, 3, 8, 56)
+    # after the 160 warm-up clocks the register must not be stuck and must follow its recurrence
+    before = list(g.state[g.head:] + g.state[:g.head])
+    nb = g.update()
+    assert nb == before[62] ^ before[51] ^ before[38] ^ before[23] ^ before[13] ^ before[0]
+    bits = g.get_bits(512)
+    assert 150 < sum(bits) < 362
+
+
+def test_dummy_circuit_counts_match_the_reference_s_own_test():
+    r1cs, z = O.synthesize(O.L2BlockCircuit.dummy())
+    assert r1cs.num_instance == 8                      # l2_circuit.rs:527-531, :540
+    assert len(z) == r1cs.num_instance + r1cs.num_witness
+    assert (r1cs.num_constraints, r1cs.num_witness) == (6415, 5958)
+    assert 4096 < r1cs.num_constraints + r1cs.num_instance <= 8192     # QAP domain 2^13
+    # "This will fail because the dummy values don't actually compute to valid roots" (l2_circuit.rs:518-519)
+    assert not r1cs.is_satisfied(z)
+
+
+@pytest.mark.parametrize("name", list(_shapes()))
+def test_oracle_is_satisfied_exactly_by_the_offchain_roots(name):
+    shape = _shapes()[name]
+    oc = _oracle_circuit(shape)
+    r1cs, z = O.synthesize(oc)
+    assert r1cs.is_satisfied(z)
+    assert z[1:8] == [O.fr_from_le_bytes_mod_order(b) for b in (oc.pre_state_root, oc.post_state_root, oc.pre_shielded_root,
+                                                                oc.post_shielded_root, oc.withdrawal_root, oc.batch_hash)] \
+        + [oc.batch_id % R]
+    for attr in ("pre_state_root", "post_state_root", "withdrawal_root", "batch_hash"):
+        bad = _oracle_circuit(shape)
+        setattr(bad, attr, bytes(31) + b"\x01")
+        r2, z2 = O.synthesize(bad)
+        assert (r2.a, r2.b, r2.c) == (r1cs.a, r1cs.b, r1cs.c)          # structure does not depend on values
+        assert not r2.is_satisfied(z2)
+
+
+def test_overspending_transfer_is_unsatisfiable():
+    c = O.L2BlockCircuit(transactions=[(_k(1), _k(2), 1001)], initial_accounts={_k(1): 1000, _k(2): 0})
+    # roots of the (wrapped-around) balances so that only the comparison can fail
+    final = {_k(1): (1000 - 1001) % R, _k(2): 1001}
+    c.pre_state_root = O.accounts_root(0, c.initial_accounts)
+    c.post_state_root = O.accounts_root(0, final)
+    c.withdrawal_root, c.batch_hash = O.withdrawal_root([]), O.batch_hash(0, c.transactions)
+    r1cs, z = O.synthesize(c)
+    bad = [i for i, (ra, rb, rc) in enumerate(zip(r1cs.a, r1cs.b, r1cs.c))
+           if sum(co * z[v] for co, v in ra) * sum(co * z[v] for co, v in rb) % R != sum(co * z[v] for co, v in rc) % R]
+    assert bad and max(bad) < 2000                     # inside enforce_cmp, before the first Poseidon fold
+    ok = O.L2BlockCircuit(transactions=[(_k(1), _k(2), 1000)], initial_accounts={_k(1): 1000, _k(2): 0})
+    r1cs, z = O.synthesize(O.with_satisfying_roots(ok))
+    assert r1cs.is_satisfied(z)                        # equality allowed (enforce_cmp(.., Greater, true))
+
+
+def test_gadget_sponge_equals_native_sponge():
+    cs = O.ConstraintSystem()
+    xs = [O.Fp.new_witness(cs, v) for v in (5, R - 1, 12345678901234567890)]
+    for n in (1, 2, 3):
+        s = O.PoseidonSpongeVar(cs, O.get_poseidon_config())
+        s.absorb(xs[:n])
+        assert s.squeeze_field_elements(1)[0].value == O.poseidon_hash([x.value for x in xs[:n]])
+    r1cs = cs.to_r1cs()
+    assert r1cs.is_satisfied(cs.assignment())
+    # 240 constraints per permutation once every state element is a variable; the first round's constant lanes are free
+    assert r1cs.num_constraints == 4 * 240 - 3 * (2 + 1 + 1)
+
+
+# ----------------------------------------------------------------------------- native synthesiser == oracle
+@pytest.mark.parametrize("name", list(_shapes()))
+def test_native_matrices_and_assignment_equal_the_oracle(name):
+    from zelana_b200 import l2_circuit as P
+    shape = _shapes()[name]
+    oc = _oracle_circuit(shape)
+    r1cs, z = O.synthesize(oc)
+    pc = _product_circuit(shape, oc)
+    circ = P.L2Circuit(pc)
+    assert (circ.num_constraints, circ.num_instance, circ.num_witness) == (r1cs.num_constraints, 8, r1cs.num_witness)
+    a, b, c = circ.matrices()
+    assert _rows(a) == r1cs.a and _rows(b) == r1cs.b and _rows(c) == r1cs.c
+    zb = circ.assign(pc)
+    assert unpack32(zb) == z
+    assert circ.is_satisfied(zb) == (True, None)
+    # the off-circuit roots (main.rs.bak:114-154) from the library equal the oracle's
+    got = P.satisfying_inputs(pc)
+    assert (got.pre_state_root, got.post_state_root, got.post_shielded_root, got.withdrawal_root, got.batch_hash) == \
+        (oc.pre_state_root, oc.post_state_root, oc.post_shielded_root, oc.withdrawal_root, oc.batch_hash)
+    # unsatisfying inputs are assigned all the same (release-mode arkworks does not check) and reported by is_satisfied
+    bad = pc.with_inputs(P.BatchPublicInputs(batch_id=pc.batch_id))
+    zbad = circ.assign(bad)
+    r0, z0 = O.synthesize(O.L2BlockCircuit(transactions=shape[0], initial_accounts=shape[1], shielded_commitments=shape[2],
+                                           withdrawals=shape[3], batch_id=shape[4]))
+    assert unpack32(zbad) == z0
+    ok, row = circ.is_satisfied(zbad)
+    assert not ok and row == next(i for i in range(r0.num_constraints) if not O.R1CS(
+        r0.num_instance, r0.num_witness, [r0.a[i]], [r0.b[i]], [r0.c[i]]).is_satisfied(z0))
+
+
+def test_account_order_does_not_matter_but_shape_does():
+    from zelana_b200 import ZkbError, l2_circuit as P
+    d = P.L2BlockCircuit.dummy()
+    circ = P.L2Circuit(d)
+    rev = P.L2BlockCircuit(transactions=d.transactions, initial_accounts=dict(reversed(list(d.initial_accounts.items()))))
+    assert circ.assign(rev) == circ.assign(d)          # BTreeMap order, whatever the insertion order
+    other_amounts = P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(1), _k(2), 5)], initial_accounts={_k(1): 9, _k(2): 1})
+    assert len(circ.assign(other_amounts)) == len(circ.assign(d))
+    # different keys with the same debit/credit pattern are the same circuit
+    renamed = P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(7), _k(8), 5)], initial_accounts={_k(7): 9, _k(8): 1})
+    circ.assign(renamed)
+    for bad in (P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(2), _k(1), 0)], initial_accounts=d.initial_accounts),
+                P.L2BlockCircuit(transactions=d.transactions, initial_accounts={_k(1): 1000}),
+                P.L2BlockCircuit(transactions=d.transactions, initial_accounts=d.initial_accounts,
+                                 withdrawals=[P.WithdrawalWitness(_k(3), 1)])):
+        with pytest.raises(ZkbError) as e:
+            circ.assign(bad)
+        assert e.value.code == -6                      # ZKB_ERR_SHAPE
+    with pytest.raises(ZkbError) as e:                 # SynthesisError::AssignmentMissing (l2_circuit.rs:263-266)
+        P.L2Circuit(P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(5), _k(1), 1)], initial_accounts={_k(1): 1}))
+    assert e.value.code == -6
+    with pytest.raises(ValueError):
+        P.L2Circuit(P.L2BlockCircuit(initial_accounts={b"short": 1}))
+
+
+def test_prover_randomness_is_stdrng_seeded_with_the_batch_id():
+    from zelana_b200 import l2_circuit as P
+    for batch_id in (0, 1, 42, 2 ** 64 - 1):
+        rng = orng.StdRng.seed_from_u64(batch_id)
+        r, s = orng.rand_fr(rng), orng.rand_fr(rng)
+        pr, ps = P.prover_randomness(batch_id)
+        assert (int.from_bytes(pr, "little"), int.from_bytes(ps, "little")) == (r, s)
+
+
+def test_native_poseidon_hash_equals_oracle():
+    from zelana_b200 import l2_circuit as P
+    rnd = random.Random(8)
+    for n in (0, 1, 2, 3):
+        for _ in range(4):
+            vals = [rnd.randrange(2 ** 256) for _ in range(n)]
+            got = P.poseidon_hash([v.to_bytes(32, "little") for v in vals])
+            assert int.from_bytes(got, "little") == O.poseidon_hash([v % R for v in vals])

@@ -44,6 +44,20 @@ class SetupOut(C.Structure):
                                           "a_query", "b_g1_query", "b_g2_query", "h_query", "l_query")]
 
 
+class L2PublicInputs(C.Structure):
+    """zkb_l2_public_inputs = BatchPublicInputs (prover.rs:48-63)"""
+    _fields_ = [(n, C.c_uint8 * 32) for n in ("pre_state_root", "post_state_root", "pre_shielded_root", "post_shielded_root",
+                                              "withdrawal_root", "batch_hash")] + [("batch_id", C.c_uint64)]
+
+
+class L2Witness(C.Structure):
+    _fields_ = [("account_pks", C.c_char_p), ("account_balances", C.POINTER(C.c_uint64)), ("n_accounts", C.c_size_t),
+                ("tx_senders", C.c_char_p), ("tx_recipients", C.c_char_p), ("tx_amounts", C.POINTER(C.c_uint64)),
+                ("n_txs", C.c_size_t),
+                ("commitments", C.c_char_p), ("n_commitments", C.c_size_t),
+                ("wd_recipients", C.c_char_p), ("wd_amounts", C.POINTER(C.c_uint64)), ("n_withdrawals", C.c_size_t)]
+
+
 _P = C.c_void_p
 _SZ = C.c_size_t
 _I = C.c_int
@@ -100,6 +114,16 @@ SIGNATURES = {
     "zkb_pk_synthetic_shard": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, _I, _I, C.POINTER(_P)]),
     "zkb_prove_partial": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "zkb_prove_combine": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "zkb_l2_last_error": (C.c_char_p, []),
+    "zkb_l2_circuit_create": (_I, [C.POINTER(L2Witness), C.POINTER(_P)]),
+    "zkb_l2_circuit_free": (None, [_P]),
+    "zkb_l2_circuit_desc": (_I, [_P, C.POINTER(R1csDesc)]),
+    "zkb_l2_circuit_assign": (_I, [_P, C.POINTER(L2PublicInputs), C.POINTER(L2Witness), _P]),
+    "zkb_l2_circuit_is_satisfied": (_I, [_P, _P, C.POINTER(_I), C.POINTER(C.c_uint64)]),
+    "zkb_l2_roots": (_I, [C.POINTER(L2Witness), C.c_uint64, _P, C.POINTER(L2PublicInputs)]),
+    "zkb_l2_poseidon_hash": (_I, [_P, _SZ, _P]),
+    "zkb_l2_prover_randomness": (_I, [C.c_uint64, _P, _P]),
+    "zkb_l2_prove": (_I, [_P, _P, _P, _P, C.POINTER(L2PublicInputs), C.POINTER(L2Witness), _P]),
 }
 
 _lib = None
