@@ -79,32 +79,30 @@ static inline Fr sub(const Fr& a, const Fr& b) {
   return r;
 }
 static inline Fr neg(const Fr& a) { return a.is_zero() ? a : raw_sub(MOD, a); }
-static inline Fr mont_mul(const Fr& a, const Fr& b) {  // CIOS
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+static inline Fr mont_mul(const Fr& a, const Fr& b) {
+  // CIOS without the extra carry word: valid because the modulus leaves its top two bits clear (r < 2^254), and for any
+  // a < 2^256, b < r the result stays below 2 r before the final subtraction.
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#pragma GCC unroll 4
   for (int i = 0; i < 4; ++i) {
-    u128 c = 0;
-    for (int j = 0; j < 4; ++j) {
-      c += (u128)a.l[j] * b.l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[4] = (uint64_t)c;
-    t[5] = (uint64_t)(c >> 64);
-    uint64_t m = t[0] * NINV;
-    c = (u128)m * MOD.l[0] + t[0];
-    c >>= 64;
-    for (int j = 1; j < 4; ++j) {
-      c += (u128)m * MOD.l[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[3] = (uint64_t)c;
-    t[4] = t[5] + (uint64_t)(c >> 64);
+    const uint64_t bi = b.l[i];
+    u128 c = (u128)a.l[0] * bi + t0;
+    const uint64_t lo = (uint64_t)c;
+    const uint64_t m = lo * NINV;
+    u128 d = (u128)m * MOD.l[0] + lo;
+    c = (u128)a.l[1] * bi + t1 + (uint64_t)(c >> 64);
+    d = (u128)m * MOD.l[1] + (uint64_t)c + (uint64_t)(d >> 64);
+    t0 = (uint64_t)d;
+    c = (u128)a.l[2] * bi + t2 + (uint64_t)(c >> 64);
+    d = (u128)m * MOD.l[2] + (uint64_t)c + (uint64_t)(d >> 64);
+    t1 = (uint64_t)d;
+    c = (u128)a.l[3] * bi + t3 + (uint64_t)(c >> 64);
+    d = (u128)m * MOD.l[3] + (uint64_t)c + (uint64_t)(d >> 64);
+    t2 = (uint64_t)d;
+    t3 = (uint64_t)(c >> 64) + (uint64_t)(d >> 64);
   }
-  Fr r = {{t[0], t[1], t[2], t[3]}};
-  return (t[4] || geq(r, MOD)) ? raw_sub(r, MOD) : r;
+  Fr r = {{t0, t1, t2, t3}};
+  return geq(r, MOD) ? raw_sub(r, MOD) : r;
 }
 
 struct Consts {
@@ -134,13 +132,47 @@ static Fr inverse(const Fr& a) {  // Fermat; a != 0
   Fr e = raw_sub(MOD, Fr{{2, 0, 0, 0}});
   return pow_limbs(a, e);
 }
+// Inverses of 1..SMALL_INV (Montgomery), by one Fermat inversion and Montgomery's trick.  The is_eq inside Boolean::kary_and
+// inverts (count - sum of bits), always a small integer; a Fermat inversion each time was a third of an assignment pass.
+constexpr uint64_t SMALL_INV = 512;
+struct SmallInverses {
+  Fr inv[SMALL_INV + 1];
+  SmallInverses() {
+    Fr prefix[SMALL_INV + 1];
+    Fr k = K.one, acc = K.one;
+    for (uint64_t i = 1; i <= SMALL_INV; ++i) {
+      prefix[i] = acc;  // (i - 1)!
+      acc = mont_mul(acc, k);
+      k = add(k, K.one);
+    }
+    Fr inv_acc = inverse(acc);  // 1 / SMALL_INV!
+    for (uint64_t i = SMALL_INV; i >= 1; --i) {
+      inv[i] = mont_mul(inv_acc, prefix[i]);
+      inv_acc = mont_mul(inv_acc, from_u64(i));
+    }
+    inv[0] = K.zero;
+  }
+};
+static Fr inverse_fast(const Fr& a) {  // a != 0
+  static const SmallInverses table;
+  Fr c = from_mont(a);
+  if ((c.l[1] | c.l[2] | c.l[3]) == 0 && c.l[0] <= SMALL_INV) return table.inv[c.l[0]];
+  Fr n = from_mont(neg(a));
+  if ((n.l[1] | n.l[2] | n.l[3]) == 0 && n.l[0] <= SMALL_INV) return neg(table.inv[n.l[0]]);
+  return inverse(a);
+}
 // Fr::from_le_bytes_mod_order for up to 32 bytes (every use in the circuit): value < 2^256 = reduce by Montgomery product
 static Fr from_le_bytes_mod_order(const uint8_t* b, size_t n) {
   Fr x = {{0, 0, 0, 0}};
   for (size_t i = 0; i < n && i < 32; ++i) x.l[i >> 3] |= (uint64_t)b[i] << (8 * (i & 7));
-  return mont_mul(x, K.r2);  // (x * R^2) / R = x R mod r, valid for any x < 2^256
+  return mont_mul(K.r2, x);  // (R^2 * x) / R = x R mod r; the multiplier operand may be any x < 2^256
 }
 static void to_le_bytes(const Fr& mont, uint8_t out[32]) {
+  if (mont.is_zero() || mont == K.one) {  // most of an assignment is bits
+    memset(out, 0, 32);
+    out[0] = mont.is_zero() ? 0 : 1;
+    return;
+  }
   Fr c = from_mont(mont);
   for (int i = 0; i < 32; ++i) out[i] = (uint8_t)(c.l[i >> 3] >> (8 * (i & 7)));
 }
@@ -444,7 +476,7 @@ struct Gadgets {
   BoolVar is_neq(const Fr& sv, const LC& slc, const Fr& ov, const LC& olc) {
     bool ne = sv != ov;
     BoolVar r = bwitness_unchecked(ne);
-    uint32_t mcol = b.new_witness(ne ? inverse(sub(sv, ov)) : K.one);
+    uint32_t mcol = b.new_witness(ne ? inverse_fast(sub(sv, ov)) : K.one);
     if (S()) {
       LC diff = lc_axpy(slc, olc, MINUS_ONE);
       b.enforce(diff, lc_var(mcol), r.lc);
@@ -562,7 +594,47 @@ struct Gadgets {
   }
 
   // ---- PoseidonSpongeVar: absorb `n` elements into a fresh sponge, squeeze one (every use in the circuit)
+  // ASSIGN mode: the same permutation on bare values.  Allocation order is what the generic path produces: per S-box on a
+  // variable lane the witnesses x^2, x^4, x^5 (pow_by_constant(5) = square, square, multiply) and three constraints; a
+  // lane that is still a constant (only possible in the first round) allocates nothing.
+  void permute_assign(FpVar st[T]) {
+    const PoseidonConfig& cfg = config();
+    Fr v[T];
+    bool c[T];
+    for (int i = 0; i < T; ++i) {
+      v[i] = st[i].v;
+      c[i] = st[i].c;
+    }
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int lanes = (r < FULL / 2 || r >= FULL / 2 + PARTIAL) ? T : 1;
+      for (int i = 0; i < T; ++i) v[i] = add(v[i], cfg.ark[r][i]);
+      for (int i = 0; i < lanes; ++i) {
+        Fr x2 = mont_mul(v[i], v[i]);
+        Fr x4 = mont_mul(x2, x2);
+        Fr x5 = mont_mul(x4, v[i]);
+        if (!c[i]) {
+          b.z.push_back(x2);
+          b.z.push_back(x4);
+          b.z.push_back(x5);
+          b.n_constraints += 3;
+        }
+        v[i] = x5;
+      }
+      Fr nw[T];
+      for (int i = 0; i < T; ++i) {
+        nw[i] = add(add(mont_mul(v[0], cfg.mds[i][0]), mont_mul(v[1], cfg.mds[i][1])), mont_mul(v[2], cfg.mds[i][2]));
+      }
+      bool any_var = !(c[0] && c[1] && c[2]);  // the MDS layer mixes every lane into every lane (no zero entries)
+      for (int i = 0; i < T; ++i) {
+        v[i] = nw[i];
+        c[i] = !any_var;
+      }
+    }
+    for (int i = 0; i < T; ++i) st[i] = FpVar{c[i], v[i], LC()};
+  }
   void permute(FpVar st[T]) {
+    static_assert(ALPHA == 5, "permute_assign hard-codes x^5");
+    if (!S()) return permute_assign(st);
     const PoseidonConfig& cfg = config();
     for (int r = 0; r < ROUNDS; ++r) {
       for (int i = 0; i < T; ++i) st[i] = add_const(st[i], cfg.ark[r][i]);
