@@ -579,3 +579,92 @@ def test_l2_sized_keygen_prove_verify_end_to_end(ctx):
         cpk = orc.ProvingKey(**{k: raw[k] for k in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query",
                                                     "b_g1_query", "b_g2_query", "h_query", "l_query")})
         assert orc.prove(cpk, orc.R1cs(ni, nw, csr=(A, B, Cm)), zb, fr_bytes([r]), fr_bytes([s])) == (a, b, c)
+
+
+# ----------------------------------------------------------------------------- the L2 batch circuit itself (rows a1, a2; 8f.3)
+def _solana_to_proof(proof_bytes):
+    """Inverse of proof_to_solana_bytes (prover.rs:304-334): -A || B || C  ->  oracle Proof with A un-negated."""
+    a = bn.g1_from_raw(proof_bytes[:64])
+    return g16.Proof(bn.G1.neg(a), bn.g2_from_raw(proof_bytes[64:192]), bn.g1_from_raw(proof_bytes[192:]))
+
+
+@pytest.fixture(scope="module")
+def l2_setup(ctx):
+    """keygen.rs:81-131 on the GPU: dummy circuit, StdRng::seed_from_u64(0)."""
+    from zelana_b200 import l2_circuit as P2
+    circ, pk_bytes, vk_bytes, raw = P2.keygen(ctx)
+    return circ, pk_bytes, vk_bytes, raw
+
+
+def test_l2_circuit_keygen_prove_verify(ctx, l2_setup):
+    """`Groth16Prover::from_bytes` + `BatchProver::prove` for the reference's own L2BlockCircuit, end to end through the C ABI
+    (zkb_l2_prove): the proof verifies by pairing under the key's VK with the seven public inputs, and equals -- byte for
+    byte -- the proof the C++ restatement of arkworks makes from the ORACLE's matrices, assignment and (r, s)."""
+    from oracle import cpu as orc
+    from oracle import l2_circuit as O
+    from oracle.rng import rand_fr
+    from zelana_b200 import l2_circuit as P2
+    circ, pk_bytes, vk_bytes, raw = l2_setup
+    vk = g16.VerifyingKey.deserialize_compressed(vk_bytes)
+    assert len(vk.gamma_abc_g1) == 8
+    dpk = ctx.proving_key_compressed(pk_bytes)
+    prover = P2.L2Prover(ctx, circ, dpk, vk_bytes)
+    cpk = orc.ProvingKey(**{k: raw[k] for k in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query",
+                                                "b_g1_query", "b_g2_query", "h_query", "l_query")})
+    for batch_id, amount in ((0, 100), (7, 1000), (2 ** 64 - 1, 0)):
+        oc = O.with_satisfying_roots(O.L2BlockCircuit(
+            transactions=[(bytes([1] * 32), bytes([2] * 32), amount)],
+            initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): 0}, batch_id=batch_id))
+        r1cs, z = O.synthesize(oc)
+        pc = P2.L2BlockCircuit(transactions=[P2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), amount)],
+                               initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): 0}, batch_id=batch_id)
+        inputs = P2.satisfying_inputs(pc)
+        assert inputs.post_state_root == oc.post_state_root
+        proof = prover.prove(inputs, pc)
+        assert prover.verify(proof) and len(proof.proof_bytes) == 256
+        assert g16.verify(vk, z[1:8], _solana_to_proof(proof.proof_bytes))
+        assert not g16.verify(vk, z[1:7] + [(z[7] + 1) % R], _solana_to_proof(proof.proof_bytes))
+        rng = StdRng.seed_from_u64(batch_id)
+        r, s = rand_fr(rng), rand_fr(rng)
+        a, b, c = orc.prove(cpk, orc.R1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c), fr_bytes(z),
+                            fr_bytes([r]), fr_bytes([s]))
+        from zelana_b200 import proof_to_solana_bytes
+        assert proof.proof_bytes == proof_to_solana_bytes(a, b, c)
+    # a batch whose roots are wrong still "proves" (release-mode arkworks only debug_asserts satisfaction) -- and is rejected
+    bad = prover.prove(P2.BatchPublicInputs(batch_id=1), P2.L2BlockCircuit.dummy())
+    zbad = unpack32(circ.assign(P2.L2BlockCircuit.dummy().with_inputs(P2.BatchPublicInputs(batch_id=1))))
+    assert not g16.verify(vk, zbad[1:8], _solana_to_proof(bad.proof_bytes))
+    prover.m.free()
+    dpk.free()
+
+
+def test_l2_circuit_key_equals_oracle_setup_on_a_smaller_shape(ctx):
+    """keygen for the no-transfer shape (the smallest L2BlockCircuit): GPU setup from the native matrices == the oracle's
+    circuit_specific_setup from the oracle's matrices, same seed; VK bytes identical."""
+    from oracle import l2_circuit as O
+    from zelana_b200 import l2_circuit as P2
+    shape = P2.L2BlockCircuit(initial_accounts={bytes([9] * 32): 5})
+    circ, pk_bytes, vk_bytes, raw = P2.keygen(ctx, shape, seed=0)
+    r1cs, _ = O.synthesize(O.L2BlockCircuit(initial_accounts={bytes([9] * 32): 5}))
+    assert (circ.num_constraints, circ.num_witness) == (r1cs.num_constraints, r1cs.num_witness)
+    opk = g16.circuit_specific_setup(r1cs, StdRng.seed_from_u64(0))
+    assert vk_bytes == opk.vk.serialize_compressed()
+    assert raw["a_query"][:64 * 16] == g1_raw(opk.a_query[:16])
+    assert raw["l_query"][-64 * 8:] == g1_raw(opk.l_query[-8:])
+    assert raw["h_query"][:64 * 4] == g1_raw(opk.h_query[:4])
+    circ.free()
+
+
+def test_l2_prove_shape_error_is_an_error_not_a_crash(ctx, l2_setup):
+    from zelana_b200 import ZkbError
+    from zelana_b200 import l2_circuit as P2
+    circ, pk_bytes, vk_bytes, raw = l2_setup
+    dpk = ctx.proving_key_compressed(pk_bytes, validate=False)
+    prover = P2.L2Prover(ctx, circ, dpk, vk_bytes)
+    two = P2.L2BlockCircuit(transactions=[P2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), 1)] * 2,
+                            initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): 0})
+    with pytest.raises(ZkbError) as e:
+        prover.prove(P2.BatchPublicInputs(), two)
+    assert e.value.code == -6
+    prover.m.free()
+    dpk.free()

@@ -7,3 +7,5 @@ checked), but creating a Context without a CUDA device raises.
 from ._lib import LIB_PATH, ZkbError, load_library  # noqa: F401
 from .api import Context, G1Bases, G2Bases, R1csMatrices, ProvingKeyDev  # noqa: F401
 from .prover import Groth16Prover, BatchPublicInputs, BatchProof, StdRng, proof_to_solana_bytes  # noqa: F401
+from .l2_circuit import (L2BlockCircuit, L2Circuit, L2Prover, TransactionWitness, ShieldedCommitmentWitness,  # noqa: F401
+                         WithdrawalWitness)
