@@ -22,6 +22,8 @@ image) timed on the host cores for the same metric; rank 0 only.
 import argparse
 import json
 import os
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before torch initialises CUDA: see zelana_b200/__init__.py
 import sys
 import threading
 import time

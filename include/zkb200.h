@@ -54,6 +54,11 @@ void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(zkb_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
 unsigned long long zkb_launch_count(zkb_ctx* ctx);
+/* A prove's device part (~140 launches on five streams for the L2 circuit) is captured as a CUDA graph the second time a
+ * (key, matrices) pair is proved on a context and replayed afterwards with one launch; on by default, off while profiling
+ * (zkb_prof_enable).  zkb_launch_count keeps counting the kernels a replay stands for. */
+int zkb_ctx_set_graphs(zkb_ctx* ctx, int on);
+int zkb_graph_stats(zkb_ctx* ctx, unsigned long long* captures, unsigned long long* replays);
 /* force the MSM window width c in [2, 23] (0 = automatic) for bases loaded AFTER this call: the width is fixed when a
  * bases handle builds its window tables 2^(c j) P.  Benchmarking/tests only. */
 int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c);

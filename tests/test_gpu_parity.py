@@ -668,3 +668,57 @@ def test_l2_prove_shape_error_is_an_error_not_a_crash(ctx, l2_setup):
     assert e.value.code == -6
     prover.m.free()
     dpk.free()
+
+
+# ----------------------------------------------------------------------------- CUDA-graph replay of the prove
+def test_prove_graph_replay_is_bit_identical_and_survives_reallocation(mimc_setup):
+    """The device part of a prove is captured as a CUDA graph on the second call for a (key, matrices) pair and replayed
+    afterwards: every replay must give the bytes the direct launches give, also with two keys interleaved on one context,
+    and after buffers were reallocated (a bigger circuit proved in between) the stale graph must not be replayed."""
+    import zelana_b200
+    r1cs, z, pk = mimc_setup
+    sq, zsq = g16.square_circuit(7)
+    pk_sq = g16.circuit_specific_setup(sq, StdRng.seed_from_u64(42))
+    big, zbig = mimc7_chain(num_perm=6, seed=9, rounds=91)          # 2185 constraints -> domain 4096: grows every buffer
+    rnd = random.Random(77)
+    cases = []
+    for i in range(6):                                              # different witness-independent randomness each time
+        cases.append((rnd.randrange(R), rnd.randrange(R)))
+
+    def run(graphs):
+        c = zelana_b200.Context(0)
+        c.set_graphs(graphs)
+        m1 = c.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+        m2 = c.r1cs(sq.num_instance, sq.num_witness, sq.a, sq.b, sq.c)
+        k1, k2 = c.proving_key(**pk_parts(pk)), c.proving_key(**pk_parts(pk_sq))
+        out = []
+        for r, s in cases:
+            out.append(c.prove(k1, m1, fr_bytes(z), fr_bytes([r]), fr_bytes([s])))
+            out.append(c.prove(k2, m2, fr_bytes(zsq), fr_bytes([s]), fr_bytes([r])))
+        stats_before = c.graph_stats()
+        # a larger circuit reallocates the prove buffers: the cached graphs are stale from here on
+        m3 = c.r1cs(big.num_instance, big.num_witness, big.a, big.b, big.c)
+        nv, n = big.num_instance + big.num_witness, 4096
+        import torch
+        import numpy as np
+        k = torch.from_numpy(_rand_fr_np(n + 16, 5).view(np.int32)).cuda()
+        k3 = c.proving_key_synthetic(nv, big.num_witness, n - 1, k, n + 16)
+        out.append(c.prove(k3, m3, fr_bytes(zbig), fr_bytes([3]), fr_bytes([4])))
+        for r, s in cases[:4]:
+            out.append(c.prove(k1, m1, fr_bytes(z), fr_bytes([s]), fr_bytes([r])))
+        stats = c.graph_stats()
+        launches = c.launch_count()
+        for h in (m1, m2, m3, k1, k2, k3):
+            h.free()
+        c.close()
+        return out, stats_before, stats, launches
+
+    direct, _, s_off, launches_off = run(False)
+    graphed, s_mid, s_on, launches_on = run(True)
+    assert s_off == (0, 0)
+    assert graphed == direct
+    assert s_mid[0] == 2 and s_mid[1] == 2 * (len(cases) - 1)       # each key: 1 direct warm-up, then captured + replayed
+    assert s_on[0] == 3 and s_on[1] > s_mid[1]                      # recaptured once after the reallocation
+    assert launches_on == launches_off                              # a replay counts the kernels it stands for
+    ref = g16.prove_with_rs(pk, r1cs, z, cases[0][0], cases[0][1])
+    assert graphed[0] == (bn.g1_to_raw(ref.a), bn.g2_to_raw(ref.b), bn.g1_to_raw(ref.c))

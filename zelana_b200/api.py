@@ -58,6 +58,16 @@ class Context:
     def launch_count(self):
         return int(self.lib.zkb_launch_count(self.h))
 
+    def set_graphs(self, on=True):
+        """CUDA-graph replay of a prove's device part (default on)."""
+        self._check(self.lib.zkb_ctx_set_graphs(self.h, int(bool(on))))
+
+    def graph_stats(self):
+        """(captures, replays) of prove graphs on this context."""
+        cap, rep = C.c_ulonglong(0), C.c_ulonglong(0)
+        self._check(self.lib.zkb_graph_stats(self.h, C.byref(cap), C.byref(rep)))
+        return int(cap.value), int(rep.value)
+
     def set_msm_window(self, c):
         self._check(self.lib.zkb_ctx_set_msm_window(self.h, c))
 

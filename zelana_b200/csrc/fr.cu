@@ -112,6 +112,13 @@ __global__ void prove_tail_scalars_kernel(const Fr* r, const Fr* s, Fr* za_tail,
   zl_tail[0] = rs.neg();
 }
 
+// out[i] = k * in[i] mod r, canonical in and out: (in R) * k / R
+__global__ void fr_scale_kernel(const Fr* in, const Fr* k, Fr* out, size_t n) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  out[i] = in[i].to_mont() * (*k);
+}
+
 // ---- trusted setup (ark-groth16 generate_parameters_with_qap; prover/src/bin/keygen.rs:87-91) -----------------------------
 // consts (Montgomery): [0] tau, [1] alpha, [2] beta, [3] gamma^-1, [4] delta^-1, [5] zt = tau^n - 1, [6] zt / n, [7] zt / delta
 __global__ void setup_consts_kernel(const Fr* in /* canonical: tau, alpha, beta, gamma, delta */, int logn, Fr* c, int* bad) {
@@ -252,6 +259,7 @@ void launch_pass(const NttPassArgs& a, cudaStream_t st) {
 void fr_state_free(zkb_ctx* ctx) {
   if (!ctx->fr_state) return;
   FrState* S = static_cast<FrState*>(ctx->fr_state);
+  g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
   if (S->wr_fwd) cudaFree(S->wr_fwd);
   if (S->wr_inv) cudaFree(S->wr_inv);
   for (auto& kv : S->tables) cudaFree(kv.second.mem);
@@ -284,6 +292,14 @@ int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n) {
 
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail) {
   prove_tail_scalars_kernel<<<1, 32, 0, ctx->stream>>>(r, s, za_tail, zl_tail);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int fr_scale(zkb_ctx* ctx, const Fr* in, const Fr* k_dev, Fr* out, size_t n) {
+  if (!n) return ZKB_OK;
+  fr_scale_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(in, k_dev, out, n);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return ZKB_OK;

@@ -501,6 +501,7 @@ template <class F>
 void bases_free_impl(typename GroupOf<F>::Bases* b) {
   if (!b) return;
   cudaSetDevice(b->device);
+  g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);  // captured prove graphs hold these pointers
   if (b->p) cudaFree(b->p);
   if (b->inf_mask) cudaFree(b->inf_mask);
   delete b;

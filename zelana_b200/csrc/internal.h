@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -22,11 +23,16 @@ constexpr int ZKB_MAX_SLICES = 8;
 
 namespace zkb {
 
+// Bumped whenever device memory that a captured prove graph may have baked in is (re)allocated or freed: scratch buffers
+// growing, keys / matrices / tables released.  A cached graph is replayed only while the epoch it was captured at is current.
+inline std::atomic<unsigned long long> g_alloc_epoch{0};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -36,7 +42,10 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
+      cudaFree(p);
+    }
     p = nullptr;
     cap = 0;
   }
@@ -92,10 +101,25 @@ struct zkb_ctx {
     cudaStream_t stream = nullptr;
     zkb::DevBuf ws;
     cudaEvent_t done = nullptr;
-  } aux[4];
+  } aux[5];                                       // [4]: s*A as its own MSM for small circuits (prove_device_part)
   cudaEvent_t ev_inputs = nullptr;
   zkb::DevBuf scal, res, tmp0, tmp1, tmp2, flag;  // staging
-  zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzb, pzl, prs, ppts;  // prove scratch
+  zkb::DevBuf pz, pzm, pwa, pwb, pwc, ph, pza, pzb, pzl, prs, ppts, pzsa, pzrb;  // prove scratch
+  // The device part of a prove (everything between the upload of z, r, s and the download of A, B, C: ~140 launches on five
+  // streams) captured once per (key, matrices) as a CUDA graph and replayed with one cudaGraphLaunch.  Small proofs are
+  // launch-bound: several contexts proving side by side serialise on the driver's launch path, not on the SMs.
+  struct ProveGraph {
+    const void* pk;
+    const void* m;
+    bool partial;
+    unsigned long long epoch;
+    cudaGraphExec_t exec;      // nullptr: seen once, uncaptured (the warm-up run that sizes every buffer)
+    unsigned long long kernels;  // launches one replay stands for
+    int failures;
+  };
+  std::vector<ProveGraph> graphs;
+  bool graphs_on = true;
+  unsigned long long graph_replays = 0, graph_captures = 0;
   void* fr_state = nullptr;                       // NTT tables, owned by fr.cu
   void* g1_table = nullptr;                       // fixed-base tables, owned by g1.cu / g2.cu
   void* g2_table = nullptr;
@@ -196,6 +220,8 @@ int fq_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t
 // C = s*A + r*B1 + L + H (projective partial sums on device) -> canonical affine
 int prove_assemble_c(zkb_ctx* ctx, const void* pA, const void* pB1, const void* pL, const void* pH, const void* r_dev,
                      const void* s_dev, void* out_c_dev);
+// C = SA + RB1 + L + H where the scalars were already folded into the MSMs (small circuits)
+int prove_assemble_sum(zkb_ctx* ctx, const void* pSA, const void* pRB1, const void* pL, const void* pH, void* out_c_dev);
 // sharded prove: sum `world` partial records [A | B1 | L | H (XYZZ G1) | B2 (XYZZ G2)] and finish the proof (g1.cu / g2.cu)
 int prove_combine_g1(zkb_ctx* ctx, const void* parts, int world, size_t stride, const void* r_dev, const void* s_dev,
                      void* out_a_dev, void* out_c_dev);
@@ -218,6 +244,7 @@ struct WitnessBufs {
 int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
                     int log_domain, const WitnessBufs& w, Fr* h_out);
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail);
+int fr_scale(zkb_ctx* ctx, const Fr* in, const Fr* k_dev, Fr* out, size_t n);  // out[i] = k * in[i], all canonical
 int setup_scalars_dev(zkb_ctx* ctx, const uint64_t* const col_ptr[3], const uint32_t* const row[3], const Fr* const coeff[3],
                       uint64_t nc, uint64_t ni, uint64_t nw, int logn, const Fr* in5, Fr* consts, Fr* u, Fr* a_out, Fr* b_out,
                       Fr* abc_out, Fr* h_out);

@@ -341,6 +341,15 @@ __device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sh) {
 // sum_s s T[s] with s = hi * C + lo (C = 2^MSM_COL_LOG columns) = C * sum_hi hi * Row[hi] + sum_lo lo * Col[lo].
 // blocks [0, rows): Row[hi] = sum_lo T[hi C + lo]; blocks [rows, 2 rows): WRow[hi] = sum_lo W[hi C + lo];
 // blocks [2 rows, 2 rows + C): Col[lo] = sum_hi T[hi C + lo].   out = Row[rows] | WRow[rows] | Col[C]
+// With few rows (small MSMs: rows <= MSM_COL_SEQ) a column is summed by ONE thread, THREADS columns per block, instead of a
+// block per column tree-summing mostly empty slots: same depth, 1/64 of the resident blocks (small proofs run many at a time
+// and are bound by block slots, not by arithmetic).
+constexpr size_t MSM_COL_SEQ = 16;
+template <int THREADS>
+inline unsigned msm_rowcol_blocks(size_t rows) {
+  constexpr size_t C = size_t(1) << MSM_COL_LOG;
+  return unsigned(2 * rows + (rows <= MSM_COL_SEQ ? C / THREADS : C));
+}
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 msm_rowcol_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ W, size_t nseg, size_t rows, XYZZ<F>* __restrict__ out) {
@@ -353,6 +362,12 @@ msm_rowcol_kernel(const XYZZ<F>* __restrict__ T, const XYZZ<F>* __restrict__ W, 
     size_t hi = b < rows ? b : b - rows;
     for (size_t lo = threadIdx.x; lo < C; lo += THREADS)
       if (hi * C + lo < nseg) acc.add(load_xyzz(src + hi * C + lo));
+  } else if (rows <= MSM_COL_SEQ) {  // block-uniform branch: these blocks never reach block_sum's barriers
+    size_t lo = (b - 2 * rows) * THREADS + threadIdx.x;
+    for (size_t hi = 0; hi < rows; hi++)
+      if (hi * C + lo < nseg) acc.add(load_xyzz(T + hi * C + lo));
+    store_xyzz(out + 2 * rows + lo, acc);
+    return;
   } else {
     size_t lo = b - 2 * rows;
     for (size_t hi = threadIdx.x; hi < rows; hi += THREADS)
@@ -590,8 +605,9 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
   P* planes = (P*)(base + L.o_planes);
   ProfScope ps(ctx, PH0 + 3);
   msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg, L.seg_log);
-  msm_rowcol_kernel<F, 64><<<unsigned(2 * L.rows + (size_t(1) << MSM_COL_LOG)), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
-  msm_plane_kernel<F, 64><<<dim3(16, 3), 64, 0, st>>>(part, L.rows, planes);
+  msm_rowcol_kernel<F, 64><<<msm_rowcol_blocks<64>(L.rows), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
+  const int nplanes = L.row_planes > L.col_planes ? L.row_planes : L.col_planes;  // planes beyond these sum nothing and are not read
+  msm_plane_kernel<F, 64><<<dim3(nplanes > 0 ? nplanes : 1, 3), 64, 0, st>>>(part, L.rows, planes);
   msm_final_kernel<F><<<1, 32, 0, st>>>(planes, L.row_planes, L.col_planes, L.seg_log, out_xyzz, out_affine);
   ctx->launches += 4;
   return cudaGetLastError();

@@ -40,6 +40,10 @@ int set_device(zkb_ctx* ctx) {
 extern "C" const char* zkb_version(void) { return "zkb200 0.2 (sm_100a)"; }
 
 extern "C" int zkb_device_count(void) {
+  // A prove runs on up to six streams and small proofs are served by several contexts per GPU: with the default 8 hardware
+  // queues, streams alias and a long single-block kernel of one proof stalls the others.  Effective only if this process has
+  // not created its CUDA context yet (zelana_b200/__init__.py sets it for Python hosts as well); never overrides the user.
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
     cudaGetLastError();
@@ -99,6 +103,9 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
   ctx->msm_ws.release();
   ctx->pzb.release();
   for (auto& lane : ctx->aux) {
@@ -111,7 +118,7 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   }
   if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
   DevBuf* bufs[] = {&ctx->scal, &ctx->res, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->flag, &ctx->pz, &ctx->pzm, &ctx->pwa,
-                    &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts};
+                    &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts, &ctx->pzsa, &ctx->pzrb};
   for (DevBuf* b : bufs) b->release();
   fr_state_free(ctx);
   fixed_table_free<Fq>(ctx);
@@ -133,6 +140,17 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
 
 extern "C" const char* zkb_last_error(zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" unsigned long long zkb_launch_count(zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int zkb_ctx_set_graphs(zkb_ctx* ctx, int on) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  ctx->graphs_on = on != 0;
+  return ZKB_OK;
+}
+extern "C" int zkb_graph_stats(zkb_ctx* ctx, unsigned long long* captures, unsigned long long* replays) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (captures) *captures = ctx->graph_captures;
+  if (replays) *replays = ctx->graph_replays;
+  return ZKB_OK;
+}
 extern "C" int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c) {
   if (!ctx || c < 0 || c > 23 || (c > 0 && c < 2)) return ZKB_ERR_INVALID_ARG;
   ctx->msm_c = c;
@@ -281,6 +299,7 @@ extern "C" int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, 
 namespace {
 
 void csr_free(CsrDev& c) {
+  g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
   if (c.row_ptr) cudaFree(c.row_ptr);
   if (c.col) cudaFree(c.col);
   if (c.coeff) cudaFree(c.coeff);
@@ -367,7 +386,9 @@ static int reserve_prove_bufs(zkb_ctx* ctx, size_t n, size_t nv, size_t nw) {
   CUDA_TRY(ctx, ctx->pzb.reserve((nv + 3) * 32));
   CUDA_TRY(ctx, ctx->pzl.reserve((nw + 1) * 32));
   CUDA_TRY(ctx, ctx->prs.reserve(64));
-  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64));
+  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64 + sizeof(XYZZ<Fq>)));
+  CUDA_TRY(ctx, ctx->pzsa.reserve((nv + 2) * 32));
+  CUDA_TRY(ctx, ctx->pzrb.reserve((nv + 2) * 32));
   return ZKB_OK;
 }
 
@@ -792,7 +813,7 @@ extern "C" int zkb_setup(zkb_ctx* ctx, const zkb_r1cs_desc* d, const zkb_setup_p
 namespace {
 
 struct ProveOut {
-  XYZZ<Fq>*pA, *pB1, *pL, *pH;
+  XYZZ<Fq>*pA, *pB1, *pL, *pH, *pSA;
   XYZZ<Fq2>* pB2;
   uint32_t *oA, *oB, *oC;
 };
@@ -808,26 +829,17 @@ ProveOut prove_out(zkb_ctx* ctx) {
   o.oA = reinterpret_cast<uint32_t*>(pts + 4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>));
   o.oB = o.oA + 16;
   o.oC = o.oB + 32;
+  o.pSA = reinterpret_cast<XYZZ<Fq>*>(o.oC + 16);
   return o;
 }
 
-// Queues the whole prover for this key (or key shard) on the context's streams.  partial: every MSM leaves its projective
-// partial sum in ProveOut (A, B1, L, H, B2); otherwise A, B and C are finished to canonical affine bytes in oA, oB, oC.
-int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
-                  const uint8_t s[32], bool partial, const char* who) {
-  if (pk->device != ctx->device || m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "%s: key/matrices on another device", who);
+// Everything of a prove that runs on the device, queued on the context's streams: z, r, s are already in pz / prs.
+int prove_device_part(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, bool partial, const char* who) {
   const size_t nv = m->ni + m->nw, nw = m->nw, ni = m->ni;
   const size_t n = size_t(1) << m->log_domain;
-  if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: key has %zu variables, circuit has %zu", who, pk->nv, nv);
-  if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: l_query has %zu points, circuit has %zu witness variables", who, pk->nw, nw);
-  ZKB_TRY(set_device(ctx));
   cudaStream_t st = ctx->stream;
-  ZKB_TRY(reserve_prove_bufs(ctx, n, nv, nw));
   Fr* rs = ctx->prs.as<Fr>();
   Fr* z = ctx->pz.as<Fr>();
-  CUDA_TRY(ctx, cudaMemcpyAsync(z, z_host, nv * 32, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
   ProveOut o = prove_out(ctx);
   const size_t na = pk->a_ext->n;   // this shard's slice [off_a, off_a + na) of the nv + 2 extended scalars
 
@@ -853,8 +865,20 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
     }
     CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming));
   }
+  // Small circuits: fold s and r into the MSMs instead of multiplying their results -- s A = MSM(a_ext, s za) on a fifth lane,
+  // r B1 = MSM(b1_ext, r zb) in place of B1 -- because the two 254-step double-and-add chains (1.9 ms on one thread each) are
+  // half the latency of an L2-sized proof, while an extra 6 k-point MSM next to the others is free.  Large circuits keep
+  // the chains: 2 ms is nothing next to a 2^21-point MSM, an extra one is not.
+  const bool prescaled = !partial && nv <= (size_t(1) << 16);
+  Fr* zsa = ctx->pzsa.as<Fr>();
+  Fr* zrb = ctx->pzrb.as<Fr>();
+  if (prescaled) {
+    ZKB_TRY(fr_scale(ctx, za, rs + 1, zsa, nv + 2));
+    ZKB_TRY(fr_scale(ctx, zb, rs, zrb, nv + 2));
+  }
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, st));
   int lane_rc = ZKB_OK;
+  bool lane_used[5] = {false, false, false, false, false};
   auto on_lane = [&](int idx, auto&& fn) {
     auto& lane = ctx->aux[idx];
     if (lane_rc != ZKB_OK) return;
@@ -862,6 +886,7 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
       lane_rc = ZKB_ERR_CUDA;
       return;
     }
+    lane_used[idx] = true;
     std::swap(ctx->stream, lane.stream);
     std::swap(ctx->msm_ws, lane.ws);
     int rc = fn();
@@ -871,9 +896,10 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
     if (rc != ZKB_OK) lane_rc = rc;
   };
   on_lane(0, [&] { return msm_dev_impl<Fq2>(ctx, pk->b2_ext, 0, zb + pk->off_a, na, partial ? nullptr : o.oB, partial ? o.pB2 : nullptr); });
-  on_lane(1, [&] { return msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za + pk->off_a, na, partial ? nullptr : o.oA, o.pA); });
-  on_lane(2, [&] { return msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, zb + pk->off_a, na, nullptr, o.pB1); });
+  on_lane(1, [&] { return msm_dev_impl<Fq>(ctx, pk->a_ext, 0, za + pk->off_a, na, partial ? nullptr : o.oA, prescaled ? nullptr : o.pA); });
+  on_lane(2, [&] { return msm_dev_impl<Fq>(ctx, pk->b1_ext, 0, (prescaled ? zrb : zb) + pk->off_a, na, nullptr, o.pB1); });
   on_lane(3, [&] { return msm_dev_impl<Fq>(ctx, pk->l_ext, 0, zl + pk->off_l, pk->l_ext->n, nullptr, o.pL); });
+  if (prescaled) on_lane(4, [&] { return msm_dev_impl<Fq>(ctx, pk->a_ext, 0, zsa + pk->off_a, na, nullptr, o.pSA); });
 
   // main stream: h = witness_map_from_matrices, then H = MSM(h_query, h) (msm_bigint truncates to the shorter of the two)
   auto main_part = [&]() -> int {
@@ -888,8 +914,8 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
   int mrc = lane_rc == ZKB_OK ? main_part() : ZKB_OK;
   // join every lane before anything else: their work reads buffers owned by this context
   bool joined = true;
-  for (auto& lane : ctx->aux)
-    if (cudaStreamWaitEvent(st, lane.done, 0) != cudaSuccess) joined = false;
+  for (int i = 0; i < 5; i++)
+    if (lane_used[i] && cudaStreamWaitEvent(st, ctx->aux[i].done, 0) != cudaSuccess) joined = false;
   if (lane_rc != ZKB_OK || mrc != ZKB_OK || !joined) {
     cudaGetLastError();
     for (auto& lane : ctx->aux) cudaStreamSynchronize(lane.stream);
@@ -897,8 +923,100 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
     return lane_rc != ZKB_OK ? lane_rc : (mrc != ZKB_OK ? mrc : ZKB_ERR_CUDA);
   }
   // C = s A + r B1 + L + H
-  if (!partial) ZKB_TRY(prove_assemble_c(ctx, o.pA, o.pB1, o.pL, o.pH, rs, rs + 1, o.oC));
+  if (prescaled) ZKB_TRY(prove_assemble_sum(ctx, o.pSA, o.pB1, o.pL, o.pH, o.oC));
+  else if (!partial) ZKB_TRY(prove_assemble_c(ctx, o.pA, o.pB1, o.pL, o.pH, rs, rs + 1, o.oC));
   return ZKB_OK;
+}
+
+
+void prove_graphs_clear(zkb_ctx* ctx) {
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
+}
+
+// Replays the captured device part when one is cached for (key, matrices) and no buffer has moved since; otherwise runs it
+// directly (first call: the run that sizes every buffer, creates the lanes and the NTT tables) or captures it (second call).
+// A capture that fails -- it is only ever an optimisation -- falls back to direct launches and is not retried for that key.
+int prove_device_graphed(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, bool partial, const char* who) {
+  if (!ctx->graphs_on || ctx->prof.on) return prove_device_part(ctx, pk, m, partial, who);
+  const unsigned long long epoch = g_alloc_epoch.load(std::memory_order_relaxed);
+  zkb_ctx::ProveGraph* slot = nullptr;
+  for (auto& g : ctx->graphs)
+    if (g.pk == pk && g.m == m && g.partial == partial) slot = &g;
+  if (slot && slot->epoch != epoch) {  // some buffer, key or table moved: whatever was captured is stale
+    if (slot->exec) cudaGraphExecDestroy(slot->exec);
+    slot->exec = nullptr;
+    slot->epoch = epoch;
+    return prove_device_part(ctx, pk, m, partial, who);  // warm again under the new layout
+  }
+  if (!slot) {
+    if (ctx->graphs.size() >= 16) prove_graphs_clear(ctx);
+    ctx->graphs.push_back({pk, m, partial, 0, nullptr, 0, 0});
+    int rc = prove_device_part(ctx, pk, m, partial, who);
+    ctx->graphs.back().epoch = g_alloc_epoch.load(std::memory_order_relaxed);  // after the allocations of this warm-up
+    return rc;
+  }
+  if (slot->exec) {
+    CUDA_TRY(ctx, cudaGraphLaunch(slot->exec, ctx->stream));
+    ctx->launches += slot->kernels;
+    ctx->graph_replays++;
+    return ZKB_OK;
+  }
+  if (slot->failures) return prove_device_part(ctx, pk, m, partial, who);
+  // capture
+  const unsigned long long launches0 = ctx->launches;
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    slot->failures++;
+    return prove_device_part(ctx, pk, m, partial, who);
+  }
+  int rc = prove_device_part(ctx, pk, m, partial, who);
+  cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+  const unsigned long long kernels = ctx->launches - launches0;
+  ctx->launches = launches0;  // nothing ran yet
+  cudaGraphExec_t exec = nullptr;
+  const unsigned long long epoch_now = g_alloc_epoch.load(std::memory_order_relaxed);
+  const bool moved = rc == ZKB_OK && ce == cudaSuccess && epoch_now != epoch;  // another context allocated meanwhile: not a failure
+  if (rc == ZKB_OK && ce == cudaSuccess && graph && !moved) ce = cudaGraphInstantiate(&exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  if (moved || rc != ZKB_OK || ce != cudaSuccess || !exec) {
+    cudaGetLastError();
+    if (moved) slot->epoch = epoch_now; else slot->failures++;
+    // leave the lanes in a defined state, then do the work directly
+    for (auto& lane : ctx->aux)
+      if (lane.stream) cudaStreamSynchronize(lane.stream);
+    cudaGetLastError();
+    return prove_device_part(ctx, pk, m, partial, who);
+  }
+  slot->exec = exec;
+  slot->kernels = kernels;
+  ctx->graph_captures++;
+  CUDA_TRY(ctx, cudaGraphLaunch(exec, ctx->stream));
+  ctx->launches += kernels;
+  ctx->graph_replays++;
+  return ZKB_OK;
+}
+
+// Queues the whole prover for this key (or key shard) on the context's streams.  partial: every MSM leaves its projective
+// partial sum in ProveOut (A, B1, L, H, B2); otherwise A, B and C are finished to canonical affine bytes in oA, oB, oC.
+int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
+                  const uint8_t s[32], bool partial, const char* who) {
+  if (pk->device != ctx->device || m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "%s: key/matrices on another device", who);
+  const size_t nv = m->ni + m->nw, nw = m->nw, ni = m->ni;
+  const size_t n = size_t(1) << m->log_domain;
+  if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: key has %zu variables, circuit has %zu", who, pk->nv, nv);
+  if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: l_query has %zu points, circuit has %zu witness variables", who, pk->nw, nw);
+  ZKB_TRY(set_device(ctx));
+  cudaStream_t st = ctx->stream;
+  ZKB_TRY(reserve_prove_bufs(ctx, n, nv, nw));
+  Fr* rs = ctx->prs.as<Fr>();
+  Fr* z = ctx->pz.as<Fr>();
+  CUDA_TRY(ctx, cudaMemcpyAsync(z, z_host, nv * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
+  return prove_device_graphed(ctx, pk, m, partial, who);
 }
 
 }  // namespace
@@ -936,7 +1054,7 @@ extern "C" int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int wor
   ZKB_TRY(set_device(ctx));
   cudaStream_t st = ctx->stream;
   CUDA_TRY(ctx, ctx->prs.reserve(64));
-  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64));
+  CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64 + sizeof(XYZZ<Fq>)));
   Fr* rs = ctx->prs.as<Fr>();
   CUDA_TRY(ctx, cudaMemcpyAsync(rs, r, 32, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(rs + 1, s, 32, cudaMemcpyHostToDevice, st));
