@@ -366,7 +366,7 @@ def run_ours(args):
     if not args.no_e2e:
         bases.free()
         bases = None
-        proofs = l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank)
+        proofs = l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, cpu_baseline=not args.no_cpu_baseline)
 
     if rank == 0:
         line = {
@@ -453,7 +453,7 @@ def mimc_r1cs_numpy(np, num_perm, seed, rounds=91):
     return 2, nv - 2, (A, B, Cm), z
 
 
-def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, contexts=6, per_context=8):
+def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, contexts=16, per_context=8, cpu_baseline=True):
     """The other half of BASELINE.json's metric ("Groth16 proofs/s (L2 batch circuit)"): every GPU proves independent batches of
     the reference's own L2BlockCircuit (prover/src/l2_circuit.rs; the L2BlockCircuit::dummy() shape keygen.rs fixes: 6415
     constraints, domain 2^13) through zkb_l2_prove = `BatchProver::prove` end to end: witness assignment on the host (Poseidon
@@ -519,12 +519,35 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, cont
         circ.assign(jobs[0][0][0])
     assign_ms = (time.perf_counter() - t1) / 8 * 1e3
     total = world * contexts * per_context
+    # the CPU restatement of arkworks' prover beside it (rank 0, N = 1): same key, same assignment, same (r, s) -> same bytes
+    cpu = None
+    if cpu_baseline and rank == 0 and world == 1:
+        from oracle import cpu as orc
+        threads = orc.max_threads()
+        cpk = orc.ProvingKey(**{k2: _raw[k2] for k2 in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query",
+                                                       "b_g1_query", "b_g2_query", "h_query", "l_query")})
+        cm = orc.R1cs(circ.num_instance, circ.num_witness, csr=(a, b, c))
+        ckt = jobs[0][0][0]
+        zb = circ.assign(ckt)
+        r_b, s_b = l2.prover_randomness(ckt.batch_id)
+        reps = 5
+        t2 = time.perf_counter()
+        for _ in range(reps):
+            cproof = orc.prove(cpk, cm, zb, r_b, s_b, threads=threads)
+        t_cpu = (time.perf_counter() - t2) / reps
+        if zelana_b200.proof_to_solana_bytes(*cproof) != bytes(jobs[0][0][4]):
+            raise SystemExit("PARITY FAILURE: L2 circuit proof from the GPU != CPU restatement's proof (same key, witness, r, s)")
+        cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": threads, "kind": "port",
+               "sample": "%d proofs of the same circuit, key and assignment, %.1f ms each; C++ restatement of ark-groth16 "
+                         "(witness map + 5 MSMs), proof bytes identical to the GPU's" % (reps, t_cpu * 1e3)}
+    graph_stats = [cx.graph_stats() for cx in ctxs]
     m.free()
     pk.free()
     for cx in ctxs:
         cx.close()
     return {"value": total / dt, "unit": "proofs/s", "proofs": total, "contexts_per_gpu": contexts,
             "host_assign_ms_per_proof": assign_ms, "keygen_s": keygen_s, "assignment_satisfied": ok,
+            "cpu_baseline": cpu, "graph_replays_rank0": sum(g[1] for g in graph_stats),
             "circuit": "L2BlockCircuit::dummy() shape (prover/src/l2_circuit.rs): %d constraints, %d witness variables, domain 2^13; "
                        "BatchProver::prove end to end per proof (host witness assignment + GPU prove), real key from the GPU "
                        "trusted setup (StdRng seed 0 as keygen.rs), one proof per context at a time, independent proofs sharded "
