@@ -453,75 +453,55 @@ def mimc_r1cs_numpy(np, num_perm, seed, rounds=91):
     return 2, nv - 2, (A, B, Cm), z
 
 
-def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, contexts=16, per_context=8, cpu_baseline=True):
+def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, lanes=16, per_lane=8, cpu_baseline=True):
     """The other half of BASELINE.json's metric ("Groth16 proofs/s (L2 batch circuit)"): every GPU proves independent batches of
     the reference's own L2BlockCircuit (prover/src/l2_circuit.rs; the L2BlockCircuit::dummy() shape keygen.rs fixes: 6415
-    constraints, domain 2^13) through zkb_l2_prove = `BatchProver::prove` end to end: witness assignment on the host (Poseidon
-    folds, comparison bits), StdRng(batch_id) -> (r, s), GPU prove, Solana byte layout.  The key is a real one: keygen.rs's flow
-    (StdRng seed 0) with the setup on the GPU.  `contexts` proofs in flight per GPU, no communication; every proof has its own
-    batch id, hence its own roots, assignment and randomness.  Aggregate proofs/s, wall clock, max over ranks."""
-    import ctypes as C
+    constraints, domain 2^13) through ONE C call per step, zkb_l2_batch_prove: per proof `BatchProver::prove` end to end --
+    witness assignment on the host (Poseidon folds, comparison bits), StdRng(batch_id) -> (r, s), GPU prove, Solana byte layout
+    -- on `lanes` contexts + host threads inside the library.  The key is a real one: keygen.rs's flow (StdRng seed 0) with the
+    setup on the GPU.  Every proof has its own batch id, hence its own roots, assignment and randomness; no communication
+    between GPUs.  Aggregate proofs/s, wall clock, max over ranks."""
     from zelana_b200 import l2_circuit as l2
-    dev = torch.device("cuda", local)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(contexts)]
-    ctxs = [zelana_b200.Context(local, stream=st.cuda_stream) for st in streams]
+    ctx = zelana_b200.Context(local)
     t0 = time.perf_counter()
-    circ, pk_bytes, vk_bytes, _raw = l2.keygen(ctxs[0])
+    circ, pk_bytes, vk_bytes, _raw = l2.keygen(ctx)
     keygen_s = time.perf_counter() - t0
-    pk = ctxs[0].proving_key_compressed(pk_bytes, validate=False)
-    a, b, c = circ.matrices()
-    m = ctxs[0].r1cs(circ.num_instance, circ.num_witness, a, b, c)
-    ctxs[0].synchronize()
-    lib = circ.lib
+    pk = ctx.proving_key_compressed(pk_bytes, validate=False)
+    prover = l2.L2BatchProver(ctx, circ, pk, lanes=lanes)
+    per_gpu = lanes * per_lane
 
     def batch(bid):
         ckt = l2.L2BlockCircuit(transactions=[l2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), 1 + bid % 1000)],
                                 initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): bid}, batch_id=bid)
-        ckt = ckt.with_inputs(l2.satisfying_inputs(ckt))
-        w, keep = l2._c_witness(ckt)
-        return ckt, w, keep, l2._c_inputs(ckt.public_inputs()), (C.c_uint8 * 256)()
+        return ckt.with_inputs(l2.satisfying_inputs(ckt))
 
-    jobs = [[batch((rank * contexts + j) * per_context + i + 1) for i in range(per_context)] for j in range(contexts)]
-
-    def work(cx, mine):
-        for ckt, w, keep, x, out in mine:
-            rc = lib.zkb_l2_prove(cx.h, pk.h, m.h, circ.h, C.byref(x), C.byref(w), out)
-            if rc != 0:
-                raise SystemExit("zkb_l2_prove failed: %d %s" % (rc, lib.zkb_l2_last_error()))
-
-    def step():
-        th = [threading.Thread(target=work, args=(ctxs[j], jobs[j])) for j in range(contexts)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-
-    for _ in range(3):     # 1st proof of a context sizes its buffers, 2nd captures the CUDA graph, 3rd replays it
-        step()
+    circuits = [batch(rank * per_gpu + i + 1) for i in range(per_gpu)]
+    pack = prover.marshal(circuits)
+    for _ in range(3):     # 1st proof of a lane sizes its buffers, 2nd captures the CUDA graph, 3rd replays it
+        proofs = prover.prove_marshalled(pack)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     timed_steps = 3
     t0 = time.perf_counter()
     for _ in range(timed_steps):
-        step()
-    torch.cuda.synchronize()
+        proofs = prover.prove_marshalled(pack)       # returns when every proof of the step is back in host memory
     dt = (time.perf_counter() - t0) / timed_steps
     if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     # one proof of this run checked the slow way (rank 0): the assignment satisfies the matrices
     ok = None
     if rank == 0:
-        ok = circ.is_satisfied(circ.assign(jobs[0][0][0]))[0]
+        ok = circ.is_satisfied(circ.assign(circuits[0]))[0]
         if not ok:
             raise SystemExit("PARITY FAILURE: L2 circuit assignment does not satisfy its own constraints")
     t1 = time.perf_counter()
     for _ in range(8):
-        circ.assign(jobs[0][0][0])
+        circ.assign(circuits[0])
     assign_ms = (time.perf_counter() - t1) / 8 * 1e3
-    total = world * contexts * per_context
+    total = world * per_gpu
     # the CPU restatement of arkworks' prover beside it (rank 0, N = 1): same key, same assignment, same (r, s) -> same bytes
     cpu = None
     if cpu_baseline and rank == 0 and world == 1:
@@ -529,32 +509,30 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, cont
         threads = orc.max_threads()
         cpk = orc.ProvingKey(**{k2: _raw[k2] for k2 in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query",
                                                        "b_g1_query", "b_g2_query", "h_query", "l_query")})
+        a, b, c = circ.matrices()
         cm = orc.R1cs(circ.num_instance, circ.num_witness, csr=(a, b, c))
-        ckt = jobs[0][0][0]
-        zb = circ.assign(ckt)
-        r_b, s_b = l2.prover_randomness(ckt.batch_id)
+        zb = circ.assign(circuits[0])
+        r_b, s_b = l2.prover_randomness(circuits[0].batch_id)
         reps = 5
         t2 = time.perf_counter()
         for _ in range(reps):
             cproof = orc.prove(cpk, cm, zb, r_b, s_b, threads=threads)
         t_cpu = (time.perf_counter() - t2) / reps
-        if zelana_b200.proof_to_solana_bytes(*cproof) != bytes(jobs[0][0][4]):
+        if zelana_b200.proof_to_solana_bytes(*cproof) != proofs[0]:
             raise SystemExit("PARITY FAILURE: L2 circuit proof from the GPU != CPU restatement's proof (same key, witness, r, s)")
         cpu = {"value": 1.0 / t_cpu, "unit": "proofs/s", "cores": threads, "kind": "port",
                "sample": "%d proofs of the same circuit, key and assignment, %.1f ms each; C++ restatement of ark-groth16 "
                          "(witness map + 5 MSMs), proof bytes identical to the GPU's" % (reps, t_cpu * 1e3)}
-    graph_stats = [cx.graph_stats() for cx in ctxs]
-    m.free()
+    prover.close()
     pk.free()
-    for cx in ctxs:
-        cx.close()
-    return {"value": total / dt, "unit": "proofs/s", "proofs": total, "contexts_per_gpu": contexts,
-            "host_assign_ms_per_proof": assign_ms, "keygen_s": keygen_s, "assignment_satisfied": ok,
-            "cpu_baseline": cpu, "graph_replays_rank0": sum(g[1] for g in graph_stats),
+    ctx.close()
+    return {"value": total / dt, "unit": "proofs/s", "proofs": total, "lanes_per_gpu": lanes, "ms_per_batch": dt * 1e3,
+            "host_assign_ms_per_proof": assign_ms, "keygen_s": keygen_s, "assignment_satisfied": ok, "cpu_baseline": cpu,
             "circuit": "L2BlockCircuit::dummy() shape (prover/src/l2_circuit.rs): %d constraints, %d witness variables, domain 2^13; "
-                       "BatchProver::prove end to end per proof (host witness assignment + GPU prove), real key from the GPU "
-                       "trusted setup (StdRng seed 0 as keygen.rs), one proof per context at a time, independent proofs sharded "
-                       "over the GPUs with no communication" % (circ.num_constraints, circ.num_witness)}
+                       "one zkb_l2_batch_prove call per step = %d x BatchProver::prove end to end (host witness assignment + GPU "
+                       "prove + Solana bytes) on %d lanes per GPU, real key from the GPU trusted setup (StdRng seed 0 as "
+                       "keygen.rs), independent proofs sharded over the GPUs with no communication"
+                       % (circ.num_constraints, circ.num_witness, per_gpu, lanes)}
 
 
 def run_prove(args):

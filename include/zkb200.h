@@ -277,6 +277,21 @@ int zkb_l2_prover_randomness(uint64_t batch_id, uint8_t r[32], uint8_t s[32]);
 int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c,
                  const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witness, uint8_t proof_out[256]);
 
+
+/* ---- batches of independent L2 proofs on one GPU (BASELINE.json config 5; the forge coordinator's chunk-per-worker
+ * parallelism, forge/crates/prover-coordinator/src/dispatcher.rs:290-330, inside one process) ------------------------------
+ * A small proof is a chain of short kernels; a B200 holds 16-32 of them at once.  A zkb_l2_batch owns `lanes` contexts on one
+ * device and as many host threads; proof i is assigned (host) and proved (GPU) on lane i mod lanes.  pk, m and c are shared.
+ * proofs_out: n x 256 B.  status_out (may be NULL): per-proof zkb_status.  Returns the first error, ZKB_OK if all succeeded;
+ * a failed proof does not invalidate the others. */
+typedef struct zkb_l2_batch zkb_l2_batch;
+int zkb_l2_batch_create(int device, int lanes /* 1..64 */, zkb_l2_batch** out);
+void zkb_l2_batch_destroy(zkb_l2_batch* b);
+int zkb_l2_batch_lanes(const zkb_l2_batch* b);
+int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c,
+                       const zkb_l2_public_inputs* inputs /* n */, const zkb_l2_witness* witnesses /* n */, size_t n,
+                       uint8_t* proofs_out, int* status_out);
+
 #ifdef __cplusplus
 }
 #endif

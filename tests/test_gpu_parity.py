@@ -722,3 +722,39 @@ def test_prove_graph_replay_is_bit_identical_and_survives_reallocation(mimc_setu
     assert launches_on == launches_off                              # a replay counts the kernels it stands for
     ref = g16.prove_with_rs(pk, r1cs, z, cases[0][0], cases[0][1])
     assert graphed[0] == (bn.g1_to_raw(ref.a), bn.g2_to_raw(ref.b), bn.g1_to_raw(ref.c))
+
+
+def test_l2_batch_prove_equals_single_proofs(ctx, l2_setup):
+    """zkb_l2_batch_prove (lanes of contexts + host threads inside the library) returns, in order, exactly the proofs
+    zkb_l2_prove makes one at a time; a batch smaller than the lane count and an empty batch work; a proof of the wrong
+    shape fails alone."""
+    from zelana_b200 import ZkbError
+    from zelana_b200 import l2_circuit as P2
+    circ, pk_bytes, vk_bytes, raw = l2_setup
+    dpk = ctx.proving_key_compressed(pk_bytes, validate=False)
+    single = P2.L2Prover(ctx, circ, dpk, vk_bytes)
+
+    def batch(bid):
+        c = P2.L2BlockCircuit(transactions=[P2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), bid)],
+                              initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): 7 * bid}, batch_id=bid)
+        return c.with_inputs(P2.satisfying_inputs(c))
+
+    circuits = [batch(i + 1) for i in range(21)]
+    expect = [single.prove_circuit(c).proof_bytes for c in circuits]
+    bp = P2.L2BatchProver(ctx, circ, dpk, lanes=8)
+    assert bp.lanes == 8
+    for _ in range(3):                       # direct launches, graph capture, graph replay
+        assert bp.prove(circuits) == expect
+    assert bp.prove(circuits[:3]) == expect[:3]
+    assert bp.prove([]) == []
+    wrong = P2.L2BlockCircuit(transactions=circuits[0].transactions * 2, initial_accounts=circuits[0].initial_accounts)
+    pack = bp.marshal(circuits[:4] + [wrong] + circuits[4:6])
+    with pytest.raises(ZkbError) as e:
+        bp.prove_marshalled(pack)
+    assert e.value.code == -6
+    n, _xs, _ws, _keep, out, status = pack
+    assert list(status)[:7] == [0, 0, 0, 0, -6, 0, 0]
+    assert [out.raw[256 * i:256 * i + 256] for i in (0, 1, 2, 3, 5, 6)] == expect[:6]
+    bp.close()
+    single.m.free()
+    dpk.free()

@@ -126,6 +126,10 @@ SIGNATURES = {
     "zkb_l2_poseidon_hash": (_I, [_P, _SZ, _P]),
     "zkb_l2_prover_randomness": (_I, [C.c_uint64, _P, _P]),
     "zkb_l2_prove": (_I, [_P, _P, _P, _P, C.POINTER(L2PublicInputs), C.POINTER(L2Witness), _P]),
+    "zkb_l2_batch_create": (_I, [_I, _I, C.POINTER(_P)]),
+    "zkb_l2_batch_destroy": (None, [_P]),
+    "zkb_l2_batch_lanes": (_I, [_P]),
+    "zkb_l2_batch_prove": (_I, [_P, _P, _P, _P, C.POINTER(L2PublicInputs), C.POINTER(L2Witness), _SZ, _P, C.POINTER(_I)]),
 }
 
 _lib = None

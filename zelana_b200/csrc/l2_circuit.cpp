@@ -80,8 +80,8 @@ static inline Fr sub(const Fr& a, const Fr& b) {
 }
 static inline Fr neg(const Fr& a) { return a.is_zero() ? a : raw_sub(MOD, a); }
 static inline Fr mont_mul(const Fr& a, const Fr& b) {
-  // CIOS without the extra carry word: valid because the modulus leaves its top two bits clear (r < 2^254), and for any
-  // a < 2^256, b < r the result stays below 2 r before the final subtraction.
+  // CIOS without the extra carry word: valid because the modulus leaves its top two bits clear (r < 2^254); with the
+  // multiplicand a < r and ANY multiplier b < 2^256 every partial sum stays below 2 r (from_le_bytes_mod_order relies on it).
   uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
 #pragma GCC unroll 4
   for (int i = 0; i < 4; ++i) {
@@ -1157,4 +1157,80 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
     g_l2_error = "out of host memory";
     return ZKB_ERR_OOM;
   }
+}
+
+// ================================================================================================ batches of proofs
+// BASELINE.json config 5 ("batch of 64 independent L2 proofs"): small proofs are latency chains, so one GPU holds many at once.
+// A zkb_l2_batch owns `lanes` contexts on one device (each with its streams, scratch and captured prove graph) and as many host
+// threads; proof i goes to lane i mod lanes: the thread assigns the witness (host) and proves (GPU), so the assignment of one
+// proof overlaps the device work of the others.  Key, matrices and circuit are shared, read-only.
+#include <thread>
+
+struct zkb_l2_batch {
+  int device = 0;
+  std::vector<zkb_ctx*> lanes;
+};
+
+int zkb_l2_batch_create(int device, int lanes, zkb_l2_batch** out) {
+  if (!out || lanes < 1 || lanes > 64) return ZKB_ERR_INVALID_ARG;
+  *out = nullptr;
+  zkb_l2_batch* b = new (std::nothrow) zkb_l2_batch();
+  if (!b) return ZKB_ERR_OOM;
+  b->device = device;
+  for (int i = 0; i < lanes; ++i) {
+    zkb_ctx* c = nullptr;
+    int rc = zkb_ctx_create(device, &c);
+    if (rc != ZKB_OK) {
+      g_l2_error = "zkb_l2_batch_create: zkb_ctx_create failed";
+      zkb_l2_batch_destroy(b);
+      return rc;
+    }
+    b->lanes.push_back(c);
+  }
+  *out = b;
+  return ZKB_OK;
+}
+
+void zkb_l2_batch_destroy(zkb_l2_batch* b) {
+  if (!b) return;
+  for (zkb_ctx* c : b->lanes) zkb_ctx_destroy(c);
+  delete b;
+}
+
+int zkb_l2_batch_lanes(const zkb_l2_batch* b) { return b ? (int)b->lanes.size() : 0; }
+
+int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c,
+                       const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witnesses, size_t n, uint8_t* proofs_out,
+                       int* status_out) {
+  if (!b || !pk || !m || !c || (n && (!inputs || !witnesses || !proofs_out))) return ZKB_ERR_INVALID_ARG;
+  const size_t nl = b->lanes.size();
+  std::vector<int> first_error(nl, ZKB_OK);
+  std::vector<std::string> messages(nl);
+  auto work = [&](size_t lane) {
+    for (size_t i = lane; i < n; i += nl) {
+      int rc = zkb_l2_prove(b->lanes[lane], pk, m, c, inputs + i, witnesses + i, proofs_out + 256 * i);
+      if (status_out) status_out[i] = rc;
+      if (rc != ZKB_OK && first_error[lane] == ZKB_OK) {
+        first_error[lane] = rc;
+        messages[lane] = zkb_l2_last_error();  // thread-local of this worker
+      }
+    }
+  };
+  try {
+    std::vector<std::thread> threads;
+    const size_t used = n < nl ? n : nl;
+    for (size_t lane = 1; lane < used; ++lane) threads.emplace_back(work, lane);
+    if (used) work(0);
+    for (auto& t : threads) t.join();
+  } catch (const std::exception& e) {  // std::system_error from thread creation
+    g_l2_error = e.what();
+    return ZKB_ERR_OOM;
+  }
+  for (size_t lane = 0; lane < nl; ++lane) {
+    if (first_error[lane] != ZKB_OK) {
+      g_l2_error = messages[lane];
+      return first_error[lane];  // per-proof codes are in status_out; the other proofs of the batch are valid
+    }
+  }
+  return ZKB_OK;
 }

@@ -254,3 +254,46 @@ class L2Prover:
     def close(self):
         self.m.free()
         self.circ.free()
+
+
+class L2BatchProver:
+    """zkb_l2_batch: `lanes` contexts + host threads inside the library proving independent batches side by side on one GPU
+    (BASELINE.json config 5).  One call proves a list of circuits; the key, matrices and circuit shape are shared."""
+
+    def __init__(self, ctx, circ: L2Circuit, pk, lanes: int = 16, device: Optional[int] = None):
+        self.ctx, self.circ, self.pk = ctx, circ, pk
+        a, b, c = circ.matrices()
+        self.m = ctx.r1cs(circ.num_instance, circ.num_witness, a, b, c)
+        ctx.synchronize()
+        h = C.c_void_p()
+        _check(circ.lib.zkb_l2_batch_create(ctx.device if device is None else device, lanes, C.byref(h)))
+        self.h = h
+        self.lanes = int(circ.lib.zkb_l2_batch_lanes(h))
+
+    def marshal(self, circuits: List[L2BlockCircuit]):
+        """-> opaque argument pack for prove_marshalled (lets a caller keep the Python-side packing out of a timed region)."""
+        n = len(circuits)
+        xs, ws, keep = (L2PublicInputs * max(n, 1))(), (L2Witness * max(n, 1))(), []
+        for i, c in enumerate(circuits):
+            xs[i] = _c_inputs(c.public_inputs())
+            w, k = _c_witness(c)
+            ws[i] = w
+            keep.append(k)
+        return n, xs, ws, keep, C.create_string_buffer(256 * max(n, 1)), (C.c_int * max(n, 1))()
+
+    def prove_marshalled(self, pack):
+        n, xs, ws, _keep, out, status = pack
+        rc = self.circ.lib.zkb_l2_batch_prove(self.h, self.pk.h, self.m.h, self.circ.h, xs, ws, n, out, status)
+        if rc != 0:
+            raise ZkbError(rc, (self.circ.lib.zkb_l2_last_error() or b"").decode())
+        return [out.raw[256 * i:256 * i + 256] for i in range(n)]
+
+    def prove(self, circuits: List[L2BlockCircuit]) -> List[bytes]:
+        """256-byte Solana proofs, one per circuit, in order."""
+        return self.prove_marshalled(self.marshal(circuits))
+
+    def close(self):
+        if self.h:
+            self.circ.lib.zkb_l2_batch_destroy(self.h)
+            self.h = None
+        self.m.free()
