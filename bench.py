@@ -527,7 +527,8 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, lane
     pk.free()
     ctx.close()
     return {"value": total / dt, "unit": "proofs/s", "proofs": total, "lanes_per_gpu": lanes, "ms_per_batch": dt * 1e3,
-            "host_assign_ms_per_proof": assign_ms, "keygen_s": keygen_s, "assignment_satisfied": ok, "cpu_baseline": cpu,
+            "host_assign_ms_per_proof": assign_ms, "host_cores": os.cpu_count(), "keygen_s": keygen_s, "assignment_satisfied": ok,
+            "cpu_baseline": cpu,
             "circuit": "L2BlockCircuit::dummy() shape (prover/src/l2_circuit.rs): %d constraints, %d witness variables, domain 2^13; "
                        "one zkb_l2_batch_prove call per step = %d x BatchProver::prove end to end (host witness assignment + GPU "
                        "prove + Solana bytes) on %d lanes per GPU, real key from the GPU trusted setup (StdRng seed 0 as "

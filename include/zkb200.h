@@ -59,6 +59,9 @@ unsigned long long zkb_launch_count(zkb_ctx* ctx);
  * (zkb_prof_enable).  zkb_launch_count keeps counting the kernels a replay stands for. */
 int zkb_ctx_set_graphs(zkb_ctx* ctx, int on);
 int zkb_graph_stats(zkb_ctx* ctx, unsigned long long* captures, unsigned long long* replays);
+/* on: host calls that wait for the GPU sleep on a blocking event instead of spinning in cudaStreamSynchronize (default off;
+ * zkb_l2_batch lanes switch it on: they outnumber the host cores and a spinning waiter takes the core an assignment needs). */
+int zkb_ctx_set_blocking_sync(zkb_ctx* ctx, int on);
 /* force the MSM window width c in [2, 23] (0 = automatic) for bases loaded AFTER this call: the width is fixed when a
  * bases handle builds its window tables 2^(c j) P.  Benchmarking/tests only. */
 int zkb_ctx_set_msm_window(zkb_ctx* ctx, int c);

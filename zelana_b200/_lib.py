@@ -74,6 +74,7 @@ SIGNATURES = {
     "zkb_launch_count": (C.c_ulonglong, [_P]),
     "zkb_ctx_set_msm_window": (_I, [_P, _I]),
     "zkb_ctx_set_graphs": (_I, [_P, _I]),
+    "zkb_ctx_set_blocking_sync": (_I, [_P, _I]),
     "zkb_graph_stats": (_I, [_P, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "zkb_prof_phase_count": (_I, []),
     "zkb_prof_phase_name": (C.c_char_p, [_I]),

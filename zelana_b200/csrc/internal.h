@@ -119,6 +119,13 @@ struct zkb_ctx {
   };
   std::vector<ProveGraph> graphs;
   bool graphs_on = true;
+  // Wait for results by sleeping on an event instead of spinning in cudaStreamSynchronize: batch lanes outnumber the host
+  // cores (8 GPUs x 16 lanes on one box) and a spinning waiter steals the core another lane's witness assignment needs.
+  bool blocking_sync = false;
+  cudaEvent_t sync_ev = nullptr;
+  // 512 B of pinned host memory: proof bytes [0, 256) and the status flag [256, 260) come back here.  A device-to-host copy
+  // into PAGEABLE memory blocks the calling thread (spinning in the driver) until everything queued before it has run.
+  uint8_t* pinned = nullptr;
   unsigned long long graph_replays = 0, graph_captures = 0;
   void* fr_state = nullptr;                       // NTT tables, owned by fr.cu
   void* g1_table = nullptr;                       // fixed-base tables, owned by g1.cu / g2.cu

@@ -1185,6 +1185,7 @@ int zkb_l2_batch_create(int device, int lanes, zkb_l2_batch** out) {
       zkb_l2_batch_destroy(b);
       return rc;
     }
+    zkb_ctx_set_blocking_sync(c, 1);  // lanes usually outnumber the cores: sleep, do not spin, while the GPU works
     b->lanes.push_back(c);
   }
   *out = b;

@@ -12,10 +12,23 @@ using namespace zkb;
 // =============================================================================================== helpers
 namespace zkb {
 
+static int ensure_pinned(zkb_ctx* ctx) {
+  if (!ctx->pinned) CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinned), 512, cudaHostAllocDefault));
+  return ZKB_OK;
+}
+
 int check_flag(zkb_ctx* ctx, const char* what) {
-  int h = 0;
-  CUDA_TRY(ctx, cudaMemcpyAsync(&h, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  ZKB_TRY(ensure_pinned(ctx));
+  int* hf = reinterpret_cast<int*>(ctx->pinned + 256);
+  CUDA_TRY(ctx, cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->blocking_sync) {
+    if (!ctx->sync_ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->sync_ev, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->sync_ev));
+  } else {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  const int h = *hf;
   if (h == 1) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: field element >= modulus", what);
   if (h == 2) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: point not on curve", what);
   if (h == 3) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: both the infinity and the sign flag are set", what);
@@ -117,6 +130,8 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
     lane.ws.release();
   }
   if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
+  if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   DevBuf* bufs[] = {&ctx->scal, &ctx->res, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->flag, &ctx->pz, &ctx->pzm, &ctx->pwa,
                     &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts, &ctx->pzsa, &ctx->pzrb};
   for (DevBuf* b : bufs) b->release();
@@ -143,6 +158,11 @@ extern "C" unsigned long long zkb_launch_count(zkb_ctx* ctx) { return ctx ? ctx-
 extern "C" int zkb_ctx_set_graphs(zkb_ctx* ctx, int on) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   ctx->graphs_on = on != 0;
+  return ZKB_OK;
+}
+extern "C" int zkb_ctx_set_blocking_sync(zkb_ctx* ctx, int on) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  ctx->blocking_sync = on != 0;
   return ZKB_OK;
 }
 extern "C" int zkb_graph_stats(zkb_ctx* ctx, unsigned long long* captures, unsigned long long* replays) {
@@ -1029,10 +1049,14 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
   ZKB_TRY(prove_enqueue(ctx, pk, m, z_host, r, s, false, "zkb_prove"));
   ProveOut o = prove_out(ctx);
   cudaStream_t st = ctx->stream;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_a, o.oA, 64, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_b, o.oB, 128, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(out_c, o.oC, 64, cudaMemcpyDeviceToHost, st));
-  return check_flag(ctx, "witness assignment");
+  // oA | oB | oC are contiguous (64 + 128 + 64 B): one copy into pinned memory, so that the wait below is the only wait
+  ZKB_TRY(ensure_pinned(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, o.oA, 256, cudaMemcpyDeviceToHost, st));
+  ZKB_TRY(check_flag(ctx, "witness assignment"));
+  memcpy(out_a, ctx->pinned, 64);
+  memcpy(out_b, ctx->pinned + 64, 128);
+  memcpy(out_c, ctx->pinned + 192, 64);
+  return ZKB_OK;
 }
 
 // One rank's share of a proof whose key is sharded over `world` GPUs: every rank runs the witness map (no
