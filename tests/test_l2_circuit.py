@@ -211,3 +211,51 @@ def test_native_poseidon_hash_equals_oracle():
             vals = [rnd.randrange(2 ** 256) for _ in range(n)]
             got = P.poseidon_hash([v.to_bytes(32, "little") for v in vals])
             assert int.from_bytes(got, "little") == O.poseidon_hash([v % R for v in vals])
+
+
+def _mid_shape():
+    """16 transfers over 24 accounts (some created by transfers), one commitment, two withdrawals: > 40 000 witness variables,
+    i.e. above the threshold where the library assigns with parallel walkers."""
+    rnd = random.Random(31)
+    rk = lambda: bytes(rnd.randrange(256) for _ in range(32))
+    keys = [rk() for _ in range(24)]
+    acc = {k: 10 ** 6 + i for i, k in enumerate(keys[:20])}
+    txs = [(keys[rnd.randrange(20)], keys[rnd.randrange(24)], rnd.randrange(1, 500)) for _ in range(16)]
+    return txs, acc, [rk()], [(rk(), 77), (rk(), 1)], 123456789
+
+
+def test_parallel_assignment_equals_the_oracle_and_the_sequential_pass():
+    """Circuits above PAR_MIN_WITNESS are assigned by two passes of parallel walkers (leaf hashes + comparisons, then the five
+    fold chains): the bytes must equal the oracle's assignment, and those of a single-threaded run of the same library."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from zelana_b200 import l2_circuit as P
+    shape = _mid_shape()
+    oc = _oracle_circuit(shape)
+    r1cs, z = O.synthesize(oc)
+    assert r1cs.num_witness > 40000 and r1cs.is_satisfied(z)
+    pc = _product_circuit(shape, oc)
+    circ = P.L2Circuit(pc)
+    assert (circ.num_constraints, circ.num_witness) == (r1cs.num_constraints, r1cs.num_witness)
+    zb = circ.assign(pc)
+    assert unpack32(zb) == z
+    assert circ.is_satisfied(zb) == (True, None)
+    # the same library, one thread (the environment variable is read once per process)
+    code = ("import sys, pickle; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from zelana_b200 import l2_circuit as P\n"
+            "pc = pickle.load(open(sys.argv[1], 'rb'))\n"
+            "sys.stdout.buffer.write(P.L2Circuit(pc).assign(pc))\n") % (ROOT, os.path.join(ROOT, "tests"))
+    import pickle
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as f:
+        pickle.dump(pc, f)
+    try:
+        outs = {}
+        for threads in ("1", "5"):
+            env = dict(os.environ, ZKB_L2_ASSIGN_THREADS=threads)
+            outs[threads] = subprocess.run([sys.executable, "-c", code, f.name], env=env, check=True, capture_output=True).stdout
+        assert outs["1"] == zb and outs["5"] == zb
+    finally:
+        os.unlink(f.name)

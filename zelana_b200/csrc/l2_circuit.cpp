@@ -18,11 +18,13 @@
 #include <algorithm>
 #include <array>
 #include <cstdint>
+#include <cstdlib>
 #include <initializer_list>
 #include <cstring>
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zkb200.h"
@@ -286,21 +288,54 @@ struct Csr {
 
 constexpr uint32_t NUM_INSTANCE = 8;  // ONE + the seven public inputs, all allocated before the first witness
 
+// One record per Poseidon hash / balance comparison, in call order: how many witnesses and constraints it allocates.  Taken
+// in the STRUCTURE pass; lets a parallel ASSIGN walker step over a piece another thread computes.
+struct CallRec {
+  uint32_t nwit, ncons;
+};
+enum CallCat { CAT_LEAF = -1 };  // >= 0: the fold chain a hash belongs to (post state, shielded, withdrawals, batch, pre state)
+constexpr int NUM_CHAINS = 5;
+
 struct Builder {
   bool structure;  // keep linear combinations and emit matrices
-  std::vector<Fr> z;  // full assignment [1, instance.., witness..], Montgomery
+  // full assignment [1, instance.., witness..], Montgomery: an owned vector, or (parallel ASSIGN) a shared array every walker
+  // indexes identically and writes only the pieces it owns
+  std::vector<Fr> zown;
+  Fr* zpar = nullptr;
+  size_t pos = 0;
+  bool write = true;
   uint32_t n_inputs = 1;
   Csr A, B, C;
   uint64_t n_constraints = 0;
-  explicit Builder(bool s) : structure(s) { z.push_back(K.one); }
+  std::vector<CallRec> recs_out;            // STRUCTURE: recorded
+  // parallel ASSIGN walker
+  const std::vector<CallRec>* recs = nullptr;
+  Fr* hash_out = nullptr;                   // output value of every hash call, shared between the two passes
+  size_t call_idx = 0, task_counter = 0;
+  int pass = 0, part = 0, nparts = 1, chain = -2;
 
+  explicit Builder(bool s) : structure(s) { emit(K.one); }
+  Builder(Fr* shared, const std::vector<CallRec>* r, Fr* hout, int pass_, int part_, int nparts_, int chain_)
+      : structure(false), zpar(shared), recs(r), hash_out(hout), pass(pass_), part(part_), nparts(nparts_), chain(chain_) {
+    write = pass == 1 && part == 0;  // the loose witnesses (inputs, balances, keys, counts) are written once
+    emit(K.one);
+  }
+  bool parallel() const { return zpar != nullptr; }
+  void emit(const Fr& v) {
+    if (zpar) {
+      if (write) zpar[pos] = v;
+    } else {
+      zown.push_back(v);
+    }
+    ++pos;
+  }
   uint32_t new_input(const Fr& v) {
-    z.push_back(v);
+    emit(v);
     return n_inputs++;
   }
   uint32_t new_witness(const Fr& v) {
-    z.push_back(v);
-    return (uint32_t)z.size() - 1;
+    emit(v);
+    return (uint32_t)pos - 1;
   }
   void enforce(const LC& a, const LC& b, const LC& c) {
     ++n_constraints;
@@ -613,9 +648,9 @@ struct Gadgets {
         Fr x4 = mont_mul(x2, x2);
         Fr x5 = mont_mul(x4, v[i]);
         if (!c[i]) {
-          b.z.push_back(x2);
-          b.z.push_back(x4);
-          b.z.push_back(x5);
+          b.emit(x2);
+          b.emit(x4);
+          b.emit(x5);
           b.n_constraints += 3;
         }
         v[i] = x5;
@@ -652,7 +687,7 @@ struct Gadgets {
       for (int i = 0; i < T; ++i) st[i] = nw[i];
     }
   }
-  FpVar hash(const std::vector<const FpVar*>& elems) {
+  FpVar hash_impl(const std::vector<const FpVar*>& elems) {
     FpVar st[T] = {constant(K.zero), constant(K.zero), constant(K.zero)};
     size_t start = 0, done = 0;  // DuplexSpongeMode::Absorbing { next_absorb_index: start }
     while (done < elems.size()) {
@@ -666,6 +701,48 @@ struct Gadgets {
     }
     permute(st);  // squeeze from the absorbing mode
     return st[CAPACITY];
+  }
+  // Runs `fn` (a hash or a comparison) as one recorded call.  Sequential modes: just run it (STRUCTURE records its size).
+  // Parallel ASSIGN: pass 1 computes the independent pieces (leaf hashes, comparisons) round-robin over the walkers, pass 2
+  // the fold chains, one walker per chain, reading the leaf outputs of pass 1; a piece another walker owns is stepped over.
+  template <class Fn>
+  FpVar call(int cat, bool is_hash, Fn&& fn) {
+    if (!b.parallel()) {
+      const size_t p0 = b.pos;
+      const uint64_t c0 = b.n_constraints;
+      FpVar out = fn();
+      if (S()) b.recs_out.push_back(CallRec{uint32_t(b.pos - p0), uint32_t(b.n_constraints - c0)});
+      return out;
+    }
+    const size_t idx = b.call_idx++;
+    const CallRec& rec = (*b.recs)[idx];
+    bool compute;
+    if (rec.nwit == 0) compute = true;  // constants only (a hash of a domain separator): free, and its value may be needed
+    else if (b.pass == 1) compute = cat == CAT_LEAF && int(b.task_counter++ % size_t(b.nparts)) == b.part;
+    else compute = cat == b.chain;
+    if (!compute) {
+      b.pos += rec.nwit;
+      b.n_constraints += rec.ncons;
+      // a leaf's value matters to the chain that folds it (pass 2); anything else stepped over is never looked at
+      return FpVar{false, (b.pass == 2 && cat == CAT_LEAF && is_hash) ? b.hash_out[idx] : K.zero, LC()};
+    }
+    const bool saved = b.write;
+    b.write = true;
+    FpVar out = fn();
+    b.write = saved;
+    if (is_hash && rec.nwit) b.hash_out[idx] = out.v;
+    return out;
+  }
+  FpVar hash(const std::vector<const FpVar*>& elems, int cat) {
+    return call(cat, true, [&] { return hash_impl(elems); });
+  }
+  bool cmp_greater_or_equal(const FpVar& self, const FpVar& other) {
+    bool ok = true;
+    call(CAT_LEAF, false, [&] {
+      ok = enforce_greater_or_equal(self, other);
+      return constant(K.zero);
+    });
+    return ok;
   }
 };
 
@@ -715,7 +792,7 @@ static SynthStatus generate_constraints(Gadgets& g, const zkb_l2_public_inputs& 
     FpVar sender_bal = s->second;
     auto r = current.find(tx.recipient);
     FpVar recipient_bal = r == current.end() ? g.constant(K.zero) : r->second;
-    ok &= g.enforce_greater_or_equal(sender_bal, amount);
+    ok &= g.cmp_greater_or_equal(sender_bal, amount);
     FpVar new_sender = g.fsub(sender_bal, amount);
     FpVar new_recipient = g.fadd(recipient_bal, amount);
     current[tx.sender] = new_sender;
@@ -723,50 +800,50 @@ static SynthStatus generate_constraints(Gadgets& g, const zkb_l2_public_inputs& 
   }
 
   FpVar domain_separator = g.constant(ds_accounts());
-  auto fold_accounts = [&](const std::map<Key, FpVar>& accounts) {
-    FpVar state = g.hash({&domain_separator, &batch_id});
+  auto fold_accounts = [&](const std::map<Key, FpVar>& accounts, int chain) {
+    FpVar state = g.hash({&domain_separator, &batch_id}, chain);
     for (const auto& kv : accounts) {
       FpVar pk = g.witness(from_le_bytes_mod_order(kv.first.data(), 32));
-      FpVar leaf = g.hash({&pk, &kv.second});
-      state = g.hash({&state, &leaf});
+      FpVar leaf = g.hash({&pk, &kv.second}, CAT_LEAF);
+      state = g.hash({&state, &leaf}, chain);
     }
     FpVar count = g.witness(from_u64(accounts.size()));
-    return g.hash({&state, &count});
+    return g.hash({&state, &count}, chain);
   };
-  g.enforce_equal(fold_accounts(current), expected_post_state);
+  g.enforce_equal(fold_accounts(current, 0), expected_post_state);
 
-  FpVar shielded_state = g.hash({&pre_shielded_root});
+  FpVar shielded_state = g.hash({&pre_shielded_root}, 1);
   for (const Key& c : w.commitments) {
     FpVar cv = g.witness(from_le_bytes_mod_order(c.data(), 32));
-    shielded_state = g.hash({&shielded_state, &cv});
+    shielded_state = g.hash({&shielded_state, &cv}, 1);
   }
   if (w.commitments.empty()) g.enforce_equal(pre_shielded_root, expected_post_shielded);
   else g.enforce_equal(shielded_state, expected_post_shielded);
 
   FpVar wd_ds = g.constant(ds_withdrawals());
-  FpVar wd_state = g.hash({&wd_ds});
+  FpVar wd_state = g.hash({&wd_ds}, 2);
   for (const auto& wd : w.withdrawals) {
     FpVar recipient = g.witness(from_le_bytes_mod_order(wd.first.data(), 32));
     FpVar amount = g.witness(from_u64(wd.second));
-    FpVar leaf = g.hash({&recipient, &amount});
-    wd_state = g.hash({&wd_state, &leaf});
+    FpVar leaf = g.hash({&recipient, &amount}, CAT_LEAF);
+    wd_state = g.hash({&wd_state, &leaf}, 2);
   }
   FpVar wd_count = g.witness(from_u64(w.withdrawals.size()));
-  g.enforce_equal(g.hash({&wd_state, &wd_count}), expected_withdrawal_root);
+  g.enforce_equal(g.hash({&wd_state, &wd_count}, 2), expected_withdrawal_root);
 
   FpVar batch_ds = g.constant(ds_batch());
-  FpVar batch_state = g.hash({&batch_ds, &batch_id});
+  FpVar batch_state = g.hash({&batch_ds, &batch_id}, 3);
   for (const Witness::Tx& tx : w.txs) {
     FpVar sender = g.witness(from_le_bytes_mod_order(tx.sender.data(), 32));
     FpVar recipient = g.witness(from_le_bytes_mod_order(tx.recipient.data(), 32));
     FpVar amount = g.witness(from_u64(tx.amount));
-    FpVar tx_hash = g.hash({&sender, &recipient, &amount});
-    batch_state = g.hash({&batch_state, &tx_hash});
+    FpVar tx_hash = g.hash({&sender, &recipient, &amount}, CAT_LEAF);
+    batch_state = g.hash({&batch_state, &tx_hash}, 3);
   }
   FpVar tx_count = g.witness(from_u64(w.txs.size()));
-  g.enforce_equal(g.hash({&batch_state, &tx_count}), expected_batch_hash);
+  g.enforce_equal(g.hash({&batch_state, &tx_count}, 3), expected_batch_hash);
 
-  g.enforce_equal(fold_accounts(account_vars), pre_state_root);
+  g.enforce_equal(fold_accounts(account_vars, 4), pre_state_root);
   return ok ? SYNTH_OK : SYNTH_CONTRADICTION;
 }
 
@@ -928,8 +1005,24 @@ struct zkb_l2_circuit {
   l2::Csr a, b, c;
   uint64_t num_constraints = 0, num_witness = 0;
   std::vector<int64_t> shape;
+  std::vector<l2::CallRec> recs;  // sizes of the hashes / comparisons in call order (parallel assignment)
   std::string err;
 };
+
+// assignment threads: ZKB_L2_ASSIGN_THREADS (1..64), default min(8, hardware threads); circuits below PAR_MIN_WITNESS
+// variables (the dummy shape: 0.6 ms on one thread) are not worth a thread start
+static int l2_assign_threads() {
+  static const int n = [] {
+    if (const char* e = getenv("ZKB_L2_ASSIGN_THREADS")) {
+      int v = atoi(e);
+      if (v >= 1 && v <= 64) return v;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    return int(hw == 0 ? 1 : (hw > 8 ? 8 : hw));
+  }();
+  return n;
+}
+constexpr uint64_t PAR_MIN_WITNESS = 40000;
 
 static thread_local std::string g_l2_error;
 const char* zkb_l2_last_error(void) { return g_l2_error.c_str(); }
@@ -957,7 +1050,8 @@ int zkb_l2_circuit_create(const zkb_l2_witness* shape, zkb_l2_circuit** out) {
     c->b.seal();
     c->c.seal();
     c->num_constraints = bld.n_constraints;
-    c->num_witness = bld.z.size() - l2::NUM_INSTANCE;
+    c->num_witness = bld.pos - l2::NUM_INSTANCE;
+    c->recs = std::move(bld.recs_out);
     c->shape = l2::shape_of(w);
     *out = c;
     return ZKB_OK;
@@ -996,16 +1090,60 @@ static int l2_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs
     g_l2_error = "witness shape (account / transfer / commitment / withdrawal pattern) differs from the circuit the key was made for";
     return ZKB_ERR_SHAPE;
   }
+  const size_t total = l2::NUM_INSTANCE + c->num_witness;
+  const int nthreads = l2_assign_threads();
+  if (nthreads > 1 && c->num_witness >= PAR_MIN_WITNESS) {
+    // Two passes over the same statements, every walker stepping over the pieces it does not own (sizes from the structure
+    // pass): 1. leaf hashes and balance comparisons, round-robin over `nthreads` walkers; 2. the five fold chains, one
+    // walker each, reading the leaf outputs.  All walkers index one shared array and write disjoint pieces of it.
+    z->assign(total, l2::K.zero);
+    std::vector<l2::Fr> hash_out(c->recs.size(), l2::K.zero);
+    std::vector<int> bad(size_t(nthreads > l2::NUM_CHAINS ? nthreads : l2::NUM_CHAINS), 0);
+    auto walk = [&](int pass, int part, int nparts, int chain) {
+      l2::Builder bld(z->data(), &c->recs, hash_out.data(), pass, part, nparts, chain);
+      l2::Gadgets g(bld);
+      l2::generate_constraints(g, *inputs, w);
+      if (bld.n_constraints != c->num_constraints || bld.pos != total || bld.call_idx != c->recs.size()) bad[size_t(part)] = 1;
+    };
+    for (int pass = 1; pass <= 2; ++pass) {
+      const int n = pass == 1 ? nthreads : l2::NUM_CHAINS;
+      std::vector<std::thread> th;
+      for (int t = 1; t < n; ++t) th.emplace_back(walk, pass, t, n, pass == 1 ? -2 : t);
+      walk(pass, 0, n, pass == 1 ? -2 : 0);
+      for (auto& t : th) t.join();
+    }
+    for (int x : bad) {
+      if (x) {
+        g_l2_error = "internal: a parallel assignment walker disagrees with the structure pass";
+        return ZKB_ERR_SHAPE;
+      }
+    }
+    return ZKB_OK;
+  }
   l2::Builder bld(false);
-  bld.z.reserve(l2::NUM_INSTANCE + c->num_witness);
+  bld.zown.reserve(total);
   l2::Gadgets g(bld);
   l2::generate_constraints(g, *inputs, w);
-  if (bld.n_constraints != c->num_constraints || bld.z.size() != l2::NUM_INSTANCE + c->num_witness) {
+  if (bld.n_constraints != c->num_constraints || bld.pos != total) {
     g_l2_error = "internal: assignment pass disagrees with the structure pass";
     return ZKB_ERR_SHAPE;
   }
-  *z = std::move(bld.z);
+  *z = std::move(bld.zown);
   return ZKB_OK;
+}
+
+// z (Montgomery) -> canonical little-endian bytes, split over the assignment threads when it is long
+static void l2_z_to_bytes(const std::vector<l2::Fr>& z, uint8_t* out) {
+  const int nthreads = l2_assign_threads();
+  auto conv = [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) l2::to_le_bytes(z[i], out + 32 * i);
+  };
+  if (nthreads <= 1 || z.size() < PAR_MIN_WITNESS) return conv(0, z.size());
+  std::vector<std::thread> th;
+  const size_t step = (z.size() + size_t(nthreads) - 1) / size_t(nthreads);
+  for (int t = 1; t < nthreads; ++t) th.emplace_back(conv, std::min(z.size(), step * size_t(t)), std::min(z.size(), step * size_t(t + 1)));
+  conv(0, std::min(z.size(), step));
+  for (auto& t : th) t.join();
 }
 
 int zkb_l2_circuit_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witness,
@@ -1015,7 +1153,7 @@ int zkb_l2_circuit_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* i
     std::vector<l2::Fr> z;
     int rc = l2_assign(c, inputs, witness, &z);
     if (rc != ZKB_OK) return rc;
-    for (size_t i = 0; i < z.size(); ++i) l2::to_le_bytes(z[i], z_out + 32 * i);
+    l2_z_to_bytes(z, z_out);
     return ZKB_OK;
   } catch (const std::bad_alloc&) {
     g_l2_error = "out of host memory";
@@ -1121,7 +1259,7 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
     int rc = l2_assign(c, inputs, witness, &z);
     if (rc != ZKB_OK) return rc;
     std::vector<uint8_t> zb(z.size() * 32);
-    for (size_t i = 0; i < z.size(); ++i) l2::to_le_bytes(z[i], &zb[32 * i]);
+    l2_z_to_bytes(z, zb.data());
     uint8_t r[32], s[32];
     zkb_l2_prover_randomness(inputs->batch_id, r, s);
     uint8_t a[64], b[128], cc[64];
@@ -1164,7 +1302,6 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
 // A zkb_l2_batch owns `lanes` contexts on one device (each with its streams, scratch and captured prove graph) and as many host
 // threads; proof i goes to lane i mod lanes: the thread assigns the witness (host) and proves (GPU), so the assignment of one
 // proof overlaps the device work of the others.  Key, matrices and circuit are shared, read-only.
-#include <thread>
 
 struct zkb_l2_batch {
   int device = 0;
