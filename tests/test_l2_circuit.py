@@ -259,3 +259,18 @@ def test_parallel_assignment_equals_the_oracle_and_the_sequential_pass():
         assert outs["1"] == zb and outs["5"] == zb
     finally:
         os.unlink(f.name)
+
+
+def test_batch_prover_without_a_gpu_is_an_error_not_a_fallback():
+    import torch
+    import zelana_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = zelana_b200.load_library()
+    h = C.c_void_p()
+    assert lib.zkb_l2_batch_create(0, 4, C.byref(h)) == -1          # ZKB_ERR_NO_DEVICE from zkb_ctx_create
+    assert not h.value
+    assert lib.zkb_l2_batch_create(0, 0, C.byref(h)) == -3          # lanes outside 1..64
+    assert lib.zkb_l2_batch_lanes(None) == 0
+    out = (C.c_uint8 * 256)()
+    assert lib.zkb_l2_prove(None, None, None, None, None, None, out) == -3
