@@ -16,7 +16,10 @@ PoseidonGrainLFSR / find_poseidon_ark_and_mds -- so that variable numbering, con
 combination come out the way `cs.finalize(); cs.to_matrices()` yields them under OptimizationGoal::Constraints (what
 ark-groth16 0.5.0 sets for both setup and prove).
 
-PARITY UNPINNED for this file: the reference holds no fixture for this circuit (prover/l2_vk.json has 3 IC points, i.e. it
+PINNED in part: the Poseidon parameter generator (Grain LFSR, rejection / mod-p sampling, Cauchy MDS) reproduces the known-answer
+tests ark-crypto-primitives 0.5.0 ships for it (`test_grain_lfsr_consistency`, `bls12_381_fr_poseidon_default_parameters_test`,
+stated over BLS12-381's Fr; tests/test_l2_circuit.py::test_poseidon_generator_reproduces_arkworks_known_answers).
+PARITY UNPINNED for the rest (the R1CS gadgets): the reference holds no fixture for this circuit (prover/l2_vk.json has 3 IC points, i.e. it
 belongs to a deleted 2-input circuit; l2_circuit.rs:512-541 only asserts 8 instance variables) and the reference cannot
 be compiled here.  What IS checked (tests/test_l2_circuit.py): 8 instance variables as the reference's own test asserts,
 the system is satisfied exactly when the roots are the Poseidon values main.rs.bak computes, the gadget sponge agrees with
@@ -409,16 +412,16 @@ class GrainLFSR:
             v = (v << 1) | int(b)
         return v
 
-    def get_field_elements_rejection_sampling(self, n):
+    def get_field_elements_rejection_sampling(self, n, modulus=R):
         out = []
         while len(out) < n:
             v = self._int_msb_first()
-            if v < R:
+            if v < modulus:
                 out.append(v)
         return out
 
-    def get_field_elements_mod_p(self, n):
-        return [self._int_msb_first() % R for _ in range(n)]
+    def get_field_elements_mod_p(self, n, modulus=R):
+        return [self._int_msb_first() % modulus for _ in range(n)]
 
 
 class PoseidonConfig:
@@ -427,14 +430,16 @@ class PoseidonConfig:
         self.mds, self.ark, self.rate, self.capacity = mds, ark, rate, capacity
 
 
-def find_poseidon_ark_and_mds(prime_bits, rate, full_rounds, partial_rounds, skip_matrices):
+def find_poseidon_ark_and_mds(prime_bits, rate, full_rounds, partial_rounds, skip_matrices, modulus=R):
+    """sponge/poseidon/mod.rs find_poseidon_ark_and_mds.  `modulus` other than BN254's r only for the arkworks known-answer
+    tests, which are stated over BLS12-381's scalar field (tests/test_l2_circuit.py)."""
     lfsr = GrainLFSR(False, prime_bits, rate + 1, full_rounds, partial_rounds)
-    ark = [lfsr.get_field_elements_rejection_sampling(rate + 1) for _ in range(full_rounds + partial_rounds)]
+    ark = [lfsr.get_field_elements_rejection_sampling(rate + 1, modulus) for _ in range(full_rounds + partial_rounds)]
     for _ in range(skip_matrices):
-        lfsr.get_field_elements_mod_p(2 * (rate + 1))
-    xs = lfsr.get_field_elements_mod_p(rate + 1)
-    ys = lfsr.get_field_elements_mod_p(rate + 1)
-    mds = [[pow((xs[i] + ys[j]) % R, -1, R) for j in range(rate + 1)] for i in range(rate + 1)]
+        lfsr.get_field_elements_mod_p(2 * (rate + 1), modulus)
+    xs = lfsr.get_field_elements_mod_p(rate + 1, modulus)
+    ys = lfsr.get_field_elements_mod_p(rate + 1, modulus)
+    mds = [[pow((xs[i] + ys[j]) % modulus, -1, modulus) for j in range(rate + 1)] for i in range(rate + 1)]
     return ark, mds
 
 

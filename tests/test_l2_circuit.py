@@ -274,3 +274,26 @@ def test_batch_prover_without_a_gpu_is_an_error_not_a_fallback():
     assert lib.zkb_l2_batch_lanes(None) == 0
     out = (C.c_uint8 * 256)()
     assert lib.zkb_l2_prove(None, None, None, None, None, None, out) == -3
+
+
+def test_poseidon_generator_reproduces_arkworks_known_answers():
+    """The only golden vectors that exist for this stack: ark-crypto-primitives 0.5.0's own tests of the parameter generator
+    `get_poseidon_config()` calls (Cargo.lock pins the crate; it is not vendored).  They are stated over BLS12-381's scalar
+    field: src/sponge/poseidon/grain_lfsr.rs `test_grain_lfsr_consistency` (PoseidonGrainLFSR::new(false, 255, 3, 8, 31): two
+    rejection-sampled, then two mod-p elements) and src/sponge/poseidon/traits.rs
+    `bls12_381_fr_poseidon_default_parameters_test` (rate 2 optimised-for-constraints entry = (alpha 17, R_F 8, R_P 31,
+    skip 0): ark[0][0] and mds[0][0])."""
+    q = 52435875175126190479447740508185965837690552500527637822603658699938581184513      # BLS12-381 Fr
+    g = O.GrainLFSR(False, 255, 3, 8, 31)
+    assert g.get_field_elements_rejection_sampling(1, q) == [
+        27117311055620256798560880810000042840428971800021819916023577129547249660720]
+    assert g.get_field_elements_rejection_sampling(1, q) == [
+        51641662388546346858987925410984003801092143452466182801674685248597955169158]
+    assert g.get_field_elements_mod_p(1, q) == [
+        30468495022634911716522728179277518871747767531215914044579216845399211650580]
+    assert g.get_field_elements_mod_p(1, q) == [
+        17250718238509906485015112994867732544602358855445377986727968022920517907825]
+    ark, mds = O.find_poseidon_ark_and_mds(255, 2, 8, 31, 0, modulus=q)
+    assert ark[0][0] == 27117311055620256798560880810000042840428971800021819916023577129547249660720
+    assert mds[0][0] == 26017457457808754696901916760153646963713419596921330311675236858336250747575
+    assert len(ark) == 39 and all(len(r) == 3 for r in ark)
