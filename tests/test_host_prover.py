@@ -55,7 +55,7 @@ def test_vk_hash_is_blake3_of_the_compressed_vk():
     assert p.verify(zp.BatchProof(inputs, bytes(256), 0)) is True
     assert p.verify(zp.BatchProof(inputs, bytes(255), 0)) is False
     assert p.verify(zp.BatchProof(inputs, bytes(388 + 236), 0)) is False
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):            # neither an L2BlockCircuit nor a custom synthesizer
         p.prove(inputs, witness=None)
 
 
@@ -161,3 +161,33 @@ def test_gpu_keygen_mimc_matches_oracle_and_proofs_verify():
                       g1_generator=bn.g1_to_raw(bn.G1_GEN), g2_generator=bn.g2_to_raw(bn.G2_GEN))
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_groth16_prover_proves_the_l2_circuit_natively():
+    """`Groth16Prover::from_bytes(pk, vk)` + `prove(inputs, witness)` with the witness as the reference's L2BlockCircuit struct:
+    constraints come from the library's native synthesiser, the proof verifies under the key's VK and equals L2Prover's."""
+    import zelana_b200
+    from zelana_b200 import l2_circuit as l2
+    ctx = zelana_b200.Context(0)
+    try:
+        circ, pk_bytes, vk_bytes, _raw = l2.keygen(ctx)
+        circ.free()
+    finally:
+        ctx.close()
+    p = zp.Groth16Prover.from_bytes(pk_bytes, vk_bytes, device=0)
+    try:
+        w = l2.L2BlockCircuit.dummy()
+        w.batch_id = 11
+        inputs = l2.satisfying_inputs(w)
+        proof = p.prove(inputs, w)
+        assert p.verify(proof) and len(proof.proof_bytes) == 256
+        again = p.prove(inputs, w)                         # cached circuit, CUDA graph from here on
+        assert again.proof_bytes == proof.proof_bytes      # StdRng(batch_id): deterministic
+        vk = g16.VerifyingKey.deserialize_compressed(vk_bytes)
+        pb = proof.proof_bytes
+        pr = g16.Proof(bn.G1.neg(bn.g1_from_raw(pb[:64])), bn.g2_from_raw(pb[64:192]), bn.g1_from_raw(pb[192:]))
+        z = l2.L2Circuit(w).assign(w.with_inputs(inputs))
+        assert g16.verify(vk, [int.from_bytes(z[32 * i:32 * i + 32], "little") for i in range(1, 8)], pr)
+    finally:
+        p.close()

@@ -8,9 +8,10 @@ Mirrors core/src/sequencer/settlement/prover.rs (same names, argument meaning an
 All group / field / NTT arithmetic runs in libzkb200.so on the GPU; this file only does what the reference's own Rust does
 on the host around the arkworks call: seed the RNG, draw (r, s), format bytes, hash the verifying key.
 
-Constraint synthesis (`prover::L2BlockCircuit::generate_constraints`, prover/src/l2_circuit.rs:179-505) is host work that
-stays in the reference's Rust in a real integration.  Here it is pluggable: pass `synthesizer`, a callable
-`(inputs, witness) -> (num_instance, num_witness, A, B, C, full_assignment_bytes)`; `prove` raises without one.
+Constraint synthesis (`prover::L2BlockCircuit::generate_constraints`, prover/src/l2_circuit.rs:179-505) is host work.  `prove`
+takes the witness as a `zelana_b200.l2_circuit.L2BlockCircuit` (the struct prover.rs:395-405 builds from BatchWitness) and
+synthesises it with the library's native L2 synthesiser (zkb_l2_*).  Other circuits: pass `synthesizer`, a callable
+`(inputs, witness) -> (num_instance, num_witness, A, B, C, full_assignment_bytes)`.
 """
 import struct
 import time
@@ -195,12 +196,21 @@ class Groth16Prover:
         return BatchProof(inputs, proof_bytes, int((time.perf_counter() - start) * 1000))
 
     def prove(self, inputs: BatchPublicInputs, witness) -> BatchProof:
-        if self.synthesizer is None:
-            raise NotImplementedError(
-                "Groth16Prover.prove needs a constraint synthesizer (the reference's L2BlockCircuit::generate_constraints is "
-                "host-side Rust; use prove_assignment with its matrices and assignment, or pass synthesizer=...)")
-        ni, nw, a, b, c, z = self.synthesizer(inputs, witness)
-        return self.prove_assignment(inputs, self.circuit(ni, nw, a, b, c), z)
+        """prover.rs:350-425.  `witness`: an L2BlockCircuit carrying the private fields (its own public fields are replaced
+        by `inputs`), or whatever the custom `synthesizer` understands."""
+        if self.synthesizer is not None:
+            ni, nw, a, b, c, z = self.synthesizer(inputs, witness)
+            return self.prove_assignment(inputs, self.circuit(ni, nw, a, b, c), z)
+        from .l2_circuit import L2BlockCircuit, L2Prover
+        if not isinstance(witness, L2BlockCircuit):
+            raise TypeError("Groth16Prover.prove: witness must be an L2BlockCircuit (or pass synthesizer=...)")
+        l2 = self._shapes.get("l2")
+        if l2 is None:
+            from .l2_circuit import L2Circuit
+            # the shape the key was generated for: L2BlockCircuit::dummy() in the reference (keygen.rs:84); a key made for
+            # another shape is served by passing a witness of that shape first
+            l2 = self._shapes["l2"] = L2Prover(self.ctx, L2Circuit(witness), self.pk, self.vk_bytes)
+        return l2.prove(inputs, witness)
 
     def verify(self, proof: BatchProof) -> bool:
         """prover.rs:427-442: the reference only checks that the proof is well-formed (exactly 256 bytes)."""
@@ -210,6 +220,6 @@ class Groth16Prover:
         if self.ctx is not None:
             self.pk.free()
             for m in self._shapes.values():
-                m.free()
+                m.close() if hasattr(m, "close") else m.free()
             self.ctx.close()
             self.ctx = None
