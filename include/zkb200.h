@@ -248,7 +248,8 @@ typedef struct {              /* L2BlockCircuit's private witness, l2_circuit.rs
   size_t n_withdrawals;
 } zkb_l2_witness;
 
-typedef struct zkb_l2_circuit zkb_l2_circuit; /* host: constraint matrices of ONE circuit shape (what a key is made for) */
+typedef struct zkb_l2_circuit zkb_l2_circuit; /* host: constraint matrices of ONE circuit shape (what a key is made for);
+                                                 immutable once created: any number of threads may share one */
 
 const char* zkb_l2_last_error(void);
 /* Structure pass = `generate_constraints` under SynthesisMode::Setup + `cs.finalize(); cs.to_matrices()`
