@@ -297,3 +297,35 @@ def test_poseidon_generator_reproduces_arkworks_known_answers():
     assert ark[0][0] == 27117311055620256798560880810000042840428971800021819916023577129547249660720
     assert mds[0][0] == 26017457457808754696901916760153646963713419596921330311675236858336250747575
     assert len(ark) == 39 and all(len(r) == 3 for r in ark)
+
+
+def test_dummy_circuit_matches_the_committed_golden_digest():
+    """tests/golden/l2_dummy_circuit.json (made by tests/golden/make_l2_golden.py) freezes the oracle's dummy circuit: counts,
+    roots, SHA-256 of the matrices and of the assignment -- and the native synthesiser must hash to the same values."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+    import struct
+    from conftest import GOLDEN
+    from zelana_b200 import l2_circuit as P
+    spec = importlib.util.spec_from_file_location("make_l2_golden", os.path.join(GOLDEN, "make_l2_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    want = json.load(open(os.path.join(GOLDEN, "l2_dummy_circuit.json")))
+    assert mk.build() == want
+    pc = P.L2BlockCircuit.dummy()
+    pc = pc.with_inputs(P.satisfying_inputs(pc))
+    circ = P.L2Circuit(pc)
+    h = hashlib.sha256()
+    for rp, col, co in circ.matrices():
+        data = co.tobytes()
+        for i in range(len(rp) - 1):
+            lo, hi = int(rp[i]), int(rp[i + 1])
+            h.update(struct.pack("<I", hi - lo))
+            for k in range(lo, hi):                      # the native rows are already sorted by column
+                h.update(struct.pack("<I", int(col[k])) + data[32 * k:32 * k + 32])
+    assert h.hexdigest() == want["matrices_sha256"]
+    z = circ.assign(pc)
+    assert hashlib.sha256(z).hexdigest() == want["assignment_sha256"]
+    assert [z[32 * i:32 * i + 32].hex() for i in range(1, 8)] == want["public_inputs_le_hex"]
