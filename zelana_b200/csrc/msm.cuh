@@ -341,10 +341,10 @@ __device__ __forceinline__ XYZZ<F> block_sum(XYZZ<F> acc, XYZZ<F>* sh) {
 // sum_s s T[s] with s = hi * C + lo (C = 2^MSM_COL_LOG columns) = C * sum_hi hi * Row[hi] + sum_lo lo * Col[lo].
 // blocks [0, rows): Row[hi] = sum_lo T[hi C + lo]; blocks [rows, 2 rows): WRow[hi] = sum_lo W[hi C + lo];
 // blocks [2 rows, 2 rows + C): Col[lo] = sum_hi T[hi C + lo].   out = Row[rows] | WRow[rows] | Col[C]
-// With few rows (MSMs up to ~2^13 points: rows <= MSM_COL_SEQ) a column is summed by ONE thread, THREADS columns per block, instead of a
+// With few rows (MSMs of a few thousand points: rows <= MSM_COL_SEQ) a column is summed by ONE thread, THREADS columns per block, instead of a
 // block per column tree-summing mostly empty slots: same depth, 1/64 of the resident blocks (small proofs run many at a time
 // and are bound by block slots, not by arithmetic).
-constexpr size_t MSM_COL_SEQ = 32;
+constexpr size_t MSM_COL_SEQ = 16;  // 32 rows (the H MSM of a 2^13 domain) measured slower this way: 218 us vs 77 us for the tree
 template <int THREADS>
 inline unsigned msm_rowcol_blocks(size_t rows) {
   constexpr size_t C = size_t(1) << MSM_COL_LOG;
