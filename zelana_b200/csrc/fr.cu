@@ -67,19 +67,49 @@ __global__ void to_mont_kernel(const Fr* in, Fr* out, size_t n, int* bad) {
   out[i] = x.to_mont();
 }
 
-// out[i] = <row_i, z> for i < nc ; optionally out[nc + j] = z[j] for j < ni ; zero up to n
+// out[i] = <row_i, z> for i < nc ; optionally out[nc + j] = z[j] for j < ni ; zero up to n.
+// One thread per row; a row of CSR_LONG_ROW terms or more (the 254-term bit-packing rows of ark-r1cs-std's comparison
+// gadget, the ~60-term rows of Poseidon's partial rounds) is handed to the whole warp afterwards: 32 lanes stride over it
+// and tree-add by shuffles, so that one long row does not hold its 31 neighbours for 254 dependent products.
+constexpr uint64_t CSR_LONG_ROW = 48;
+__device__ __forceinline__ Fr shfl_down_fr(const Fr& v, int d) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, v.v[i], d);
+  return r;
+}
 __global__ void csr_matvec_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
                                   const Fr* __restrict__ coeff, const Fr* __restrict__ z, uint64_t nc, uint64_t ni,
                                   int append_instance, size_t n, Fr* __restrict__ out) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int lane = threadIdx.x & 31;
   Fr acc = Fr::zero();
+  uint64_t lo = 0, hi = 0;
+  bool is_long = false;
   if (i < nc) {
-    for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) acc = acc + coeff[k] * z[col[k]];
+    lo = row_ptr[i];
+    hi = row_ptr[i + 1];
+    is_long = hi - lo >= CSR_LONG_ROW;
+    if (!is_long)
+      for (uint64_t k = lo; k < hi; k++) acc = acc + coeff[k] * z[col[k]];
   } else if (append_instance && i < nc + ni) {
     acc = z[i - nc];
   }
-  out[i] = acc;
+  unsigned pending = __ballot_sync(0xffffffffu, is_long);   // blockDim is a multiple of 32: whole warps take part
+  while (pending) {
+    const int src = __ffs(pending) - 1;
+    pending &= pending - 1;
+    const uint64_t rlo = __shfl_sync(0xffffffffu, lo, src), rhi = __shfl_sync(0xffffffffu, hi, src);
+    Fr part = Fr::zero();
+    for (uint64_t k = rlo + lane; k < rhi; k += 32) part = part + coeff[k] * z[col[k]];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part = part + shfl_down_fr(part, d);  // lane 0 ends with the row sum
+    Fr total;
+#pragma unroll
+    for (int w = 0; w < 8; w++) total.v[w] = __shfl_sync(0xffffffffu, part.v[w], 0);
+    if (lane == src) acc = total;
+  }
+  if (i < n) out[i] = acc;
 }
 
 // zinv = (g^n - 1)^-1, g = 5: the inverse of the vanishing polynomial on the coset (one thread, once per domain size)
