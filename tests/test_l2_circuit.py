@@ -329,3 +329,22 @@ def test_dummy_circuit_matches_the_committed_golden_digest():
     z = circ.assign(pc)
     assert hashlib.sha256(z).hexdigest() == want["assignment_sha256"]
     assert [z[32 * i:32 * i + 32].hex() for i in range(1, 8)] == want["public_inputs_le_hex"]
+
+
+def test_roots_edge_cases_zero_amounts_u64_limits_and_refusals():
+    from zelana_b200 import ZkbError, l2_circuit as P
+    top = 2 ** 64 - 1
+    ok = P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(1), _k(2), 0), P.TransactionWitness(_k(1), _k(2), top)],
+                          initial_accounts={_k(1): top, _k(2): 0}, batch_id=top)
+    ok = ok.with_inputs(P.satisfying_inputs(ok))
+    circ = P.L2Circuit(ok)
+    assert circ.is_satisfied(circ.assign(ok)) == (True, None)
+    oc = O.with_satisfying_roots(O.L2BlockCircuit(transactions=[(_k(1), _k(2), 0), (_k(1), _k(2), top)],
+                                                  initial_accounts={_k(1): top, _k(2): 0}, batch_id=top))
+    assert (ok.pre_state_root, ok.post_state_root, ok.batch_hash) == (oc.pre_state_root, oc.post_state_root, oc.batch_hash)
+    for bad in (P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(1), _k(2), 6)], initial_accounts={_k(1): 5, _k(2): 0}),
+                P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(3), _k(2), 1)], initial_accounts={_k(1): 5, _k(2): 0}),
+                P.L2BlockCircuit(transactions=[P.TransactionWitness(_k(1), _k(2), 2)], initial_accounts={_k(1): 5, _k(2): top})):
+        with pytest.raises(ZkbError) as e:              # overspend / unknown sender / recipient beyond 64 bits
+            P.satisfying_inputs(bad)
+        assert e.value.code == -3

@@ -1199,6 +1199,10 @@ int zkb_l2_roots(const zkb_l2_witness* witness, uint64_t batch_id, const uint8_t
       // oneself ends with balance + amount (reference quirk, preserved)
       auto r = after.find(tx.recipient);
       uint64_t sender_bal = s->second, recipient_bal = r == after.end() ? 0 : r->second;
+      if (recipient_bal + tx.amount < recipient_bal) {  // the circuit adds in the field; a u64 that wraps cannot match it
+        g_l2_error = "a recipient balance exceeds 64 bits";
+        return ZKB_ERR_INVALID_ARG;
+      }
       after[tx.sender] = sender_bal - tx.amount;
       after[tx.recipient] = recipient_bal + tx.amount;
     }
