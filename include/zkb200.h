@@ -52,6 +52,10 @@ int zkb_ctx_set_stream(zkb_ctx* ctx, void* cuda_stream);
 int zkb_ctx_synchronize(zkb_ctx* ctx);
 void zkb_ctx_destroy(zkb_ctx* ctx);
 const char* zkb_last_error(zkb_ctx* ctx);
+/* page-locked host memory: assignments handed to zkb_prove_batch_begin from such a buffer are fetched by the GPU without a
+ * staging copy, overlapped with compute (any host memory works; pageable memory is copied synchronously) */
+int zkb_host_alloc_pinned(size_t bytes, void** out);
+void zkb_host_free_pinned(void* p);
 /* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
 unsigned long long zkb_launch_count(zkb_ctx* ctx);
 /* A prove's device part (~140 launches on five streams for the L2 circuit) is captured as a CUDA graph the second time a
@@ -90,13 +94,18 @@ int zkb_scalar_mul(zkb_ctx* ctx, int group, const uint8_t* points, const uint8_t
 /* out = sum_i points[i] (plain point sum, exercises add/double/inverse edge cases); host memory. */
 int zkb_point_sum(zkb_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out);
 
-/* ---- bases (proving-key query vectors resident in HBM) --------------------------------------- */
+/* ---- bases (proving-key query vectors resident in HBM) ---------------------------------------
+ * validate != 0 means what arkworks' Validate::Yes means, on every loading path (raw affine or compressed): coordinates
+ * canonical, point on the curve and -- G2 only, G1 has cofactor 1 -- in the prime-order subgroup. */
 int zkb_g1_bases_load(zkb_ctx* ctx, const uint8_t* affine_host, size_t n, int validate, zkb_g1_bases** out);
 int zkb_g2_bases_load(zkb_ctx* ctx, const uint8_t* affine_host, size_t n, int validate, zkb_g2_bases** out);
 /* bases[i] = k_i * G (G = (1,2)), k_i = 32 B canonical LE Fr scalars in DEVICE memory: synthetic keys with
  * known discrete logs, generated on the GPU. */
 int zkb_g1_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, zkb_g1_bases** out);
 int zkb_g2_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, zkb_g2_bases** out);
+/* window width c and window count of the handle's resident tables: nwin x len points (64 / 128 B each) live in HBM */
+int zkb_g1_bases_window(const zkb_g1_bases* b, int* c, int* nwin);
+int zkb_g2_bases_window(const zkb_g2_bases* b, int* c, int* nwin);
 size_t zkb_g1_bases_len(const zkb_g1_bases* b);
 size_t zkb_g2_bases_len(const zkb_g2_bases* b);
 /* copy bases [offset, offset+n) back as canonical affine bytes (host) */
@@ -120,6 +129,11 @@ int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_g2_bases* bases, size_t offset, const
 /* Multi-GPU combine: k partial sums (gathered from k ranks, device memory) -> canonical affine (device). */
 int zkb_msm_g1_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
 int zkb_msm_g2_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
+/* Parity hook for the batched MSM behind zkb_prove_batch: `batch` scalar vectors (vector p at scalars_dev + p * stride * 32 B)
+ * against the same bases [offset, offset + n) -> batch canonical affine points in device memory.  group: 1 = G1, 2 = G2
+ * (bases: the matching handle type). */
+int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
+                        int batch, void* out_affine_dev);
 #define ZKB_G1_PARTIAL_BYTES 128
 #define ZKB_G2_PARTIAL_BYTES 256
 
@@ -148,7 +162,11 @@ int zkb_r1cs_load(zkb_ctx* ctx, const zkb_r1cs_desc* desc, zkb_r1cs** out);
 void zkb_r1cs_free(zkb_r1cs* m);
 /* log2 of the QAP domain: next_pow2(num_constraints + num_instance) */
 int zkb_r1cs_log_domain(const zkb_r1cs* m);
-/* z = full assignment [1, instance.., witness..], (num_instance + num_witness) x 32 B canonical, host.
+/* num_instance + num_witness: the length (in 32-byte elements) every z_host passed with these matrices must have */
+uint64_t zkb_r1cs_num_variables(const zkb_r1cs* m);
+uint64_t zkb_r1cs_num_constraints(const zkb_r1cs* m);
+/* z = full assignment [1, instance.., witness..], zkb_r1cs_num_variables(m) x 32 B canonical, host (the callee cannot check
+ * the length of a bare pointer: size the buffer from that accessor).
  * h_out: domain_size x 32 B canonical coefficients of h(X), host. */
 int zkb_witness_map(zkb_ctx* ctx, const zkb_r1cs* m, const uint8_t* z_host, uint8_t* h_out_host);
 
@@ -183,6 +201,18 @@ int zkb_pk_synthetic(zkb_ctx* ctx, size_t num_vars, size_t num_witness, size_t h
  * (StdRng::seed_from_u64(batch_id) -> Fr::rand twice, prover.rs:354).  z_host as in zkb_witness_map. */
 int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
               const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
+
+/* ---- a batch of proofs of ONE circuit with ONE key (BASELINE.json config 5; the forge coordinator's chunk-per-worker
+ * dispatch, forge/crates/prover-coordinator/src/dispatcher.rs:290-330, as one set of kernels): K x
+ * create_proof_with_reduction_and_matrices.  z_host: K assignments back to back, K x zkb_r1cs_num_variables(m) x 32 B;
+ * rs_host: K x (r || s), 64 B each; out: K x 256 B, proof i = A (64) | B (128) | C (64) canonical affine, A not negated
+ * (byte-identical to K calls of zkb_prove).  1 <= K <= 4096.  _begin queues the work and returns; the host buffers must stay
+ * valid until _end, which waits and copies the results out.  One batch in flight per context. */
+int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
+                          size_t k);
+int zkb_prove_batch_end(zkb_ctx* ctx, size_t k, uint8_t* out);
+int zkb_prove_batch(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host, size_t k,
+                    uint8_t* out);
 
 /* ---- trusted setup: ark-groth16 generate_parameters_with_qap (Groth16::circuit_specific_setup, keygen.rs:87-91) -------- */
 typedef struct {
@@ -284,8 +314,9 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
 
 /* ---- batches of independent L2 proofs on one GPU (BASELINE.json config 5; the forge coordinator's chunk-per-worker
  * parallelism, forge/crates/prover-coordinator/src/dispatcher.rs:290-330, inside one process) ------------------------------
- * A small proof is a chain of short kernels; a B200 holds 16-32 of them at once.  A zkb_l2_batch owns `lanes` contexts on one
- * device and as many host threads; proof i is assigned (host) and proved (GPU) on lane i mod lanes.  pk, m and c are shared.
+ * A zkb_l2_batch owns a pool of `lanes` host threads and two device contexts.  A batch is cut into sub-batches (<= 128 proofs,
+ * env ZKB_L2_SUBBATCH): the pool assigns a sub-batch's witnesses into pinned memory, zkb_prove_batch_begin proves it with one
+ * set of batched kernels, and the next sub-batch is assigned meanwhile.  pk, m and c are shared, read-only.
  * proofs_out: n x 256 B.  status_out (may be NULL): per-proof zkb_status.  Returns the first error, ZKB_OK if all succeeded;
  * a failed proof does not invalidate the others. */
 typedef struct zkb_l2_batch zkb_l2_batch;

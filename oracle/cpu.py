@@ -44,6 +44,8 @@ def lib():
         L.orc_g1_bases_free.argtypes = [_P]
         L.orc_msm_g1_pre.argtypes = [_P, _SZ, _P, _SZ, _I, _P]
         L.orc_ntt.argtypes = [_P, _I, _I, _I, _I]
+        L.orc_poly_eval.argtypes = [_P, _SZ, _P, _SZ, _I, _P]
+        L.orc_root_of_unity.argtypes = [_I, _P]
         L.orc_witness_map.restype = _I
         L.orc_witness_map.argtypes = [_U64, _U64, _U64] + [_P] * 9 + [_P, _P, _I]
         L.orc_pk_new.restype = _P
@@ -146,6 +148,22 @@ def ntt(data, log_n, inverse=False, coset=False, threads=0):
     assert len(a) == 32 << log_n
     lib().orc_ntt(_ptr(a), log_n, int(inverse), int(coset), threads or max_threads())
     return a.tobytes()
+
+
+def poly_eval(coeffs, points, threads=0):
+    """[P(x) for x in points], P given by n x 32 B canonical coefficients; by definition (blocked Horner), no FFT."""
+    cf = _np(coeffs)
+    pts = b"".join(int(x).to_bytes(32, "little") for x in points)
+    P = _np(pts)
+    out = np.empty(32 * len(points), dtype=np.uint8)
+    lib().orc_poly_eval(_ptr(cf), len(cf) // 32, _ptr(P), len(points), threads or max_threads(), _ptr(out))
+    return [int.from_bytes(out[32 * i:32 * i + 32].tobytes(), "little") for i in range(len(points))]
+
+
+def root_of_unity(log_n):
+    out = np.empty(32, dtype=np.uint8)
+    lib().orc_root_of_unity(log_n, _ptr(out))
+    return int.from_bytes(out.tobytes(), "little")
 
 
 def csr_arrays(rows):

@@ -640,6 +640,31 @@ void orc_ntt(uint8_t* data, int logn, int inverse, int coset, int threads) {
   for (size_t i = 0; i < n; i++) a[i].to_canonical(data + 32 * i);
 }
 
+// P(x) = sum_j coeffs[j] x^j at each of `npts` points, straight from the definition (blocked Horner, no FFT code shared):
+// the checker of sampled NTT outputs at sizes where a full CPU transform is too slow (tests/test_gpu_parity_scale.py).
+// ark-poly semantics being checked: fft(a)[k] = P_a(g w^k), ifft(y)[j] = g^-j n^-1 P_y(w^-j)  (g = 1 without a coset).
+void orc_poly_eval(const uint8_t* coeffs, size_t n, const uint8_t* points, size_t npts, int threads, uint8_t* out) {
+  const size_t blk = size_t(1) << 14;
+  const size_t nb = (n + blk - 1) / blk;
+  for (size_t p = 0; p < npts; p++) {
+    Fr x = Fr::from_canonical(points + 32 * p);
+    std::vector<Fr> part(nb);
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (size_t b = 0; b < nb; b++) {
+      size_t s = b * blk, e = s + blk < n ? s + blk : n;
+      Fr acc = Fr::zero();
+      for (size_t j = e; j-- > s;) acc = acc * x + Fr::from_canonical(coeffs + 32 * j);
+      part[b] = acc;
+    }
+    Fr xb = fr_pow_u64(x, blk), acc = Fr::zero();
+    for (size_t b = nb; b-- > 0;) acc = acc * xb + part[b];
+    acc.to_canonical(out + 32 * p);
+  }
+}
+
+// w_n = 5^((r-1)/n), the generator ark-poly's Radix2EvaluationDomain::new(n) uses; canonical bytes
+void orc_root_of_unity(int logn, uint8_t out[32]) { fr_root_of_unity(logn).to_canonical(out); }
+
 int orc_witness_map(uint64_t nc, uint64_t ni, uint64_t nw, const u64* a_rp, const uint32_t* a_col, const uint8_t* a_co,
                     const u64* b_rp, const uint32_t* b_col, const uint8_t* b_co, const u64* c_rp, const uint32_t* c_col,
                     const uint8_t* c_co, const uint8_t* z, uint8_t* h_out, int threads) {

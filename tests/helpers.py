@@ -1,6 +1,8 @@
 """Shared test fixtures: synthetic circuits, known-dlog bases, byte packing."""
 import random
 
+import numpy as np
+
 from oracle import bn254 as bn
 from oracle import groth16 as g16
 
@@ -83,3 +85,24 @@ def pk_parts(pk):
         delta_g1=bn.g1_to_raw(pk.delta_g1), delta_g2=bn.g2_to_raw(pk.vk.delta_g2),
         a_query=g1_raw(pk.a_query), b_g1_query=g1_raw(pk.b_g1_query), b_g2_query=g2_raw(pk.b_g2_query),
         h_query=g1_raw(pk.h_query), l_query=g1_raw(pk.l_query))
+
+
+def dot_mod_r(k, s):
+    """sum_i k_i * s_i mod r for two [n, 8] u32 little-endian limb arrays, exactly: 16-bit limbs, float64 BLAS products over
+    blocks of 2^18 rows (every partial sum < 2^50 is an exact double), recombined with Python integers."""
+    n = k.shape[0]
+    acc = [[0] * 16 for _ in range(16)]
+    blk = 1 << 18
+    for lo in range(0, n, blk):
+        a = np.ascontiguousarray(k[lo:lo + blk]).view(np.uint16).astype(np.float64)   # [m, 16]
+        b = np.ascontiguousarray(s[lo:lo + blk]).view(np.uint16).astype(np.float64)
+        m = a.T @ b                                                                   # [16, 16], entries < 2^50
+        for i in range(16):
+            row = m[i]
+            for j in range(16):
+                acc[i][j] += int(row[j])
+    total = 0
+    for i in range(16):
+        for j in range(16):
+            total += acc[i][j] << (16 * (i + j))
+    return total % R

@@ -116,3 +116,38 @@ def test_prove_square_circuit_reproduces_reference_fixture():
     proof = g16.Proof(bn.g1_from_raw(a), bn.g2_from_raw(b), bn.g1_from_raw(c))
     pc = json.load(open(os.path.join(REF_FIXTURES, "proof_for_onchain.json")))["proof_components"]
     assert proof.serialize_uncompressed() == bytes(pc["pi_a"]) + bytes(pc["pi_b"]) + bytes(pc["pi_c"])
+
+
+def test_dot_mod_r_helper_is_exact():
+    """tests/helpers.py::dot_mod_r (the exact sum k_i s_i mod r behind the 2^24 known-dlog MSM check) against Python integers."""
+    import numpy as np
+    from helpers import dot_mod_r
+    from oracle import bn254 as bn
+
+    def rnd(n, seed):
+        rs = np.random.RandomState(seed)
+        a = rs.randint(0, 1 << 32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+        a[:, 7] %= 0x30644E72
+        return a
+
+    k, s = rnd(3000, 1), rnd(3000, 2)
+    ints = lambda a: [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+    assert dot_mod_r(k, s) == sum(x * y for x, y in zip(ints(k), ints(s))) % bn.R
+
+
+def test_poly_eval_matches_ntt_definition():
+    """oracle poly_eval (Horner, shares no code with the FFT) against the C++ FFT and the Python oracle's root of unity."""
+    import random
+    from oracle import bn254 as bn
+    R = bn.R
+    lg = 9
+    n = 1 << lg
+    rnd = random.Random(5)
+    a = [rnd.randrange(R) for _ in range(n)]
+    data = b"".join(x.to_bytes(32, "little") for x in a)
+    w = orc.root_of_unity(lg)
+    assert pow(w, n, R) == 1 and pow(w, n // 2, R) == R - 1
+    f = orc.ntt(data, lg, coset=True)
+    ks = [0, 1, 77, n - 1]
+    for k, e in zip(ks, orc.poly_eval(data, [5 * pow(w, k, R) % R for k in ks])):
+        assert int.from_bytes(f[32 * k:32 * k + 32], "little") == e == sum(c * pow(5 * pow(w, k, R), j, R) for j, c in enumerate(a)) % R

@@ -758,3 +758,61 @@ def test_l2_batch_prove_equals_single_proofs(ctx, l2_setup):
     bp.close()
     single.m.free()
     dpk.free()
+
+
+def test_prove_batch_equals_single_proves(ctx, l2_setup):
+    """zkb_prove_batch (batched mat-vecs / NTTs / MSMs: K scalar vectors against one window table, per-proof bucket arrays,
+    s A and r B1 by double-and-add instead of extra MSMs) returns exactly the K proofs zkb_prove makes one at a time -- for
+    K = 1, an odd K, r = 0 and s = 0 among the randomness, and a second call on the same context (buffers reused)."""
+    from zelana_b200 import l2_circuit as P2
+    circ, pk_bytes, vk_bytes, raw = l2_setup
+    dpk = ctx.proving_key_compressed(pk_bytes, validate=False)
+    a, b, c = circ.matrices()
+    m = ctx.r1cs(circ.num_instance, circ.num_witness, a, b, c)
+
+    def assignment(bid):
+        ck = P2.L2BlockCircuit(transactions=[P2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), 3 * bid + 1)],
+                               initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): bid}, batch_id=bid)
+        return circ.assign(ck.with_inputs(P2.satisfying_inputs(ck)))
+
+    K = 11
+    zs = [assignment(i + 1) for i in range(K)]
+    rs = [P2.prover_randomness(i + 1) for i in range(K)]
+    rs[3] = (bytes(32), rs[3][1])            # r = 0
+    rs[5] = (rs[5][0], bytes(32))            # s = 0
+    rs[7] = (fr_bytes([R - 1]), fr_bytes([1]))
+    expect = [ctx.prove(dpk, m, z, r, s) for z, (r, s) in zip(zs, rs)]
+    got = ctx.prove_batch(dpk, m, b"".join(zs), b"".join(r + s for r, s in rs))
+    assert got == expect
+    assert ctx.prove_batch(dpk, m, zs[2], rs[2][0] + rs[2][1]) == [expect[2]]
+    assert ctx.prove_batch(dpk, m, b"".join(zs[:5]), b"".join(r + s for r, s in rs[:5])) == expect[:5]
+    with pytest.raises(Exception):
+        ctx.prove_batch(dpk, m, b"".join(zs[:2]), rs[0][0] + rs[0][1])      # two assignments, one (r, s)
+    m.free()
+    dpk.free()
+
+
+def test_msm_batch_equals_single_msms(ctx):
+    """msm_run_batch through zkb_debug_msm_batch: K scalar vectors against one table == K separate MSMs (G1 and G2), with
+    zero / one / maximal scalars and a vector of all zeros among them."""
+    import numpy as np
+    import torch
+    n, K = 3000, 9
+    k = _rand_fr_np(n, 81)
+    for group in (1, 2):
+        gen = ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate
+        bases = gen(torch.from_numpy(k.view(np.int32)).cuda(), n)
+        sc = _rand_fr_np(n * K, 82 + group).reshape(K, n, 8)
+        sc[1] = 0
+        sc[2, ::2] = 0
+        sc[3, :, 1:] = 0
+        sc[3, :, 0] = 1
+        rm1 = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint32)
+        sc[4, :100] = rm1
+        single = [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p]) for p in range(K)]
+        got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda(), n, n, K)
+        assert got == single
+        # a sub-range with a stride larger than the vector length
+        got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda()[:, 5:], n - 500, n, K, offset=5)
+        assert got == [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p, 5:n - 495], offset=5) for p in range(K)]
+        bases.free()

@@ -71,6 +71,8 @@ SIGNATURES = {
     "zkb_ctx_synchronize": (_I, [_P]),
     "zkb_ctx_destroy": (None, [_P]),
     "zkb_last_error": (C.c_char_p, [_P]),
+    "zkb_host_alloc_pinned": (_I, [_SZ, C.POINTER(_P)]),
+    "zkb_host_free_pinned": (None, [_P]),
     "zkb_launch_count": (C.c_ulonglong, [_P]),
     "zkb_ctx_set_msm_window": (_I, [_P, _I]),
     "zkb_ctx_set_graphs": (_I, [_P, _I]),
@@ -89,6 +91,8 @@ SIGNATURES = {
     "zkb_g2_bases_load": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
     "zkb_g1_bases_generate": (_I, [_P, _P, _SZ, C.POINTER(_P)]),
     "zkb_g2_bases_generate": (_I, [_P, _P, _SZ, C.POINTER(_P)]),
+    "zkb_g1_bases_window": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
+    "zkb_g2_bases_window": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "zkb_g1_bases_len": (_SZ, [_P]),
     "zkb_g2_bases_len": (_SZ, [_P]),
     "zkb_g1_bases_read": (_I, [_P, _P, _SZ, _SZ, _P]),
@@ -101,17 +105,23 @@ SIGNATURES = {
     "zkb_msm_g2_dev": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P]),
     "zkb_msm_g1_combine": (_I, [_P, _P, _I, _P]),
     "zkb_msm_g2_combine": (_I, [_P, _P, _I, _P]),
+    "zkb_debug_msm_batch": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZ, _I, _P]),
     "zkb_ntt": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_ntt_dev": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_r1cs_load": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(_P)]),
     "zkb_r1cs_free": (None, [_P]),
     "zkb_r1cs_log_domain": (_I, [_P]),
+    "zkb_r1cs_num_variables": (C.c_uint64, [_P]),
+    "zkb_r1cs_num_constraints": (C.c_uint64, [_P]),
     "zkb_witness_map": (_I, [_P, _P, _P, _P]),
     "zkb_pk_load": (_I, [_P, C.POINTER(PkDesc), _I, C.POINTER(_P)]),
     "zkb_pk_load_compressed": (_I, [_P, _P, _SZ, _I, C.POINTER(_P)]),
     "zkb_pk_free": (None, [_P]),
     "zkb_pk_synthetic": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, C.POINTER(_P)]),
     "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "zkb_prove_batch_begin": (_I, [_P, _P, _P, _P, _P, _SZ]),
+    "zkb_prove_batch_end": (_I, [_P, _SZ, _P]),
+    "zkb_prove_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P]),
     "zkb_setup": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(SetupParams), C.POINTER(SetupOut)]),
     "zkb_pk_load_shard": (_I, [_P, C.POINTER(PkDesc), _I, _I, _I, C.POINTER(_P)]),
     "zkb_pk_synthetic_shard": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, _I, _I, C.POINTER(_P)]),

@@ -42,6 +42,7 @@ class Context:
             raise ZkbError(rc, "zkb_ctx_create(device=%d) failed (a CUDA device is required; no CPU fallback)" % device)
         self.h = h
         self.device = device
+        self.stream_handle = None      # None: the context's own non-blocking stream
         if stream is not None:
             self.set_stream(stream)
 
@@ -51,6 +52,7 @@ class Context:
 
     def set_stream(self, stream):
         self._check(self.lib.zkb_ctx_set_stream(self.h, C.c_void_p(int(stream) if stream else 0)))
+        self.stream_handle = int(stream) if stream else None
 
     def synchronize(self):
         self._check(self.lib.zkb_ctx_synchronize(self.h))
@@ -183,6 +185,16 @@ class Context:
     def msm_g2_combine(self, partials_dev, k, out_affine_dev):
         self._check(self.lib.zkb_msm_g2_combine(self.h, _devptr(partials_dev), k, _devptr(out_affine_dev)))
 
+    def debug_msm_batch(self, group, bases, scalars_dev, n, stride, batch, offset=0):
+        """Parity hook: `batch` MSMs over the same bases in one batched pass -> list of canonical affine byte strings."""
+        import torch
+        sz = 64 if group == 1 else 128
+        out = torch.zeros(batch * sz, dtype=torch.uint8, device=scalars_dev.device)
+        self._check(self.lib.zkb_debug_msm_batch(self.h, group, bases.h, offset, _devptr(scalars_dev), n, stride, batch, _devptr(out)))
+        self.synchronize()
+        o = bytes(out.cpu().numpy())
+        return [o[sz * i:sz * (i + 1)] for i in range(batch)]
+
     # ---- NTT
     def ntt(self, data, log_n, inverse=False, coset=False):
         pi, ki = _buf(data)
@@ -221,14 +233,13 @@ class Context:
 
     def setup(self, num_instance, num_witness, a, b, c, *, alpha, beta, gamma, delta, tau, g1_generator, g2_generator):
         """Groth16 parameter generation on the GPU (zkb_setup) from explicit toxic waste -> dict of raw affine byte strings."""
-        csr = [m if isinstance(m, tuple) else _csr_arrays(m) for m in (a, b, c)]
+        csr = [_checked_csr(m, num_instance + num_witness) for m in (a, b, c)]
+        if not (len(csr[0][0]) == len(csr[1][0]) == len(csr[2][0])):
+            raise ZkbError(-6, "A, B and C must have the same number of rows")
         keep = []
         d = R1csDesc()
         d.num_constraints, d.num_instance, d.num_witness = len(csr[0][0]) - 1, num_instance, num_witness
         for name, (rp, col, co) in zip(("a", "b", "c"), csr):
-            rp = np.ascontiguousarray(rp, dtype=np.uint64)
-            col = np.ascontiguousarray(col, dtype=np.uint32)
-            co = np.ascontiguousarray(co, dtype=np.uint8).reshape(-1)
             keep += [rp, col, co]
             setattr(d, name, Csr(rp.ctypes.data, col.ctypes.data, co.ctypes.data))
         prm = SetupParams()
@@ -250,8 +261,16 @@ class Context:
         self._check(self.lib.zkb_setup(self.h, C.byref(d), C.byref(prm), C.byref(out)))
         return {k: bufs[k][:sizes[k]].tobytes() for k in sizes}
 
+    @staticmethod
+    def _check_z(r1cs, kz):
+        """The C ABI takes a bare pointer: a short assignment would be an out-of-bounds host read, so check it here."""
+        want = (r1cs.num_instance + r1cs.num_witness) * 32
+        if len(kz) != want:
+            raise ZkbError(-6, "assignment has %d bytes, the matrices need %d (num_instance + num_witness) x 32" % (len(kz), want))
+
     def witness_map(self, r1cs, z_bytes):
         pz, kz = _buf(z_bytes)
+        self._check_z(r1cs, kz)
         n = 1 << r1cs.log_domain
         out = np.empty(n * 32, dtype=np.uint8)
         self._check(self.lib.zkb_witness_map(self.h, r1cs.h, pz, out.ctypes.data_as(C.c_void_p)))
@@ -264,6 +283,7 @@ class Context:
     def prove_partial(self, pk, r1cs, z_bytes, r_bytes, s_bytes, out_partial_dev):
         """This rank's share of a sharded proof -> PROVE_PARTIAL_BYTES at out_partial_dev (device memory)."""
         pz, kz = _buf(z_bytes)
+        self._check_z(r1cs, kz)
         pr, kr = _buf(r_bytes)
         ps, ks = _buf(s_bytes)
         self._check(self.lib.zkb_prove_partial(self.h, pk.h, r1cs.h, pz, pr, ps, _devptr(out_partial_dev)))
@@ -278,10 +298,28 @@ class Context:
                                                ob.ctypes.data_as(C.c_void_p), oc.ctypes.data_as(C.c_void_p)))
         return oa.tobytes(), ob.tobytes(), oc.tobytes()
 
+    def prove_batch(self, pk, r1cs, z_bytes, rs_bytes):
+        """K proofs of one circuit/key in one set of batched launches (zkb_prove_batch).  z_bytes: K assignments back to back;
+        rs_bytes: K x (r || s).  -> list of (A, B, C) byte triples, identical to K calls of prove()."""
+        pz, kz = _buf(z_bytes)
+        prs, krs = _buf(rs_bytes)
+        per = (r1cs.num_instance + r1cs.num_witness) * 32
+        k = len(krs) // 64
+        if k < 1 or len(krs) != k * 64 or len(kz) != k * per:
+            raise ZkbError(-6, "prove_batch: %d bytes of assignments and %d bytes of (r, s) do not describe the same number of proofs"
+                           % (len(kz), len(krs)))
+        out = np.empty(k * 256, dtype=np.uint8)
+        self._check(self.lib.zkb_prove_batch(self.h, pk.h, r1cs.h, pz, prs, k, out.ctypes.data_as(C.c_void_p)))
+        o = out.tobytes()
+        return [(o[256 * i:256 * i + 64], o[256 * i + 64:256 * i + 192], o[256 * i + 192:256 * i + 256]) for i in range(k)]
+
     def prove(self, pk, r1cs, z_bytes, r_bytes, s_bytes):
         pz, kz = _buf(z_bytes)
+        self._check_z(r1cs, kz)
         pr, kr = _buf(r_bytes)
         ps, ks = _buf(s_bytes)
+        if len(kr) != 32 or len(ks) != 32:
+            raise ZkbError(-3, "r and s are 32-byte canonical Fr elements")
         oa = np.empty(64, dtype=np.uint8)
         ob = np.empty(128, dtype=np.uint8)
         oc = np.empty(64, dtype=np.uint8)
@@ -301,6 +339,12 @@ class _Bases:
 
     def __len__(self):
         return int(getattr(self.ctx.lib, self._len)(self.h))
+
+    def window(self):
+        """(c, nwin): window width and number of resident window tables (nwin x len points in HBM)."""
+        c, nwin = C.c_int(0), C.c_int(0)
+        self.ctx._check(getattr(self.ctx.lib, self._window)(self.h, C.byref(c), C.byref(nwin)))
+        return int(c.value), int(nwin.value)
 
     def read(self, offset=0, n=None):
         n = len(self) - offset if n is None else n
@@ -322,6 +366,7 @@ class _Bases:
 
 class G1Bases(_Bases):
     _free, _len, _read, _size = "zkb_g1_bases_free", "zkb_g1_bases_len", "zkb_g1_bases_read", 64
+    _window = "zkb_g1_bases_window"
 
     @classmethod
     def _load(cls, ctx, data, validate):
@@ -333,6 +378,7 @@ class G1Bases(_Bases):
 
 class G2Bases(_Bases):
     _free, _len, _read, _size = "zkb_g2_bases_free", "zkb_g2_bases_len", "zkb_g2_bases_read", 128
+    _window = "zkb_g2_bases_window"
 
     @classmethod
     def _load(cls, ctx, data, validate):
@@ -358,6 +404,23 @@ def _csr_arrays(rows):
     return row_ptr, col, coeff
 
 
+def _checked_csr(m, nvars):
+    """rows of (coeff, var) or a prebuilt (row_ptr, col, coeff) triple -> contiguous arrays whose lengths agree with row_ptr[-1]
+    (the C side trusts row_ptr to index col / coeff)."""
+    rp, col, co = m if isinstance(m, tuple) else _csr_arrays(m)
+    rp = np.ascontiguousarray(rp, dtype=np.uint64)
+    col = np.ascontiguousarray(col, dtype=np.uint32)
+    co = np.ascontiguousarray(co, dtype=np.uint8).reshape(-1)
+    nnz = int(rp[-1]) if len(rp) else 0
+    if len(rp) < 1 or int(rp[0]) != 0:
+        raise ZkbError(-6, "CSR row_ptr must start at 0")
+    if len(col) < nnz or len(co) < nnz * 32:
+        raise ZkbError(-6, "CSR arrays shorter than row_ptr[-1] = %d entries (col %d, coeff %d bytes)" % (nnz, len(col), len(co)))
+    if nnz and int(col[:nnz].max()) >= nvars:
+        raise ZkbError(-6, "CSR column index beyond the %d variables" % nvars)
+    return rp, col, co
+
+
 class R1csMatrices:
     """Device-resident ConstraintMatrices (ark-relations): rows of (coeff, variable)."""
 
@@ -366,13 +429,11 @@ class R1csMatrices:
         self.ctx = ctx
         keep = []
         d = R1csDesc()
-        csr = [m if isinstance(m, tuple) else _csr_arrays(m) for m in (a, b, c)]
-        assert len(csr[0][0]) == len(csr[1][0]) == len(csr[2][0])
+        csr = [_checked_csr(m, num_instance + num_witness) for m in (a, b, c)]
+        if not (len(csr[0][0]) == len(csr[1][0]) == len(csr[2][0])):
+            raise ZkbError(-6, "A, B and C must have the same number of rows")
         d.num_constraints, d.num_instance, d.num_witness = len(csr[0][0]) - 1, num_instance, num_witness
         for name, (rp, col, co) in zip(("a", "b", "c"), csr):
-            rp = np.ascontiguousarray(rp, dtype=np.uint64)
-            col = np.ascontiguousarray(col, dtype=np.uint32)
-            co = np.ascontiguousarray(co, dtype=np.uint8).reshape(-1)
             keep += [rp, col, co]
             setattr(d, name, Csr(rp.ctypes.data, col.ctypes.data, co.ctypes.data))
         h = C.c_void_p()

@@ -80,7 +80,10 @@ __device__ __forceinline__ Fr shfl_down_fr(const Fr& v, int d) {
 }
 __global__ void csr_matvec_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
                                   const Fr* __restrict__ coeff, const Fr* __restrict__ z, uint64_t nc, uint64_t ni,
-                                  int append_instance, size_t n, Fr* __restrict__ out) {
+                                  int append_instance, size_t n, Fr* __restrict__ out, size_t z_stride) {
+  // blockIdx.y: which assignment of a batch (z_stride elements apart; outputs n apart)
+  z += size_t(blockIdx.y) * z_stride;
+  out += size_t(blockIdx.y) * n;
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   Fr acc = Fr::zero();
@@ -275,13 +278,13 @@ int ensure_ntt_tables(zkb_ctx* ctx, FrState* S, int logn, NttTables** out) {
 }
 
 template <int LR>
-void launch_pass(const NttPassArgs& a, cudaStream_t st) {
+void launch_pass(const NttPassArgs& a, int batch, cudaStream_t st) {
   constexpr int TQ = 4;
   constexpr int NE = (1 << LR) * TQ;
   constexpr int NT = NE / 2 < 32 ? 32 : NE / 2;
   size_t nq = size_t(1) << (a.logn - LR);
   unsigned blocks = unsigned((nq + TQ - 1) / TQ);
-  ntt_pass_kernel<LR, TQ><<<blocks, NT, 0, st>>>(a);
+  ntt_pass_kernel<LR, TQ><<<dim3(blocks, unsigned(batch)), NT, 0, st>>>(a);
 }
 
 }  // namespace
@@ -336,11 +339,18 @@ int fr_scale(zkb_ctx* ctx, const Fr* in, const Fr* k_dev, Fr* out, size_t n) {
 }
 
 int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset) {
+  return ntt_batch_dev_impl(ctx, in, out, logn, inverse, coset, 1);
+}
+
+// `batch` transforms of 2^logn elements each, back to back in `in` and `out`: one launch per pass for all of them
+// (blockIdx.y = polynomial).  A batch of small proofs runs its 7 x K transforms of 2^13 this way.
+int ntt_batch_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset, int batch) {
   if (logn < 0 || logn > 28) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: log_n %d outside [0, 28]", logn);
+  if (batch < 1 || batch > 65535) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: batch %d outside [1, 65535]", batch);
   size_t n = size_t(1) << logn;
   if (logn == 0) {
     // size-1 domain: identity (coset scale g^0 = 1, 1/n = 1)
-    if (in != out) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (in != out) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, sizeof(Fr) * batch, cudaMemcpyDeviceToDevice, ctx->stream));
     return ZKB_OK;
   }
   FrState* S = state(ctx);
@@ -351,11 +361,11 @@ int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int
   int base = logn / npass, extra = logn % npass;
   Fr* scratch[2] = {nullptr, nullptr};
   if (npass >= 2 || in == out) {
-    CUDA_TRY(ctx, ctx->tmp0.reserve(n * sizeof(Fr)));
+    CUDA_TRY(ctx, ctx->tmp0.reserve(n * sizeof(Fr) * batch));
     scratch[0] = ctx->tmp0.as<Fr>();
   }
   if (npass >= 3) {
-    CUDA_TRY(ctx, ctx->tmp1.reserve(n * sizeof(Fr)));
+    CUDA_TRY(ctx, ctx->tmp1.reserve(n * sizeof(Fr) * batch));
     scratch[1] = ctx->tmp1.as<Fr>();
   }
   const Fr* src = in;
@@ -387,21 +397,21 @@ int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int
     a.has_post = (last && inverse) ? 1 : 0;
     a.post = coset ? T->coset_inv_post : ninv_tab;
     switch (lr) {
-      case 1: launch_pass<1>(a, ctx->stream); break;
-      case 2: launch_pass<2>(a, ctx->stream); break;
-      case 3: launch_pass<3>(a, ctx->stream); break;
-      case 4: launch_pass<4>(a, ctx->stream); break;
-      case 5: launch_pass<5>(a, ctx->stream); break;
-      case 6: launch_pass<6>(a, ctx->stream); break;
-      case 7: launch_pass<7>(a, ctx->stream); break;
-      default: launch_pass<8>(a, ctx->stream); break;
+      case 1: launch_pass<1>(a, batch, ctx->stream); break;
+      case 2: launch_pass<2>(a, batch, ctx->stream); break;
+      case 3: launch_pass<3>(a, batch, ctx->stream); break;
+      case 4: launch_pass<4>(a, batch, ctx->stream); break;
+      case 5: launch_pass<5>(a, batch, ctx->stream); break;
+      case 6: launch_pass<6>(a, batch, ctx->stream); break;
+      case 7: launch_pass<7>(a, batch, ctx->stream); break;
+      default: launch_pass<8>(a, batch, ctx->stream); break;
     }
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     src = dst;
     logm -= lr;
   }
-  if (npass == 1 && in == out) CUDA_TRY(ctx, cudaMemcpyAsync(out, scratch[0], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (npass == 1 && in == out) CUDA_TRY(ctx, cudaMemcpyAsync(out, scratch[0], n * sizeof(Fr) * batch, cudaMemcpyDeviceToDevice, ctx->stream));
   return ZKB_OK;
 }
 
@@ -437,9 +447,9 @@ int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev
   {
     ProfScope ps(ctx, PH_MATVEC);
     ZKB_TRY(fr_to_mont(ctx, w.z, w.zm, nv));
-    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(A.row_ptr, A.col, A.coeff, w.zm, nc, ni, 1, n, w.wa);
-    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(B.row_ptr, B.col, B.coeff, w.z, nc, ni, 0, n, w.wb);
-    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(C.row_ptr, C.col, C.coeff, w.z, nc, ni, 0, n, w.wc);
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(A.row_ptr, A.col, A.coeff, w.zm, nc, ni, 1, n, w.wa, 0);
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(B.row_ptr, B.col, B.coeff, w.z, nc, ni, 0, n, w.wb, 0);
+    csr_matvec_kernel<<<blocks_for(n, 128), 128, 0, st>>>(C.row_ptr, C.col, C.coeff, w.z, nc, ni, 0, n, w.wc, 0);
     ctx->launches += 3;
     CUDA_TRY(ctx, cudaGetLastError());
   }
@@ -457,6 +467,42 @@ int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev
     CUDA_TRY(ctx, cudaGetLastError());
   }
   ZKB_TRY(ntt_dev_impl(ctx, w.wa, h_out, lg, 1, 1));  // coset_domain.ifft_in_place
+  return ZKB_OK;
+}
+
+// K witness maps at once (a batch of proofs of ONE circuit).  z: K x nv canonical; w3: 3 K n elements of scratch laid out
+// [a-chain of every proof | b-chains | c-chains] so that each NTT stage is ONE batched launch over 3 K polynomials;
+// zm: K x nv scratch; h_out: K x n canonical coefficients of the K quotients.
+int witness_map_batch_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
+                          int lg, int K, const Fr* z, Fr* zm, Fr* w3, Fr* h_out) {
+  const size_t n = size_t(1) << lg;
+  const size_t nv = ni + nw;
+  cudaStream_t st = ctx->stream;
+  Fr* wa = w3;
+  Fr* wb = w3 + size_t(K) * n;
+  Fr* wc = w3 + 2 * size_t(K) * n;
+  {
+    ProfScope ps(ctx, PH_MATVEC);
+    ZKB_TRY(fr_to_mont(ctx, z, zm, nv * size_t(K)));
+    dim3 grid(blocks_for(n, 128), unsigned(K));
+    csr_matvec_kernel<<<grid, 128, 0, st>>>(A.row_ptr, A.col, A.coeff, zm, nc, ni, 1, n, wa, nv);
+    csr_matvec_kernel<<<grid, 128, 0, st>>>(B.row_ptr, B.col, B.coeff, z, nc, ni, 0, n, wb, nv);
+    csr_matvec_kernel<<<grid, 128, 0, st>>>(C.row_ptr, C.col, C.coeff, z, nc, ni, 0, n, wc, nv);
+    ctx->launches += 3;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  ZKB_TRY(ntt_batch_dev_impl(ctx, w3, w3, lg, 1, 0, 3 * K));  // domain.ifft_in_place on a, b, c of every proof
+  ZKB_TRY(ntt_batch_dev_impl(ctx, w3, w3, lg, 0, 1, 3 * K));  // coset_domain.fft_in_place
+  {
+    ProfScope ps(ctx, PH_POINTWISE);
+    NttTables* T = nullptr;
+    ZKB_TRY(ensure_ntt_tables(ctx, state(ctx), lg, &T));
+    const size_t tot = n * size_t(K);   // the K a-chains, b-chains, c-chains are each contiguous: one flat pointwise pass
+    qap_pointwise_kernel<<<blocks_for(tot, 128), 128, 0, st>>>(wa, wb, wc, T->zinv, tot, wa);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  ZKB_TRY(ntt_batch_dev_impl(ctx, wa, h_out, lg, 1, 1, K));  // coset_domain.ifft_in_place
   return ZKB_OK;
 }
 

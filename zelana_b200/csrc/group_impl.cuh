@@ -52,7 +52,11 @@ template <> struct FieldIO<Fq2> {
   }
 };
 
-// canonical affine bytes -> Montgomery affine, optional on-curve validation
+template <class F> struct SubgroupCheck;
+template <> struct SubgroupCheck<Fq> { static constexpr bool NEEDED = false; };
+template <> struct SubgroupCheck<Fq2> { static constexpr bool NEEDED = true; };
+
+// canonical affine bytes -> Montgomery affine, optional validation (on curve; G2: in the prime-order subgroup)
 template <class F>
 __global__ void affine_import_kernel(const uint32_t* in, Affine<F>* out, size_t n, int validate, int* bad) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -67,6 +71,12 @@ __global__ void affine_import_kernel(const uint32_t* in, Affine<F>* out, size_t 
     F lhs = p.y.sqr();
     F rhs = p.x.sqr() * p.x + CurveB<F>::b();
     if (lhs != rhs) { atomicExch(bad, 2); return; }
+    // same meaning of `validate` as the compressed loader and arkworks' Validate::Yes: G2 has a cofactor, so an on-curve
+    // point must also be killed by r (G1 has cofactor 1: nothing to check)
+    if (SubgroupCheck<F>::NEEDED) {
+      const uint32_t r[8] = {FrCfg::M0, FrCfg::M1, FrCfg::M2, FrCfg::M3, FrCfg::M4, FrCfg::M5, FrCfg::M6, FrCfg::M7};
+      if (!XYZZ<F>::from_affine(p).mul_words(r).is_inf()) { atomicExch(bad, 4); return; }
+    }
   }
   out[i] = p;
 }
@@ -217,6 +227,28 @@ __global__ void fixed_base_mul_kernel(const Affine<F>* __restrict__ table, const
     if (d) acc.madd(table[w * 255 + d - 1]);
   }
   out[i] = acc.to_affine();
+}
+
+// k * G for a fixed_base_table_kernel table of G (8-bit windows: at most 32 mixed additions, no doublings); k: 8 canonical words
+template <class F>
+__device__ __forceinline__ XYZZ<F> fixed_table_mul(const Affine<F>* __restrict__ table, const uint32_t* k) {
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (int w = 0; w < 32; w++) {
+    uint32_t d = (k[w >> 2] >> (8 * (w & 3))) & 0xffu;
+    if (d) acc.madd(load_affine(table + w * 255 + d - 1));
+  }
+  return acc;
+}
+
+// same table, generator read from device memory (a key's delta)
+template <class F>
+__global__ void fixed_base_table_dev_kernel(const Affine<F>* gen, Affine<F>* table) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 32 * 255) return;
+  int w = t / 255, d = t % 255 + 1;
+  uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  k[w / 4] = uint32_t(d) << (8 * (w % 4));
+  table[t] = XYZZ<F>::from_affine(*gen).mul_words(k).to_affine();
 }
 
 // ------------------------------------------------------------------------------------------- host drivers
@@ -523,6 +555,43 @@ int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t o
   return ZKB_OK;
 }
 
+// `batch` scalar vectors (vector p at scalars_dev + p * stride * 32 bytes) against bases [offset, offset + n): one sort /
+// accumulation / reduction for all (msm_run_batch).  out_partial_dev: batch x XYZZ; out_affine_dev: batch x canonical affine.
+template <class F>
+int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                       size_t stride, int batch, void* out_affine_dev, void* out_partial_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!bases || offset + n > bases->n || (!scalars_dev && n) || batch < 1 || stride < n)
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_batch: bad bases range, scalars or batch");
+  if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_batch: bases live on device %d, ctx on %d", bases->device, ctx->device);
+  ZKB_TRY(set_device(ctx));
+  cudaError_t e = msm_run_batch<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset,
+                                   static_cast<const uint32_t*>(scalars_dev), n, stride, batch,
+                                   static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run_batch: %s", cudaGetErrorString(e));
+  }
+  return ZKB_OK;
+}
+
+// 32 x 255 fixed-base table (8-bit windows) of bases->p[idx]: delta_g1 / delta_g2 of a key, for the per-proof r, s multiples
+template <class F>
+int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t idx, void** out_table) {
+  if (!bases || idx >= bases->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "fixed_table_for_base: bad index");
+  Affine<F>* table = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&table, 32 * 255 * sizeof(Affine<F>)));
+  fixed_base_table_dev_kernel<F><<<blocks_for(32 * 255, 64), 64, 0, ctx->stream>>>(bases->p + idx, table);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    cudaFree(table);
+    ZKB_FAIL(ctx, ZKB_ERR_CUDA, "fixed_base_table_dev_kernel: %s", cudaGetErrorString(e));
+  }
+  *out_table = table;
+  return ZKB_OK;
+}
+
 template <class F>
 int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
                   uint8_t* out) {
@@ -573,6 +642,8 @@ int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
   template int msm_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, void*, void*);              \
   template int msm_host_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const uint8_t*, size_t, uint8_t*);              \
   template int msm_combine_impl<F>(zkb_ctx*, const void*, int, void*);                                                      \
+  template int msm_batch_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*); \
+  template int fixed_table_for_base<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, void**);                                  \
   template void fixed_table_free<F>(zkb_ctx*);                                                                             \
   template int fixed_base_batch<F>(zkb_ctx*, const uint8_t*, const void*, size_t, uint8_t*);
 

@@ -127,6 +127,9 @@ struct zkb_ctx {
   // into PAGEABLE memory blocks the calling thread (spinning in the driver) until everything queued before it has run.
   uint8_t* pinned = nullptr;
   unsigned long long graph_replays = 0, graph_captures = 0;
+  zkb::DevBuf bz, bzm, bw3, bh, brs, bpart, bout;   // batched prove (zkb_prove_batch): K assignments, 3 K chains, K quotients
+  uint8_t* bpinned = nullptr;                     // K x 256 B of results, pinned
+  size_t bpinned_cap = 0;
   void* fr_state = nullptr;                       // NTT tables, owned by fr.cu
   void* g1_table = nullptr;                       // fixed-base tables, owned by g1.cu / g2.cu
   void* g2_table = nullptr;
@@ -218,6 +221,9 @@ template <class F> int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bas
 template <class F> int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host,
                                      size_t n, uint8_t* out);
 template <class F> int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out);
+template <class F> int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
+                                          size_t n, size_t stride, int batch, void* out_affine_dev, void* out_partial_dev);
+template <class F> int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t idx, void** out_table);
 template <class F> void fixed_table_free(zkb_ctx* ctx);
 // out_host[i] = scalars_dev[i] * generator  (canonical 32 B scalars on the device; raw canonical affine out; zero -> infinity)
 template <class F> int fixed_base_batch(zkb_ctx* ctx, const uint8_t* generator_raw, const void* scalars_dev, size_t n, uint8_t* out_host);
@@ -233,6 +239,13 @@ int prove_assemble_sum(zkb_ctx* ctx, const void* pSA, const void* pRB1, const vo
 int prove_combine_g1(zkb_ctx* ctx, const void* parts, int world, size_t stride, const void* r_dev, const void* s_dev,
                      void* out_a_dev, void* out_c_dev);
 int prove_combine_g2(zkb_ctx* ctx, const void* parts, int world, size_t stride, void* out_b_dev);
+// Batched prove, last step (K proofs of one key).  G1: A = PA + a_query[0] + alpha + r delta, B1 = PB1 + b_query[0] + beta + s delta,
+// C = s A + r B1 - r s delta + PL + PH; out: K x 256 B records, A at +0 and C at +192.  G2: B = PB2 + b0 + beta + s delta at +64.
+// tails: the three points (query[0], alpha|beta, delta) = the last three bases of a_ext / b1_ext / b2_ext; fb_*: fixed-base
+// tables of delta (fixed_table_for_base); rs: K x (r, s) canonical.
+int prove_batch_finish_g1(zkb_ctx* ctx, int K, const void* PA, const void* PB1, const void* PL, const void* PH, const void* rs,
+                          const void* a_tail, const void* b1_tail, const void* fb_delta1, void* out);
+int prove_batch_finish_g2(zkb_ctx* ctx, int K, const void* PB2, const void* rs, const void* b2_tail, const void* fb_delta2, void* out);
 
 // fr.cu
 struct CsrDev {
@@ -244,12 +257,15 @@ struct CsrDev {
 int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);  // flags non-canonical input in ctx->flag
 int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset);
+int ntt_batch_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset, int batch);
 void fr_state_free(zkb_ctx* ctx);
 struct WitnessBufs {
   Fr *z, *zm, *wa, *wb, *wc;
 };
 int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
                     int log_domain, const WitnessBufs& w, Fr* h_out);
+int witness_map_batch_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
+                          int log_domain, int K, const Fr* z, Fr* zm, Fr* w3, Fr* h_out);
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail);
 int fr_scale(zkb_ctx* ctx, const Fr* in, const Fr* k_dev, Fr* out, size_t n);  // out[i] = k * in[i], all canonical
 int setup_scalars_dev(zkb_ctx* ctx, const uint64_t* const col_ptr[3], const uint32_t* const row[3], const Fr* const coeff[3],
@@ -281,4 +297,5 @@ struct zkb_pk {
   // nv / nw / nh keep describing the WHOLE key.  Unsharded: offsets 0.
   size_t off_a = 0, off_l = 0, off_h = 0;   // a_ext, b1_ext and b2_ext share off_a
   int shard = 0, world = 1;
+  void *fb_delta1 = nullptr, *fb_delta2 = nullptr;  // fixed-base tables of delta_g1 / delta_g2 (built by the first batched prove)
 };

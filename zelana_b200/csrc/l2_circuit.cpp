@@ -17,6 +17,11 @@
 //   * the GPU never waits for it: zkb_l2_prove assigns on the host and hands z to zkb_prove.
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdint>
 #include <cstdlib>
 #include <initializer_list>
@@ -1027,6 +1032,31 @@ constexpr uint64_t PAR_MIN_WITNESS = 40000;
 static thread_local std::string g_l2_error;
 const char* zkb_l2_last_error(void) { return g_l2_error.c_str(); }
 
+// Joins whatever was started when the scope ends, also while an exception unwinds: a std::thread destroyed joinable calls
+// std::terminate, and emplace_back can throw std::system_error half way through starting the workers.
+struct JoinGuard {
+  std::vector<std::thread> th;
+  ~JoinGuard() {
+    for (auto& t : th)
+      if (t.joinable()) t.join();
+  }
+};
+
+// Nothing may unwind through the C ABI (the host is Rust: UB): every exported zkb_l2_* body ends in these handlers.
+#define ZKB_L2_CATCH_ALL()                    \
+  catch (const std::bad_alloc&) {             \
+    g_l2_error = "out of host memory";        \
+    return ZKB_ERR_OOM;                       \
+  }                                           \
+  catch (const std::exception& e) {           \
+    g_l2_error = e.what();                    \
+    return ZKB_ERR_INVALID_ARG;               \
+  }                                           \
+  catch (...) {                               \
+    g_l2_error = "unknown C++ exception";     \
+    return ZKB_ERR_INVALID_ARG;               \
+  }
+
 int zkb_l2_circuit_create(const zkb_l2_witness* shape, zkb_l2_circuit** out) {
   if (!out) return ZKB_ERR_INVALID_ARG;
   *out = nullptr;
@@ -1107,10 +1137,9 @@ static int l2_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs
     };
     for (int pass = 1; pass <= 2; ++pass) {
       const int n = pass == 1 ? nthreads : l2::NUM_CHAINS;
-      std::vector<std::thread> th;
-      for (int t = 1; t < n; ++t) th.emplace_back(walk, pass, t, n, pass == 1 ? -2 : t);
+      JoinGuard jg;
+      for (int t = 1; t < n; ++t) jg.th.emplace_back(walk, pass, t, n, pass == 1 ? -2 : t);
       walk(pass, 0, n, pass == 1 ? -2 : 0);
-      for (auto& t : th) t.join();
     }
     for (int x : bad) {
       if (x) {
@@ -1139,11 +1168,10 @@ static void l2_z_to_bytes(const std::vector<l2::Fr>& z, uint8_t* out) {
     for (size_t i = lo; i < hi; ++i) l2::to_le_bytes(z[i], out + 32 * i);
   };
   if (nthreads <= 1 || z.size() < PAR_MIN_WITNESS) return conv(0, z.size());
-  std::vector<std::thread> th;
+  JoinGuard jg;
   const size_t step = (z.size() + size_t(nthreads) - 1) / size_t(nthreads);
-  for (int t = 1; t < nthreads; ++t) th.emplace_back(conv, std::min(z.size(), step * size_t(t)), std::min(z.size(), step * size_t(t + 1)));
+  for (int t = 1; t < nthreads; ++t) jg.th.emplace_back(conv, std::min(z.size(), step * size_t(t)), std::min(z.size(), step * size_t(t + 1)));
   conv(0, std::min(z.size(), step));
-  for (auto& t : th) t.join();
 }
 
 int zkb_l2_circuit_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witness,
@@ -1155,14 +1183,13 @@ int zkb_l2_circuit_assign(const zkb_l2_circuit* c, const zkb_l2_public_inputs* i
     if (rc != ZKB_OK) return rc;
     l2_z_to_bytes(z, z_out);
     return ZKB_OK;
-  } catch (const std::bad_alloc&) {
-    g_l2_error = "out of host memory";
-    return ZKB_ERR_OOM;
   }
+  ZKB_L2_CATCH_ALL()
 }
 
 int zkb_l2_circuit_is_satisfied(const zkb_l2_circuit* c, const uint8_t* z, int* satisfied, uint64_t* first_bad_row) {
   if (!c || !z || !satisfied) return ZKB_ERR_INVALID_ARG;
+  try {
   size_t nz = l2::NUM_INSTANCE + c->num_witness;
   std::vector<l2::Fr> zm(nz);
   for (size_t i = 0; i < nz; ++i) zm[i] = l2::from_le_bytes_mod_order(z + 32 * i, 32);
@@ -1180,6 +1207,8 @@ int zkb_l2_circuit_is_satisfied(const zkb_l2_circuit* c, const uint8_t* z, int* 
     }
   }
   return ZKB_OK;
+  }
+  ZKB_L2_CATCH_ALL()
 }
 
 int zkb_l2_roots(const zkb_l2_witness* witness, uint64_t batch_id, const uint8_t pre_shielded_root[32],
@@ -1231,10 +1260,8 @@ int zkb_l2_roots(const zkb_l2_witness* witness, uint64_t batch_id, const uint8_t
     }
     l2::to_le_bytes(l2::hash_native({bh, l2::from_u64(w.txs.size())}), out->batch_hash);
     return ZKB_OK;
-  } catch (const std::bad_alloc&) {
-    g_l2_error = "out of host memory";
-    return ZKB_ERR_OOM;
   }
+  ZKB_L2_CATCH_ALL()
 }
 
 int zkb_l2_poseidon_hash(const uint8_t* elems, size_t n, uint8_t out[32]) {
@@ -1255,6 +1282,31 @@ int zkb_l2_prover_randomness(uint64_t batch_id, uint8_t r[32], uint8_t s[32]) {
   return ZKB_OK;
 }
 
+// proof_to_solana_bytes (prover.rs:304-334): -A || B || C, 32-byte LE coordinates
+static void l2_format_solana(const uint8_t a[64], const uint8_t b[128], const uint8_t cc[64], uint8_t proof_out[256]) {
+  static const uint64_t FQ[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  bool a_inf = true;
+  for (int i = 0; i < 64; ++i) a_inf &= a[i] == 0;
+  memcpy(proof_out, a, 32);
+  if (a_inf) {
+    memset(proof_out + 32, 0, 32);
+  } else {
+    uint64_t y[4], o[4];
+    memcpy(y, a + 32, 32);
+    bool y_zero = (y[0] | y[1] | y[2] | y[3]) == 0;
+    l2::u128 br = 0;
+    for (int i = 0; i < 4; ++i) {
+      l2::u128 t = (l2::u128)FQ[i] - y[i] - (uint64_t)br;
+      o[i] = (uint64_t)t;
+      br = (t >> 64) & 1;
+    }
+    if (y_zero) memset(o, 0, sizeof o);
+    memcpy(proof_out + 32, o, 32);
+  }
+  memcpy(proof_out + 64, b, 128);
+  memcpy(proof_out + 192, cc, 64);
+}
+
 int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c, const zkb_l2_public_inputs* inputs,
                  const zkb_l2_witness* witness, uint8_t proof_out[256]) {
   if (!ctx || !pk || !m || !proof_out) return ZKB_ERR_INVALID_ARG;
@@ -1262,6 +1314,11 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
     std::vector<l2::Fr> z;
     int rc = l2_assign(c, inputs, witness, &z);
     if (rc != ZKB_OK) return rc;
+    if (zkb_r1cs_num_variables(m) != z.size()) {  // m / pk made for another circuit shape: zkb_prove would read past zb
+      g_l2_error = "zkb_l2_prove: the matrices have " + std::to_string(zkb_r1cs_num_variables(m)) + " variables, the circuit " +
+                   std::to_string(z.size());
+      return ZKB_ERR_SHAPE;
+    }
     std::vector<uint8_t> zb(z.size() * 32);
     l2_z_to_bytes(z, zb.data());
     uint8_t r[32], s[32];
@@ -1272,107 +1329,283 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
       g_l2_error = zkb_last_error(ctx);
       return rc;
     }
-    // proof_to_solana_bytes (prover.rs:304-334): -A || B || C, 32-byte LE coordinates
-    static const uint64_t FQ[4] = {0x3c208c16d87cfd47ull, 0x97816a916871ca8dull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
-    bool a_inf = true;
-    for (int i = 0; i < 64; ++i) a_inf &= a[i] == 0;
-    memcpy(proof_out, a, 32);
-    if (a_inf) {
-      memset(proof_out + 32, 0, 32);
-    } else {
-      uint64_t y[4], o[4];
-      memcpy(y, a + 32, 32);
-      bool y_zero = (y[0] | y[1] | y[2] | y[3]) == 0;
-      l2::u128 br = 0;
-      for (int i = 0; i < 4; ++i) {
-        l2::u128 t = (l2::u128)FQ[i] - y[i] - (uint64_t)br;
-        o[i] = (uint64_t)t;
-        br = (t >> 64) & 1;
-      }
-      if (y_zero) memset(o, 0, sizeof o);
-      memcpy(proof_out + 32, o, 32);
-    }
-    memcpy(proof_out + 64, b, 128);
-    memcpy(proof_out + 192, cc, 64);
+    l2_format_solana(a, b, cc, proof_out);
     return ZKB_OK;
-  } catch (const std::bad_alloc&) {
-    g_l2_error = "out of host memory";
-    return ZKB_ERR_OOM;
   }
+  ZKB_L2_CATCH_ALL()
 }
 
 // ================================================================================================ batches of proofs
-// BASELINE.json config 5 ("batch of 64 independent L2 proofs"): small proofs are latency chains, so one GPU holds many at once.
-// A zkb_l2_batch owns `lanes` contexts on one device (each with its streams, scratch and captured prove graph) and as many host
-// threads; proof i goes to lane i mod lanes: the thread assigns the witness (host) and proves (GPU), so the assignment of one
-// proof overlaps the device work of the others.  Key, matrices and circuit are shared, read-only.
+// BASELINE.json config 5 ("batch of 64 independent L2 proofs"; the forge coordinator's chunk-per-worker dispatch,
+// forge/crates/prover-coordinator/src/dispatcher.rs:290-330, inside one process).  Round 1 ran many small proofs side by side,
+// each a chain of ~100 short kernels at 0.02-0.1 waves.  Now a batch is cut into sub-batches of up to ZKB_L2_SUBBATCH (128)
+// proofs; a sub-batch is ASSIGNED on the host by a pool of `lanes` worker threads (Poseidon folds, comparison bits: 0.6 ms
+// per proof per core) straight into pinned memory and PROVED on the GPU by one zkb_prove_batch_begin: batched mat-vecs and
+// NTTs, five batched MSMs sharing the key's window tables, one finishing kernel.  Two device slots alternate, so the
+// assignment of sub-batch j+1 runs while the GPU proves sub-batch j.  Key, matrices and circuit are shared, read-only.
+
+namespace {
+
+class WorkerPool {
+ public:
+  explicit WorkerPool(int nthreads) {
+    for (int i = 1; i < nthreads; ++i) threads_.emplace_back([this] { loop(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : threads_)
+      if (t.joinable()) t.join();
+  }
+  // fn(i) for every i < count, on the pool's threads and the caller's; returns when all are done.  fn must not throw.
+  void parallel_for(size_t count, const std::function<void(size_t)>& fn) {
+    if (count == 0) return;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      count_ = count;
+      next_.store(0);
+      pending_ = count;
+      ++generation_;
+    }
+    cv_.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void drain() {
+    size_t finished = 0;
+    for (;;) {
+      size_t i = next_.fetch_add(1);
+      if (i >= count_) break;
+      (*fn_)(i);
+      ++finished;
+    }
+    if (finished) {
+      std::lock_guard<std::mutex> lk(mu_);
+      pending_ -= finished;
+      if (pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+      }
+      drain();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t count_ = 0, pending_ = 0;
+  std::atomic<size_t> next_{0};
+  unsigned long long generation_ = 0;
+  bool stop_ = false;
+};
+
+struct BatchSlot {
+  zkb_ctx* ctx = nullptr;
+  uint8_t* z = nullptr;       // pinned: count x nv x 32
+  uint8_t* rs = nullptr;      // pinned: count x 64
+  size_t z_cap = 0, rs_cap = 0;
+  std::vector<uint8_t> out;   // count x 256 (A | B | C)
+  size_t base = 0, count = 0;
+  bool busy = false;
+};
+
+}  // namespace
 
 struct zkb_l2_batch {
   int device = 0;
-  std::vector<zkb_ctx*> lanes;
+  int lanes = 1;
+  std::unique_ptr<WorkerPool> pool;
+  BatchSlot slots[2];
+  std::mutex mu;   // one zkb_l2_batch_prove at a time per batch object
 };
 
 int zkb_l2_batch_create(int device, int lanes, zkb_l2_batch** out) {
   if (!out || lanes < 1 || lanes > 64) return ZKB_ERR_INVALID_ARG;
   *out = nullptr;
-  zkb_l2_batch* b = new (std::nothrow) zkb_l2_batch();
-  if (!b) return ZKB_ERR_OOM;
-  b->device = device;
-  for (int i = 0; i < lanes; ++i) {
-    zkb_ctx* c = nullptr;
-    int rc = zkb_ctx_create(device, &c);
-    if (rc != ZKB_OK) {
-      g_l2_error = "zkb_l2_batch_create: zkb_ctx_create failed";
-      zkb_l2_batch_destroy(b);
-      return rc;
+  try {
+    std::unique_ptr<zkb_l2_batch> b(new zkb_l2_batch());
+    b->device = device;
+    b->lanes = lanes;
+    for (auto& s : b->slots) {
+      int rc = zkb_ctx_create(device, &s.ctx);
+      if (rc != ZKB_OK) {
+        g_l2_error = "zkb_l2_batch_create: zkb_ctx_create failed";
+        for (auto& t : b->slots)
+          if (t.ctx) zkb_ctx_destroy(t.ctx);
+        return rc;
+      }
+      zkb_ctx_set_blocking_sync(s.ctx, 1);  // the dispatcher sleeps, not spins, while the GPU works: the cores belong to the pool
     }
-    zkb_ctx_set_blocking_sync(c, 1);  // lanes usually outnumber the cores: sleep, do not spin, while the GPU works
-    b->lanes.push_back(c);
+    b->pool.reset(new WorkerPool(lanes));
+    *out = b.release();
+    return ZKB_OK;
   }
-  *out = b;
-  return ZKB_OK;
+  ZKB_L2_CATCH_ALL()
 }
 
 void zkb_l2_batch_destroy(zkb_l2_batch* b) {
   if (!b) return;
-  for (zkb_ctx* c : b->lanes) zkb_ctx_destroy(c);
+  b->pool.reset();
+  for (auto& s : b->slots) {
+    if (s.ctx) {
+      zkb_ctx_synchronize(s.ctx);
+      if (s.z) zkb_host_free_pinned(s.z);
+      if (s.rs) zkb_host_free_pinned(s.rs);
+      zkb_ctx_destroy(s.ctx);
+    }
+  }
   delete b;
 }
 
-int zkb_l2_batch_lanes(const zkb_l2_batch* b) { return b ? (int)b->lanes.size() : 0; }
+int zkb_l2_batch_lanes(const zkb_l2_batch* b) { return b ? b->lanes : 0; }
+
+static size_t l2_subbatch(size_t n) {
+  static const size_t cap = [] {
+    if (const char* e = getenv("ZKB_L2_SUBBATCH")) {
+      long v = atol(e);
+      if (v >= 1 && v <= 4096) return size_t(v);
+    }
+    return size_t(128);
+  }();
+  size_t kb = (n + 1) / 2;   // at least two sub-batches per call, so that assignment and proving overlap
+  if (kb < 16) kb = 16;
+  if (kb > cap) kb = cap;
+  return kb;
+}
 
 int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2_circuit* c,
                        const zkb_l2_public_inputs* inputs, const zkb_l2_witness* witnesses, size_t n, uint8_t* proofs_out,
                        int* status_out) {
   if (!b || !pk || !m || !c || (n && (!inputs || !witnesses || !proofs_out))) return ZKB_ERR_INVALID_ARG;
-  const size_t nl = b->lanes.size();
-  std::vector<int> first_error(nl, ZKB_OK);
-  std::vector<std::string> messages(nl);
-  auto work = [&](size_t lane) {
-    for (size_t i = lane; i < n; i += nl) {
-      int rc = zkb_l2_prove(b->lanes[lane], pk, m, c, inputs + i, witnesses + i, proofs_out + 256 * i);
-      if (status_out) status_out[i] = rc;
-      if (rc != ZKB_OK && first_error[lane] == ZKB_OK) {
-        first_error[lane] = rc;
-        messages[lane] = zkb_l2_last_error();  // thread-local of this worker
+  try {
+    std::lock_guard<std::mutex> guard(b->mu);
+    const size_t nv = l2::NUM_INSTANCE + c->num_witness;
+    if (zkb_r1cs_num_variables(m) != nv) {
+      g_l2_error = "zkb_l2_batch_prove: the matrices have " + std::to_string(zkb_r1cs_num_variables(m)) + " variables, the circuit " +
+                   std::to_string(nv);
+      return ZKB_ERR_SHAPE;
+    }
+    std::vector<int> status(n, ZKB_OK);
+    std::mutex err_mu;
+    int first_rc = ZKB_OK;
+    std::string first_msg;
+    auto note = [&](int rc, const std::string& msg) {
+      std::lock_guard<std::mutex> lk(err_mu);
+      if (first_rc == ZKB_OK) {
+        first_rc = rc;
+        first_msg = msg;
+      }
+    };
+    auto finish = [&](BatchSlot& s) {
+      if (!s.busy) return;
+      s.busy = false;
+      s.out.resize(s.count * 256);
+      int rc = zkb_prove_batch_end(s.ctx, s.count, s.out.data());
+      if (rc != ZKB_OK) {
+        note(rc, zkb_last_error(s.ctx));
+        for (size_t k = 0; k < s.count; ++k)
+          if (status[s.base + k] == ZKB_OK) status[s.base + k] = rc;
+        return;
+      }
+      for (size_t k = 0; k < s.count; ++k) {
+        if (status[s.base + k] != ZKB_OK) continue;
+        const uint8_t* r = s.out.data() + 256 * k;
+        l2_format_solana(r, r + 64, r + 192, proofs_out + 256 * (s.base + k));
+      }
+    };
+    const size_t kb = l2_subbatch(n);
+    for (size_t j = 0; j * kb < n; ++j) {
+      BatchSlot& s = b->slots[j & 1];
+      finish(s);
+      s.base = j * kb;
+      s.count = n - s.base < kb ? n - s.base : kb;
+      if (s.z_cap < s.count * nv * 32) {
+        if (s.z) zkb_host_free_pinned(s.z);
+        s.z = nullptr;
+        s.z_cap = 0;
+        void* p = nullptr;
+        int rc = zkb_host_alloc_pinned(kb * nv * 32, &p);
+        if (rc != ZKB_OK) {
+          g_l2_error = "zkb_l2_batch_prove: pinned host allocation failed";
+          return rc;
+        }
+        s.z = static_cast<uint8_t*>(p);
+        s.z_cap = kb * nv * 32;
+      }
+      if (s.rs_cap < s.count * 64) {
+        if (s.rs) zkb_host_free_pinned(s.rs);
+        s.rs = nullptr;
+        s.rs_cap = 0;
+        void* p = nullptr;
+        int rc = zkb_host_alloc_pinned(kb * 64, &p);
+        if (rc != ZKB_OK) {
+          g_l2_error = "zkb_l2_batch_prove: pinned host allocation failed";
+          return rc;
+        }
+        s.rs = static_cast<uint8_t*>(p);
+        s.rs_cap = kb * 64;
+      }
+      // host: witness assignment of the sub-batch, one proof per task, straight into the pinned staging buffer
+      std::function<void(size_t)> assign_one = [&](size_t k) {
+        const size_t i = s.base + k;
+        uint8_t* zdst = s.z + k * nv * 32;
+        int rc;
+        try {
+          std::vector<l2::Fr> z;
+          rc = l2_assign(c, inputs + i, witnesses + i, &z);
+          if (rc == ZKB_OK) {
+            if (z.size() != nv) rc = ZKB_ERR_SHAPE;
+            else l2_z_to_bytes(z, zdst);
+          }
+        } catch (const std::bad_alloc&) {
+          rc = ZKB_ERR_OOM;
+          g_l2_error = "out of host memory";
+        } catch (...) {
+          rc = ZKB_ERR_INVALID_ARG;
+          g_l2_error = "exception in the witness assignment";
+        }
+        if (rc != ZKB_OK) {
+          status[i] = rc;
+          note(rc, g_l2_error);           // thread-local message of this worker
+          memset(zdst, 0, nv * 32);       // a valid (all-zero) assignment keeps the rest of the sub-batch provable
+        }
+        zkb_l2_prover_randomness(inputs[i].batch_id, s.rs + 64 * k, s.rs + 64 * k + 32);
+      };
+      b->pool->parallel_for(s.count, assign_one);
+      int rc = zkb_prove_batch_begin(s.ctx, pk, m, s.z, s.rs, s.count);
+      if (rc != ZKB_OK) {
+        note(rc, zkb_last_error(s.ctx));
+        for (size_t k = 0; k < s.count; ++k)
+          if (status[s.base + k] == ZKB_OK) status[s.base + k] = rc;
+      } else {
+        s.busy = true;
       }
     }
-  };
-  try {
-    std::vector<std::thread> threads;
-    const size_t used = n < nl ? n : nl;
-    for (size_t lane = 1; lane < used; ++lane) threads.emplace_back(work, lane);
-    if (used) work(0);
-    for (auto& t : threads) t.join();
-  } catch (const std::exception& e) {  // std::system_error from thread creation
-    g_l2_error = e.what();
-    return ZKB_ERR_OOM;
-  }
-  for (size_t lane = 0; lane < nl; ++lane) {
-    if (first_error[lane] != ZKB_OK) {
-      g_l2_error = messages[lane];
-      return first_error[lane];  // per-proof codes are in status_out; the other proofs of the batch are valid
+    finish(b->slots[0]);
+    finish(b->slots[1]);
+    if (status_out)
+      for (size_t i = 0; i < n; ++i) status_out[i] = status[i];
+    if (first_rc != ZKB_OK) {
+      g_l2_error = first_msg;
+      return first_rc;  // per-proof codes are in status_out; the other proofs of the batch are valid
     }
+    return ZKB_OK;
   }
-  return ZKB_OK;
+  ZKB_L2_CATCH_ALL()
 }

@@ -14,8 +14,8 @@
 //     zero digits -- and every digit of a base that is the point at infinity (half of a real b_query) -- get the
 //     sentinel key, sort last and never reach the accumulation.
 // Pipeline (all on one stream, no host synchronisation; a host-scalar MSM uploads in slices that run it per slice):
-//   1. msm_digits_kernel        canonical scalars -> signed c-bit digits -> entries.
-//   2. cub::DeviceRadixSort     entries by bucket.  Library sort, HBM-bound.
+//   1-2. sort.cuh               canonical scalars -> signed c-bit digits -> entries sorted by bucket: digit extraction fused
+//                               into the first pass of an own LSD radix sort (7 bits per pass, decoupled look-back).
 //   3. msm_accumulate_kernel    the hot loop.  The sorted entry list is cut into equal chunks, one per thread, so
 //                               load balance does not depend on the scalar distribution.  A thread sums the runs
 //                               in its chunk with XYZZ mixed additions (8M+2S) on gathered 64-byte affine points;
@@ -33,10 +33,10 @@
 //                               with bit y set); no scalar multiplications, no long dependent chains.
 //   6. msm_final_kernel         one warp sums the planes with shuffles, XYZZ -> affine -> canonical bytes.
 #pragma once
-#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
 #include "internal.h"
+#include "sort.cuh"
 
 namespace zkb {
 
@@ -126,49 +126,11 @@ __global__ void __launch_bounds__(128) window_tables_kernel(Affine<F>* table, si
 }
 
 // ------------------------------------------------------------------------------------------- 1. digits
-// scalars: n x 32 bytes canonical little-endian (NOT Montgomery): what msm_bigint receives.
-// entry (w, i): keys[w * n + i] = |digit| - 1 (sentinel for 0), vals[w * n + i] = (w * table_n + first + i) | neg << 31
+// (the digits themselves are extracted inside the sort: sort.cuh)
 template <class F>
 __global__ void inf_mask_kernel(const Affine<F>* __restrict__ bases, size_t n, uint8_t* __restrict__ mask) {
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) mask[i] = load_affine(bases + i).is_inf() ? 1 : 0;
-}
-
-static __global__ void msm_digits_kernel(const uint32_t* __restrict__ scalars, size_t n, int c, int nwin, uint32_t sentinel,
-                                         size_t table_n, size_t first, const uint8_t* __restrict__ inf_mask,
-                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (inf_mask && inf_mask[first + i]) {  // s * infinity = infinity: no entries
-    for (int w = 0; w < nwin; w++) {
-      keys[size_t(w) * n + i] = sentinel;
-      vals[size_t(w) * n + i] = 0;
-    }
-    return;
-  }
-  const uint4* sp = reinterpret_cast<const uint4*>(scalars + i * 8);
-  uint4 lo = sp[0], hi = sp[1];
-  uint32_t s[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, 0u};
-  uint32_t carry = 0;
-  const uint32_t mask = (1u << c) - 1u;
-  const uint32_t half = 1u << (c - 1);
-  for (int w = 0; w < nwin; w++) {
-    int bit = w * c;
-    int word = bit >> 5, sh = bit & 31;
-    uint64_t two = (word < 8) ? (uint64_t(s[word]) | (uint64_t(s[word + 1]) << 32)) : 0ull;
-    uint32_t v = (uint32_t(two >> sh) & mask) + carry;
-    uint32_t neg = 0;
-    if (v > half) {  // digit = v - 2^c, negative
-      v = (1u << c) - v;
-      neg = 1;
-      carry = 1;
-    } else {
-      carry = 0;
-    }
-    size_t o = size_t(w) * n + i;
-    keys[o] = v ? (v - 1u) : sentinel;
-    vals[o] = uint32_t(size_t(w) * table_n + first + i) | (neg << 31);
-  }
 }
 
 // ------------------------------------------------------------------------------------------- 3. accumulate
@@ -190,22 +152,29 @@ __device__ __forceinline__ XYZZ<F> load_xyzz(const XYZZ<F>* p) {
   return r;
 }
 
+// total_dev: the number of sorted entries (known only on the device: zero digits produce no entry).  The list is cut into
+// `nthreads` equal chunks HERE, from that count, so every thread has work whatever the scalar distribution (witness-like
+// scalars are half zeros); a chunk is at least `min_chunk` entries.
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ keys,
-                      const uint32_t* __restrict__ vals, size_t total, int chunk, uint32_t sentinel,
-                      XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads, uint32_t* __restrict__ head_keys) {
+                      const uint32_t* __restrict__ vals, const uint32_t* __restrict__ total_dev, size_t nthreads, int min_chunk,
+                      uint32_t sentinel, XYZZ<F>* __restrict__ buckets, XYZZ<F>* __restrict__ heads,
+                      uint32_t* __restrict__ head_keys) {
   size_t t = size_t(blockIdx.x) * THREADS + threadIdx.x;
-  size_t start = t * size_t(chunk);
-  if (start >= total) return;
+  if (t >= nthreads) return;
+  const size_t total = *total_dev;
+  size_t chunk = (total + nthreads - 1) / nthreads;
+  if (chunk < size_t(min_chunk)) chunk = size_t(min_chunk);
+  size_t start = t * chunk;
+  if (start >= total) {
+    head_keys[t] = sentinel;
+    return;
+  }
   size_t end = start + chunk;
   if (end > total) end = total;
 
   uint32_t cur = keys[start];
-  if (cur >= sentinel) {
-    head_keys[t] = sentinel;
-    return;
-  }
   bool first_run = true;
   XYZZ<F> acc = XYZZ<F>::inf();
   // software pipeline: the point of entry j+1 is in flight while entry j is added
@@ -216,15 +185,12 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
     Affine<F> pt = nxt;
     uint32_t neg = nxt_neg;
     uint32_t k = cur;
-    bool more = false;
-    if (j + 1 < end) {
+    const bool more = j + 1 < end;
+    if (more) {
       k = keys[j + 1];
-      if (k < sentinel) {
-        uint32_t v2 = vals[j + 1];
-        nxt = load_affine(table + (v2 & 0x7fffffffu));
-        nxt_neg = v2 >> 31;
-        more = true;
-      }
+      uint32_t v2 = vals[j + 1];
+      nxt = load_affine(table + (v2 & 0x7fffffffu));
+      nxt_neg = v2 >> 31;
     }
     if (neg) pt.y = pt.y.neg();
     acc.madd(pt);
@@ -456,6 +422,86 @@ __global__ void msm_combine_kernel(const XYZZ<F>* __restrict__ parts, int k, uin
   store_affine_canonical<F>(acc.to_affine_vartime(), out_affine);
 }
 
+// ------------------------------------------------------------------------------------------- batched reduction
+// K scalar vectors against ONE table (a batch of small proofs sharing a key): bucket array = K x nbuck, keys = p * nbuck + b.
+// msm_bucket_seg_kernel runs over the flat array (S divides nbuck: segments never straddle two vectors); then one warp per
+// vector folds its nsp = nbuck / S segment records:  R_p = sum_s W[p,s] + S * sum_s s T[p,s].
+// Lane l owns the q = nsp / 32 consecutive segments s = l q + i:  sum_s s T_s = q sum_l l A_l + sum_l B_l  with
+// A_l = sum_i T_{lq+i}, B_l = sum_i i T_{lq+i} (running sums); sum_l l A_l = sum_{j>=1} (suffix sum of A at j): shuffles only.
+template <class F>
+__device__ __forceinline__ F shfl_field(const F& a, int src);
+template <>
+__device__ __forceinline__ Fq shfl_field<Fq>(const Fq& a, int src) {
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+  return r;
+}
+template <>
+__device__ __forceinline__ Fq2 shfl_field<Fq2>(const Fq2& a, int src) {
+  return {shfl_field<Fq>(a.c0, src), shfl_field<Fq>(a.c1, src)};
+}
+template <class F>
+__device__ __forceinline__ XYZZ<F> shfl_xyzz(const XYZZ<F>& p, int src) {
+  return {shfl_field<F>(p.x, src), shfl_field<F>(p.y, src), shfl_field<F>(p.zz, src), shfl_field<F>(p.zzz, src)};
+}
+// lane 0 ends with the sum over all lanes
+template <class F>
+__device__ __forceinline__ XYZZ<F> warp_sum_xyzz(XYZZ<F> v, int lane) {
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) {
+    XYZZ<F> o = shfl_xyzz(v, (lane + d) & 31);
+    if (lane < d) v.add(o);
+  }
+  return v;
+}
+
+template <class F>
+__global__ void __launch_bounds__(32)
+msm_batch_fold_kernel(const XYZZ<F>* __restrict__ W, const XYZZ<F>* __restrict__ T, int nsp, int seg_log, XYZZ<F>* __restrict__ out) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const XYZZ<F>* Wp = W + size_t(p) * nsp;
+  const XYZZ<F>* Tp = T + size_t(p) * nsp;
+  const int q = nsp >= 32 ? nsp >> 5 : 1;   // nsp is a power of two
+  const int s0 = lane * q;
+  XYZZ<F> A = XYZZ<F>::inf(), B = XYZZ<F>::inf(), Ws = XYZZ<F>::inf();
+  if (s0 < nsp) {
+    XYZZ<F> run = XYZZ<F>::inf();
+    for (int i = q - 1; i >= 1; i--) {
+      run.add(load_xyzz(Tp + s0 + i));
+      B.add(run);
+    }
+    A = run;
+    A.add(load_xyzz(Tp + s0));
+    for (int i = 0; i < q; i++) Ws.add(load_xyzz(Wp + s0 + i));
+  }
+  // suffix sums of A over the lanes, then their sum over lanes 1..31 = sum_l l A_l
+  XYZZ<F> sx = A;
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    XYZZ<F> o = shfl_xyzz(sx, (lane + d) & 31);
+    if (lane + d < 32) sx.add(o);
+  }
+  XYZZ<F> z = lane >= 1 ? sx : XYZZ<F>::inf();
+  z = warp_sum_xyzz(z, lane);
+  B = warp_sum_xyzz(B, lane);
+  Ws = warp_sum_xyzz(Ws, lane);
+  if (lane != 0) return;
+  for (int k = 1; k < q; k <<= 1) z = z.dbl();   // q sum_l l A_l
+  z.add(B);
+  for (int k = 0; k < seg_log; k++) z = z.dbl();  // S * (...)
+  z.add(Ws);
+  store_xyzz(out + p, z);
+}
+
+// XYZZ -> canonical affine bytes, one thread per point (the K results of a batched MSM)
+template <class F>
+__global__ void xyzz_to_affine_bytes_kernel(const XYZZ<F>* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  store_affine_canonical<F>(load_xyzz(in + i).to_affine_vartime(), out + i * (sizeof(Affine<F>) / 4));
+}
+
 // ------------------------------------------------------------------------------------------- driver
 template <class F>
 struct MsmTraits;
@@ -470,60 +516,68 @@ struct MsmTraits<Fq2> {
   static constexpr int THREADS_PER_SM = 256;
 };
 
-// Workspace layout of one MSM whose entries arrive in up to `nslices` slices of at most `n_slice` points each.
+// Workspace layout of one MSM (or one batch of `batch` MSMs over the same table) whose entries arrive in up to `nslices`
+// slices of at most `n_slice` points per scalar vector each.
 template <class F>
 struct MsmLayout {
   using P = XYZZ<F>;
-  int c = 0, nwin = 0, nslices = 1, key_bits = 0, row_planes = 0, col_planes = 0, seg_log = 0;
-  uint32_t nbuck = 0, sentinel = 0;
-  size_t n_slice = 0, total = 0, chunk = 0, nthreads = 0, nseg = 0, rows = 0, sort_tmp = 0, bytes = 0;
-  size_t o_k0, o_v0, o_k1, o_v1, o_tmp, o_buck, o_h0, o_hk0, o_h1, o_hk1, o_W, o_T, o_part, o_planes;
+  int c = 0, nwin = 0, nslices = 1, batch = 1, key_bits = 0, row_planes = 0, col_planes = 0, seg_log = 0, min_chunk = 16;
+  uint32_t nbuck = 0;        // buckets per scalar vector
+  uint32_t nbuck_all = 0;    // batch * nbuck: size of the bucket array; also the "no head" marker of the head lists
+  SortLayout sort;
+  size_t n_slice = 0, total = 0, nthreads = 0, nseg = 0, rows = 0, bytes = 0;
+  size_t o_hdr, o_k0, o_v0, o_k1, o_v1, o_buck, o_h0, o_hk0, o_h1, o_hk1, o_W, o_T, o_part, o_planes;
 };
 
 template <class F>
-static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, int nslices, cudaStream_t st) {
+static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, int nslices, int batch = 1) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
   MsmLayout<F> L;
   L.c = c;
   L.nwin = nwin;
   L.nslices = nslices;
+  L.batch = batch;
   L.n_slice = n_slice;
   L.nbuck = 1u << (c - 1);
-  L.sentinel = L.nbuck;
-  L.key_bits = ilog2_ceil(size_t(L.nbuck) + 1);
-  L.total = size_t(nwin) * n_slice;
-  // Equal chunks of the sorted list, one per thread, sized so that the threads fill a WHOLE number of resident waves
-  // (no partial last wave): at least 4 waves so that the block scheduler evens out per-thread variance, ~512 entries per
-  // thread when the list is long (few heads: one per thread).
+  L.nbuck_all = L.nbuck * uint32_t(batch);
+  L.key_bits = ilog2_ceil(size_t(L.nbuck_all));
+  L.total = size_t(nwin) * n_slice * size_t(batch);   // upper bound: zero digits produce no entry
+  L.sort = sort_layout(L.key_bits, n_slice * size_t(batch), nwin);
+  // The sorted list is cut into equal chunks, one per thread, with the thread count a WHOLE number of resident waves (no partial
+  // last wave): at least 4 waves so that the block scheduler evens out per-thread variance, ~512 entries per thread when the
+  // list is long (few heads: one per thread).  The chunk length itself is computed on the device from the real entry count.
   size_t resident = size_t(sm_count) * T::THREADS_PER_SM;
   size_t waves = (L.total + resident * 256) / (resident * 512);
   if (waves < 4) waves = 4;
-  L.chunk = (L.total + waves * resident - 1) / (waves * resident);
-  if (L.chunk < 16) L.chunk = 16;
-  L.nthreads = (L.total + L.chunk - 1) / L.chunk;
-  // bucket reduction: segments of S buckets, then row / column sums of the nseg segment totals and their bit planes
-  // enough segments to occupy the GPU (>= 2^13 threads) before making them long: with few buckets a 32-long segment is a
-  // 64-addition dependent chain on a handful of threads -- pure latency (it dominated small proofs)
-  L.seg_log = c - 1 - 13;
+  size_t chunk = (L.total + waves * resident - 1) / (waves * resident);
+  if (chunk < size_t(L.min_chunk)) chunk = size_t(L.min_chunk);
+  L.nthreads = (L.total + chunk - 1) / chunk;
+  if (L.nthreads == 0) L.nthreads = 1;
+  // Bucket reduction: segments of S buckets, then row / column sums of the segment totals and their bit planes.  S is chosen
+  // so that ~2^17 segments exist (one thread each: enough to fill the GPU) before segments get long: a segment is a dependent
+  // chain of 2 S additions, and at 8 GPUs (2^19 buckets per shard) the chain, not the arithmetic, was the reduction's time.
+  L.seg_log = c - 1 - 17;
   L.seg_log = L.seg_log < 1 ? 1 : (L.seg_log > MSM_SEG_LOG_MAX ? MSM_SEG_LOG_MAX : L.seg_log);
+  if (batch > 1) {
+    // batched: one warp folds nbuck / S segment records per vector; S = 32 keeps that at <= 2^(c-6) records
+    L.seg_log = c - 1 < MSM_SEG_LOG_MAX ? c - 1 : MSM_SEG_LOG_MAX;
+  }
   if (c - 1 < L.seg_log) L.seg_log = c - 1;
   const size_t S = size_t(1) << L.seg_log;
-  L.nseg = (size_t(L.nbuck) + S - 1) / S;
+  L.nseg = (size_t(L.nbuck_all) + S - 1) / S;
   L.rows = (L.nseg + (size_t(1) << MSM_COL_LOG) - 1) >> MSM_COL_LOG;
   L.row_planes = L.rows > 1 ? ilog2_ceil(L.rows) : 0;
   L.col_planes = L.nseg > 1 ? (L.nseg >= (size_t(1) << MSM_COL_LOG) ? MSM_COL_LOG : ilog2_ceil(L.nseg)) : 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, L.sort_tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, int(L.total), 0, L.key_bits, st);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off += align_up(bytes);
     return o;
   };
+  L.o_hdr = take(L.sort.hdr_bytes);
   L.o_k0 = take(L.total * 4), L.o_v0 = take(L.total * 4), L.o_k1 = take(L.total * 4), L.o_v1 = take(L.total * 4);
-  L.o_tmp = take(L.sort_tmp);
-  L.o_buck = take(size_t(L.nbuck) * sizeof(P));
+  L.o_buck = take(size_t(L.nbuck_all) * sizeof(P));
   size_t nh1 = (L.nthreads + 31) / 32;
   L.o_h0 = take(L.nthreads * sizeof(P)), L.o_hk0 = take(L.nthreads * 4);
   L.o_h1 = take(nh1 * sizeof(P)), L.o_hk1 = take(nh1 * 4);
@@ -535,52 +589,47 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   return L;
 }
 
-// Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE), accumulated into the
-// (shared) bucket array; `first_slice` clears it.
+// Stages 1-4 for one slice: points [first, first + n) of the table, scalars (device, canonical LE; vector p of a batch at
+// scalars + p * stride * 8 words), accumulated into the (shared) bucket array; `first_slice` clears it.
 template <class F>
 cudaError_t msm_accumulate_slice(zkb_ctx* ctx, const MsmLayout<F>& L, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask,
-                                 size_t first, const uint32_t* scalars, size_t n, bool first_slice) {
+                                 size_t first, const uint32_t* scalars, size_t n, size_t stride, bool first_slice) {
   using T = MsmTraits<F>;
   using P = XYZZ<F>;
   constexpr int PH0 = GroupOf<F>::PH0;
   cudaStream_t st = ctx->stream;
   char* base = static_cast<char*>(ctx->msm_ws.p);
+  uint32_t* hdr = (uint32_t*)(base + L.o_hdr);
   uint32_t *k0 = (uint32_t*)(base + L.o_k0), *v0 = (uint32_t*)(base + L.o_v0);
   uint32_t *k1 = (uint32_t*)(base + L.o_k1), *v1 = (uint32_t*)(base + L.o_v1);
   P* buckets = (P*)(base + L.o_buck);
   P* hp[2] = {(P*)(base + L.o_h0), (P*)(base + L.o_h1)};
   uint32_t* hk[2] = {(uint32_t*)(base + L.o_hk0), (uint32_t*)(base + L.o_hk1)};
-  const size_t total = size_t(L.nwin) * n;
-  const size_t nthreads = (total + L.chunk - 1) / L.chunk;
-  {
-    ProfScope ps(ctx, PH0 + 0);
-    msm_digits_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(scalars, n, L.c, L.nwin, L.sentinel, table_n, first, inf_mask, k0, v0);
-    ctx->launches++;
-  }
+  const uint32_t *sk = nullptr, *sv = nullptr;
   {
     ProfScope ps(ctx, PH0 + 1);
-    size_t tmp = L.sort_tmp;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(base + L.o_tmp, tmp, k0, k1, v0, v1, int(total), 0, L.key_bits, st);
+    EntrySource src{scalars, n, stride, L.batch, L.c, L.nwin, L.nbuck, table_n, first, inf_mask};
+    SortLayout sl = sort_layout(L.key_bits, n * size_t(L.batch), L.nwin);   // this slice's tile counts; buffers sized by L.sort
+    cudaError_t e = msm_sort_entries(src, sl, ctx->sm_count, hdr, k0, v0, k1, v1, st, &sk, &sv, &ctx->launches);
     if (e != cudaSuccess) return e;
   }
-  if (first_slice) cudaMemsetAsync(buckets, 0, size_t(L.nbuck) * sizeof(P), st);
-  cudaMemsetAsync(hk[0], 0xff, nthreads * 4, st);
+  if (first_slice) cudaMemsetAsync(buckets, 0, size_t(L.nbuck_all) * sizeof(P), st);
   {
     ProfScope ps(ctx, PH0 + 2);
-    unsigned acc_blocks = unsigned((nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
-    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(table, k1, v1, total, int(L.chunk), L.sentinel,
-                                                                                  buckets, hp[0], hk[0]);
+    unsigned acc_blocks = unsigned((L.nthreads + T::ACC_THREADS - 1) / T::ACC_THREADS);
+    msm_accumulate_kernel<F, T::ACC_THREADS><<<acc_blocks, T::ACC_THREADS, 0, st>>>(
+        table, sk, sv, hdr + SortHeader::TOTAL, L.nthreads, L.min_chunk, L.nbuck_all, buckets, hp[0], hk[0]);
     ctx->launches++;
   }
   {
     ProfScope ps(ctx, PH0 + 3);
     // heads: 32x per level; the last level (<= 32 heads) folds everything into the buckets
-    size_t count = nthreads;
+    size_t count = L.nthreads;
     int cur = 0;
     while (true) {
       int last = count <= 32 ? 1 : 0;
       size_t nw = (count + 31) / 32;
-      msm_heads_warp_kernel<F><<<unsigned((nw * 32 + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, L.sentinel, buckets,
+      msm_heads_warp_kernel<F><<<unsigned((nw * 32 + 63) / 64), 64, 0, st>>>(hp[cur], hk[cur], count, L.nbuck_all, buckets,
                                                                           hp[cur ^ 1], hk[cur ^ 1], last);
       ctx->launches++;
       if (last) break;
@@ -604,7 +653,19 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
   P* part = (P*)(base + L.o_part);
   P* planes = (P*)(base + L.o_planes);
   ProfScope ps(ctx, PH0 + 3);
-  msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck, W, Tt, L.nseg, L.seg_log);
+  msm_bucket_seg_kernel<F><<<unsigned((L.nseg + 63) / 64), 64, 0, st>>>(buckets, L.nbuck_all, W, Tt, L.nseg, L.seg_log);
+  if (L.batch > 1) {
+    // out_xyzz: `batch` partial sums; out_affine: `batch` canonical affine points
+    P* res = out_xyzz ? out_xyzz : part;   // part holds 2 rows + 256 >= batch records only when batch <= 256: see msm_run_batch
+    const int nsp = int(L.nbuck >> L.seg_log);
+    msm_batch_fold_kernel<F><<<unsigned(L.batch), 32, 0, st>>>(W, Tt, nsp, L.seg_log, res);
+    ctx->launches += 2;
+    if (out_affine) {
+      xyzz_to_affine_bytes_kernel<F><<<unsigned((L.batch + 63) / 64), 64, 0, st>>>(res, size_t(L.batch), out_affine);
+      ctx->launches++;
+    }
+    return cudaGetLastError();
+  }
   msm_rowcol_kernel<F, 64><<<msm_rowcol_blocks<64>(L.rows), 64, 0, st>>>(Tt, W, L.nseg, L.rows, part);
   const int nplanes = L.row_planes > L.col_planes ? L.row_planes : L.col_planes;  // planes beyond these sum nothing and are not read
   msm_plane_kernel<F, 64><<<dim3(nplanes > 0 ? nplanes : 1, 3), 64, 0, st>>>(part, L.rows, planes);
@@ -625,11 +686,36 @@ cudaError_t msm_run(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, const 
     if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>), st);
     return cudaGetLastError();
   }
-  if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
-  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1, st);
+  if (size_t(nwin) * n >= (size_t(1) << 30) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1);
   cudaError_t e = ctx->msm_ws.reserve(L.bytes);
   if (e != cudaSuccess) return e;
-  e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first, scalars, n, true);
+  e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first, scalars, n, n, true);
+  if (e != cudaSuccess) return e;
+  return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
+}
+
+// `batch` MSMs over the SAME bases [first, first + n): scalar vector p at scalars + p * stride * 8 words.  One sort, one
+// accumulation, one reduction for all of them (a batch of small proofs sharing a proving key; per-vector bucket arrays).
+// out_xyzz: batch x XYZZ (may be null); out_affine: batch x canonical affine (may be null).
+template <class F>
+cudaError_t msm_run_batch(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask, int c, int nwin, size_t first,
+                          const uint32_t* scalars, size_t n, size_t stride, int batch, XYZZ<F>* out_xyzz, uint32_t* out_affine) {
+  cudaStream_t st = ctx->stream;
+  if (batch < 1) return cudaErrorInvalidValue;
+  if (batch == 1) return msm_run<F>(ctx, table, table_n, inf_mask, c, nwin, first, scalars, n, out_xyzz, out_affine);
+  if (n == 0) {
+    if (out_xyzz) cudaMemsetAsync(out_xyzz, 0, sizeof(XYZZ<F>) * batch, st);
+    if (out_affine) cudaMemsetAsync(out_affine, 0, sizeof(Affine<F>) * batch, st);
+    return cudaGetLastError();
+  }
+  if (size_t(nwin) * n * size_t(batch) >= (size_t(1) << 30) || size_t(nwin) * table_n >= (size_t(1) << 31) ||
+      (size_t(batch) << (c - 1)) > (size_t(1) << 27) || (!out_xyzz && batch > 256))
+    return cudaErrorInvalidValue;
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, n, 1, batch);
+  cudaError_t e = ctx->msm_ws.reserve(L.bytes);
+  if (e != cudaSuccess) return e;
+  e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first, scalars, n, stride, true);
   if (e != cudaSuccess) return e;
   return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
 }
@@ -640,7 +726,7 @@ template <class F>
 cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, const uint8_t* inf_mask, int c, int nwin, size_t first,
                                 const uint8_t* scalars_host, uint32_t* scalars_dev, size_t n, int nslices,
                                 XYZZ<F>* out_xyzz, uint32_t* out_affine) {
-  if (size_t(nwin) * n >= (size_t(1) << 31) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
+  if (size_t(nwin) * n >= (size_t(1) << 30) || size_t(nwin) * table_n >= (size_t(1) << 31)) return cudaErrorInvalidValue;
   // Slice k+1 is three times slice k: accumulating a point takes ~4x longer than copying its scalar, so every upload after
   // the (small) first one hides behind the previous slice's compute.
   if (nslices > ZKB_MAX_SLICES - 1) nslices = ZKB_MAX_SLICES - 1;
@@ -661,7 +747,7 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
   size_t per = 0;
   for (int k = 0; k < nslices; k++)
     if (bound[k + 1] - bound[k] > per) per = bound[k + 1] - bound[k];
-  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, per, nslices, ctx->stream);
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, c, nwin, per, nslices);
   cudaError_t e = ctx->msm_ws.reserve(L.bytes);
   if (e != cudaSuccess) return e;
   if (!ctx->copy_stream) {
@@ -685,11 +771,11 @@ cudaError_t msm_run_host_sliced(zkb_ctx* ctx, const Affine<F>* table, size_t tab
     size_t lo = bound[k], cnt = bound[k + 1] - bound[k];
     cudaStreamWaitEvent(ctx->stream, ctx->copy_done[k], 0);
     if (!cnt) continue;
-    e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first + lo, scalars_dev + lo * 8, cnt, used == 0);
+    e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first + lo, scalars_dev + lo * 8, cnt, cnt, used == 0);
     if (e != cudaSuccess) return e;
     used++;
   }
-  if (!used) cudaMemsetAsync(static_cast<char*>(ctx->msm_ws.p) + L.o_buck, 0, size_t(L.nbuck) * sizeof(XYZZ<F>), ctx->stream);
+  if (!used) cudaMemsetAsync(static_cast<char*>(ctx->msm_ws.p) + L.o_buck, 0, size_t(L.nbuck_all) * sizeof(XYZZ<F>), ctx->stream);
   return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
 }
 

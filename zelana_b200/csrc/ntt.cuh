@@ -132,6 +132,9 @@ ntt_pass_kernel(NttPassArgs a) {
   constexpr int NT = NE / 2 < 32 ? 32 : NE / 2;    // threads per block
   __shared__ uint4 p0[NE], p1[NE];                 // SoA halves: conflict-free 16 B accesses
 
+  // blockIdx.y: which polynomial of a batch (each n elements long, back to back in both buffers)
+  a.in += size_t(blockIdx.y) << a.logn;
+  a.out += size_t(blockIdx.y) << a.logn;
   const size_t nq = size_t(1) << (a.logn - LR);    // columns = n / R
   const size_t q0 = size_t(blockIdx.x) * TQ;
   const int logB = a.logn - a.logm;

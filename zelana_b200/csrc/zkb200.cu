@@ -5,6 +5,7 @@
 
 #include <cstdlib>
 #include <initializer_list>
+#include <mutex>
 #include <utility>
 
 using namespace zkb;
@@ -33,6 +34,7 @@ int check_flag(zkb_ctx* ctx, const char* what) {
   if (h == 2) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: point not on curve", what);
   if (h == 3) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: both the infinity and the sign flag are set", what);
   if (h == 4) ZKB_FAIL(ctx, ZKB_ERR_NOT_CANONICAL, "%s: point not in the prime-order subgroup", what);
+  if (h != 0) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "%s: unexpected device status flag %d", what, h);
   return ZKB_OK;
 }
 
@@ -52,11 +54,17 @@ int set_device(zkb_ctx* ctx) {
 // =============================================================================================== context
 extern "C" const char* zkb_version(void) { return "zkb200 0.2 (sm_100a)"; }
 
+// A prove runs on up to six streams and batches use several lanes per GPU: with the default 8 hardware queues, streams alias
+// and a long single-block kernel of one proof stalls the others.  CUDA reads CUDA_DEVICE_MAX_CONNECTIONS once, when the
+// process creates its CUDA context, so the host should export it before its first CUDA call (for Python hosts
+// zelana_b200/__init__.py does).  As a convenience the FIRST zkb_ctx_create of a process sets it if the user has not -- once,
+// under std::call_once (setenv is not safe against concurrent getenv in a threaded host, so never from a query function).
+static void max_connections_once() {
+  static std::once_flag once;
+  std::call_once(once, [] { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); });
+}
+
 extern "C" int zkb_device_count(void) {
-  // A prove runs on up to six streams and small proofs are served by several contexts per GPU: with the default 8 hardware
-  // queues, streams alias and a long single-block kernel of one proof stalls the others.  Effective only if this process has
-  // not created its CUDA context yet (zelana_b200/__init__.py sets it for Python hosts as well); never overrides the user.
-  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
     cudaGetLastError();
@@ -68,6 +76,7 @@ extern "C" int zkb_device_count(void) {
 extern "C" int zkb_ctx_create(int device, zkb_ctx** out) {
   if (!out) return ZKB_ERR_INVALID_ARG;
   *out = nullptr;
+  max_connections_once();
   int n = zkb_device_count();
   if (n <= 0 || device < 0 || device >= n) return ZKB_ERR_NO_DEVICE;
   zkb_ctx* ctx = new (std::nothrow) zkb_ctx();
@@ -132,6 +141,8 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   if (ctx->ev_inputs) cudaEventDestroy(ctx->ev_inputs);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->bpinned) cudaFreeHost(ctx->bpinned);
+  for (DevBuf* b : {&ctx->bz, &ctx->bzm, &ctx->bw3, &ctx->bh, &ctx->brs, &ctx->bpart, &ctx->bout}) b->release();
   DevBuf* bufs[] = {&ctx->scal, &ctx->res, &ctx->tmp0, &ctx->tmp1, &ctx->tmp2, &ctx->flag, &ctx->pz, &ctx->pzm, &ctx->pwa,
                     &ctx->pwb, &ctx->pwc, &ctx->ph, &ctx->pza, &ctx->pzl, &ctx->prs, &ctx->ppts, &ctx->pzsa, &ctx->pzrb};
   for (DevBuf* b : bufs) b->release();
@@ -151,6 +162,21 @@ extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+// Page-locked host memory for buffers the GPU reads or writes asynchronously (assignments of a batch, results).
+extern "C" int zkb_host_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return ZKB_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    *out = nullptr;
+    return ZKB_ERR_OOM;
+  }
+  return ZKB_OK;
+}
+extern "C" void zkb_host_free_pinned(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 extern "C" const char* zkb_last_error(zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -265,6 +291,18 @@ extern "C" int zkb_g1_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, 
 extern "C" int zkb_g2_bases_generate(zkb_ctx* ctx, const void* k_dev, size_t n, zkb_g2_bases** out) {
   return bases_generate_impl<Fq2>(ctx, k_dev, n, out);
 }
+extern "C" int zkb_g1_bases_window(const zkb_g1_bases* b, int* c, int* nwin) {
+  if (!b) return ZKB_ERR_INVALID_ARG;
+  if (c) *c = b->c;
+  if (nwin) *nwin = b->nwin;
+  return ZKB_OK;
+}
+extern "C" int zkb_g2_bases_window(const zkb_g2_bases* b, int* c, int* nwin) {
+  if (!b) return ZKB_ERR_INVALID_ARG;
+  if (c) *c = b->c;
+  if (nwin) *nwin = b->nwin;
+  return ZKB_OK;
+}
 extern "C" size_t zkb_g1_bases_len(const zkb_g1_bases* b) { return b ? b->n : 0; }
 extern "C" size_t zkb_g2_bases_len(const zkb_g2_bases* b) { return b ? b->n : 0; }
 extern "C" int zkb_g1_bases_read(zkb_ctx* ctx, const zkb_g1_bases* b, size_t off, size_t n, uint8_t* o) {
@@ -291,6 +329,21 @@ extern "C" int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_g2_bases* b, size_t off, c
 }
 extern "C" int zkb_msm_g1_combine(zkb_ctx* ctx, const void* parts, int k, void* out) { return msm_combine_impl<Fq>(ctx, parts, k, out); }
 extern "C" int zkb_msm_g2_combine(zkb_ctx* ctx, const void* parts, int k, void* out) { return msm_combine_impl<Fq2>(ctx, parts, k, out); }
+
+// parity hook for the batched MSM (msm_run_batch): `batch` scalar vectors, vector p at scalars_dev + p * stride * 32 bytes,
+// against bases [offset, offset + n) -> batch canonical affine points (device).  group: 1 = G1, 2 = G2.
+extern "C" int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, size_t offset, const void* scalars_dev, size_t n,
+                                   size_t stride, int batch, void* out_affine_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if ((group != 1 && group != 2) || !bases || !out_affine_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_debug_msm_batch: bad argument");
+  ZKB_TRY(set_device(ctx));
+  void* part = nullptr;
+  const size_t psz = group == 1 ? sizeof(XYZZ<Fq>) : sizeof(XYZZ<Fq2>);
+  CUDA_TRY(ctx, ctx->bpart.reserve(size_t(batch > 0 ? batch : 1) * psz));
+  part = ctx->bpart.p;
+  return group == 1 ? msm_batch_dev_impl<Fq>(ctx, static_cast<const zkb_g1_bases*>(bases), offset, scalars_dev, n, stride, batch, out_affine_dev, part)
+                    : msm_batch_dev_impl<Fq2>(ctx, static_cast<const zkb_g2_bases*>(bases), offset, scalars_dev, n, stride, batch, out_affine_dev, part);
+}
 
 // =============================================================================================== NTT
 extern "C" int zkb_ntt_dev(zkb_ctx* ctx, const void* in_dev, void* out_dev, int log_n, int direction, int coset) {
@@ -393,6 +446,8 @@ extern "C" void zkb_r1cs_free(zkb_r1cs* m) {
 }
 
 extern "C" int zkb_r1cs_log_domain(const zkb_r1cs* m) { return m ? m->log_domain : -1; }
+extern "C" uint64_t zkb_r1cs_num_variables(const zkb_r1cs* m) { return m ? m->ni + m->nw : 0; }
+extern "C" uint64_t zkb_r1cs_num_constraints(const zkb_r1cs* m) { return m ? m->nc : 0; }
 
 
 static int reserve_prove_bufs(zkb_ctx* ctx, size_t n, size_t nv, size_t nw) {
@@ -466,6 +521,8 @@ extern "C" void zkb_pk_free(zkb_pk* pk) {
   zkb_g1_bases_free(pk->l_ext);
   zkb_g1_bases_free(pk->h);
   zkb_g2_bases_free(pk->b2_ext);
+  if (pk->fb_delta1) cudaFree(pk->fb_delta1);
+  if (pk->fb_delta2) cudaFree(pk->fb_delta2);
   delete pk;
 }
 
@@ -1040,6 +1097,159 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
 }
 
 }  // namespace
+
+// =============================================================================================== batched prove
+namespace {
+
+struct BatchOut {
+  XYZZ<Fq>*pA, *pB1, *pL, *pH;
+  XYZZ<Fq2>* pB2;
+};
+
+BatchOut batch_out(zkb_ctx* ctx, size_t K) {
+  BatchOut o;
+  o.pA = ctx->bpart.as<XYZZ<Fq>>();
+  o.pB1 = o.pA + K;
+  o.pL = o.pA + 2 * K;
+  o.pH = o.pA + 3 * K;
+  o.pB2 = reinterpret_cast<XYZZ<Fq2>*>(o.pA + 4 * K);
+  return o;
+}
+
+int ensure_lanes(zkb_ctx* ctx) {
+  if (ctx->ev_inputs) return ZKB_OK;
+  for (auto& lane : ctx->aux) {
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&lane.stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaEventCreateWithFlags(&lane.done, cudaEventDisableTiming));
+  }
+  CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_inputs, cudaEventDisableTiming));
+  return ZKB_OK;
+}
+
+}  // namespace
+
+// K proofs of ONE circuit with ONE key, as one set of fat launches instead of K chains of small ones (ark-groth16
+// create_proof_with_reduction_and_matrices x K; the data-parallel analogue of the forge coordinator's chunk-per-worker
+// dispatch, forge/crates/prover-coordinator/src/dispatcher.rs:290-330): batched mat-vecs and NTTs (3 K polynomials per
+// launch), five batched MSMs (K scalar vectors against one window table, per-proof bucket arrays: msm_run_batch) on five
+// lanes, and one finishing kernel per group.  Asynchronous: _begin queues everything on ctx's streams including the copy of
+// the K x 256 B results into pinned memory; _end waits and hands them out.  z_host and rs_host must stay valid until _end.
+extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
+                                     size_t K) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!pk_c || !m || !z_host || !rs_host || K < 1 || K > 4096) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: bad argument (1 <= K <= 4096)");
+  zkb_pk* pk = const_cast<zkb_pk*>(pk_c);   // the delta tables are built on first use
+  if (pk->world != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: sharded key");
+  if (pk->device != ctx->device || m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: key/matrices on another device");
+  const size_t nv = m->ni + m->nw, nw = m->nw, ni = m->ni;
+  const size_t n = size_t(1) << m->log_domain;
+  if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove_batch: key has %zu variables, circuit has %zu", pk->nv, nv);
+  if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove_batch: l_query has %zu points, circuit has %zu witness variables", pk->nw, nw);
+  ZKB_TRY(set_device(ctx));
+  cudaStream_t st = ctx->stream;
+  ZKB_TRY(ensure_lanes(ctx));
+  if (!pk->fb_delta1) {
+    // delta_g1 / delta_g2 are the last base of a_ext / b2_ext.  Built once per key; the build runs on this context's stream and
+    // is complete before any later work of this stream.  (Contexts sharing a key: call one batched prove before going wide.)
+    void *t1 = nullptr, *t2 = nullptr;
+    ZKB_TRY(fixed_table_for_base<Fq>(ctx, pk->a_ext, nv + 1, &t1));
+    int rc = fixed_table_for_base<Fq2>(ctx, pk->b2_ext, nv + 1, &t2);
+    if (rc != ZKB_OK) {
+      cudaFree(t1);
+      return rc;
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    pk->fb_delta2 = t2;
+    pk->fb_delta1 = t1;
+  }
+  CUDA_TRY(ctx, ctx->bz.reserve(K * nv * 32));
+  CUDA_TRY(ctx, ctx->bzm.reserve(K * nv * 32));
+  CUDA_TRY(ctx, ctx->bw3.reserve(3 * K * n * 32));
+  CUDA_TRY(ctx, ctx->bh.reserve(K * n * 32));
+  CUDA_TRY(ctx, ctx->brs.reserve(K * 64));
+  CUDA_TRY(ctx, ctx->bpart.reserve(K * (4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>))));
+  CUDA_TRY(ctx, ctx->bout.reserve(K * 256));
+  if (ctx->bpinned_cap < K * 256) {
+    if (ctx->bpinned) cudaFreeHost(ctx->bpinned);
+    ctx->bpinned = nullptr;
+    ctx->bpinned_cap = 0;
+    CUDA_TRY(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->bpinned), K * 256, cudaHostAllocDefault));
+    ctx->bpinned_cap = K * 256;
+  }
+  Fr* z = ctx->bz.as<Fr>();
+  Fr* rs = ctx->brs.as<Fr>();
+  ZKB_TRY(clear_flag(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(z, z_host, K * nv * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(rs, rs_host, K * 64, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, st));
+  BatchOut o = batch_out(ctx, K);
+  // A, B1, B2, L depend on z only: four lanes next to the witness maps + H on the main stream
+  int lane_rc = ZKB_OK;
+  bool lane_used[5] = {false, false, false, false, false};
+  auto on_lane = [&](int idx, auto&& fn) {
+    auto& lane = ctx->aux[idx];
+    if (lane_rc != ZKB_OK) return;
+    if (cudaStreamWaitEvent(lane.stream, ctx->ev_inputs, 0) != cudaSuccess) {
+      lane_rc = ZKB_ERR_CUDA;
+      return;
+    }
+    lane_used[idx] = true;
+    std::swap(ctx->stream, lane.stream);
+    std::swap(ctx->msm_ws, lane.ws);
+    int rc = fn();
+    if (rc == ZKB_OK && cudaEventRecord(lane.done, ctx->stream) != cudaSuccess) rc = ZKB_ERR_CUDA;
+    std::swap(ctx->stream, lane.stream);
+    std::swap(ctx->msm_ws, lane.ws);
+    if (rc != ZKB_OK) lane_rc = rc;
+  };
+  const int Ki = int(K);
+  on_lane(0, [&] { return msm_batch_dev_impl<Fq2>(ctx, pk->b2_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pB2); });
+  on_lane(1, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->a_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pA); });
+  on_lane(2, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->b1_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pB1); });
+  on_lane(3, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->l_ext, 0, z + ni, nw, nv, Ki, nullptr, o.pL); });
+  int mrc = ZKB_OK;
+  if (lane_rc == ZKB_OK) {
+    mrc = witness_map_batch_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, Ki, z, ctx->bzm.as<Fr>(), ctx->bw3.as<Fr>(),
+                                ctx->bh.as<Fr>());
+    size_t hn = pk->nh < n ? pk->nh : n;
+    if (mrc == ZKB_OK) mrc = msm_batch_dev_impl<Fq>(ctx, pk->h, 0, ctx->bh.as<Fr>(), hn, n, Ki, nullptr, o.pH);
+  }
+  bool joined = true;
+  for (int i = 0; i < 5; i++)
+    if (lane_used[i] && cudaStreamWaitEvent(st, ctx->aux[i].done, 0) != cudaSuccess) joined = false;
+  if (lane_rc != ZKB_OK || mrc != ZKB_OK || !joined) {
+    cudaGetLastError();
+    for (auto& lane : ctx->aux) cudaStreamSynchronize(lane.stream);
+    cudaStreamSynchronize(st);
+    if (lane_rc == ZKB_ERR_CUDA || !joined) ctx->err = "zkb_prove_batch: CUDA error while queueing the MSM lanes";
+    return lane_rc != ZKB_OK ? lane_rc : (mrc != ZKB_OK ? mrc : ZKB_ERR_CUDA);
+  }
+  const Affine<Fq>* a_tail = pk->a_ext->p + (nv - 1);     // a_query[0], alpha_g1, delta_g1
+  const Affine<Fq>* b1_tail = pk->b1_ext->p + (nv - 1);   // b_g1_query[0], beta_g1, delta_g1
+  const Affine<Fq2>* b2_tail = pk->b2_ext->p + (nv - 1);  // b_g2_query[0], beta_g2, delta_g2
+  ZKB_TRY(prove_batch_finish_g1(ctx, Ki, o.pA, o.pB1, o.pL, o.pH, rs, a_tail, b1_tail, pk->fb_delta1, ctx->bout.p));
+  ZKB_TRY(prove_batch_finish_g2(ctx, Ki, o.pB2, rs, b2_tail, pk->fb_delta2, ctx->bout.p));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->bpinned, ctx->bout.p, K * 256, cudaMemcpyDeviceToHost, st));
+  return ZKB_OK;
+}
+
+// out: K x 256 B, proof i = A (64) | B (128) | C (64) canonical affine, A not negated -- three zkb_prove outputs back to back.
+extern "C" int zkb_prove_batch_end(zkb_ctx* ctx, size_t K, uint8_t* out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out || K * 256 > ctx->bpinned_cap) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch_end: no batch of %zu proofs in flight", K);
+  ZKB_TRY(set_device(ctx));
+  int rc = check_flag(ctx, "witness assignment");   // waits for the stream
+  if (rc != ZKB_OK) return rc;
+  memcpy(out, ctx->bpinned, K * 256);
+  return ZKB_OK;
+}
+
+extern "C" int zkb_prove_batch(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host, size_t K,
+                               uint8_t* out) {
+  int rc = zkb_prove_batch_begin(ctx, pk, m, z_host, rs_host, K);
+  if (rc != ZKB_OK) return rc;
+  return zkb_prove_batch_end(ctx, K, out);
+}
 
 extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t r[32],
                          const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {

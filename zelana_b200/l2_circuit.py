@@ -179,6 +179,9 @@ class L2Circuit:
         return z.raw
 
     def is_satisfied(self, z: bytes):
+        want = (self.num_instance + self.num_witness) * 32
+        if len(z) != want:
+            raise ZkbError(-6, "assignment has %d bytes, this circuit needs %d" % (len(z), want))
         ok, row = C.c_int(0), C.c_uint64(0)
         _check(self.lib.zkb_l2_circuit_is_satisfied(self.h, z, C.byref(ok), C.byref(row)))
         return bool(ok.value), (None if ok.value else int(row.value))

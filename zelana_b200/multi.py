@@ -33,15 +33,31 @@ class GpuMsmEngine:
         self._part = torch.zeros(self.partial_bytes, dtype=torch.uint8, device=self.device)
         self._out = torch.zeros(self.affine_bytes, dtype=torch.uint8, device=self.device)
 
+    def _shares_torch_stream(self):
+        return self.ctx.stream_handle is not None and self.ctx.stream_handle == torch.cuda.current_stream(self.device).cuda_stream
+
     def msm_partial(self, scalars_dev, n):
-        """scalars_dev: CUDA tensor of n x 32 B canonical scalars for THIS rank's range -> partial-sum tensor."""
+        """scalars_dev: CUDA tensor of n x 32 B canonical scalars for THIS rank's range -> partial-sum tensor.
+        The library queues its kernels on the Context's stream; the collective that follows runs on torch's current stream.
+        Unless the two are the same stream (Context(device, stream=torch stream), as bench.py does) they must be ordered here:
+        scalars written by torch before the MSM reads them, the partial sum complete before NCCL gathers it."""
+        shared = self._shares_torch_stream()
+        if not shared:
+            torch.cuda.current_stream(self.device).synchronize()
         fn = self.ctx.msm_g1_dev if self.group == 1 else self.ctx.msm_g2_dev
         fn(self.bases, scalars_dev, n, out_partial_dev=self._part)
+        if not shared:
+            self.ctx.synchronize()
         return self._part
 
     def combine(self, parts, k):
+        shared = self._shares_torch_stream()
+        if not shared:
+            torch.cuda.current_stream(self.device).synchronize()   # the all-gather that filled `parts`
         fn = self.ctx.msm_g1_combine if self.group == 1 else self.ctx.msm_g2_combine
         fn(parts, k, self._out)
+        if not shared:
+            self.ctx.synchronize()
         return self._out
 
 
