@@ -126,6 +126,21 @@ int zkb_msm_g1_dev(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const
                    void* out_affine_dev, void* out_partial_dev);
 int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_g2_bases* bases, size_t offset, const void* scalars_dev, size_t n,
                    void* out_affine_dev, void* out_partial_dev);
+/* Host scalars in, projective partial sum out (device memory, asynchronous on ctx's stream): one rank's share of a
+ * range-sharded MSM with the sliced upload pipeline of zkb_msm_g1; feed the partials of all ranks to zkb_msm_g{1,2}_combine. */
+int zkb_msm_g1_partial(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+                       void* out_partial_dev);
+int zkb_msm_g2_partial(zkb_ctx* ctx, const zkb_g2_bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+                       void* out_partial_dev);
+/* The whole multi-GPU MSM behind one call, no torch / NCCL needed (SURVEY.md 8b `zkb_msm_g1_multi`, 8e): one process, one
+ * context per GPU; bases[i] (loaded on ctxs[i]) holds range i of the points, in order, and the n = sum_i len(bases[i]) host
+ * scalars are split the same way.  Each GPU runs its partial MSM from its own host thread (sliced upload overlapped with the
+ * accumulation); the n_gpus partial sums (128 / 256 B) are gathered through host memory and added on ctxs[0].
+ * What a Rust `GpuGroth16Prover` holding one context per device calls (core/src/sequencer/settlement/prover.rs:160-169). */
+int zkb_msm_g1_multi(zkb_ctx* const* ctxs, const zkb_g1_bases* const* bases, int n_gpus, const uint8_t* scalars_host, size_t n,
+                     uint8_t out_affine_host[64]);
+int zkb_msm_g2_multi(zkb_ctx* const* ctxs, const zkb_g2_bases* const* bases, int n_gpus, const uint8_t* scalars_host, size_t n,
+                     uint8_t out_affine_host[128]);
 /* Multi-GPU combine: k partial sums (gathered from k ranks, device memory) -> canonical affine (device). */
 int zkb_msm_g1_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
 int zkb_msm_g2_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_affine_dev);
@@ -134,6 +149,11 @@ int zkb_msm_g2_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_
  * (bases: the matching handle type). */
 int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
                         int batch, void* out_affine_dev);
+/* Parity hook for the MSM front end (signed-digit extraction fused with the radix sort): the entries of `batch` scalar vectors
+ * sorted by key = vector * 2^(c-1) + |digit| - 1, value = table index | sign << 31.  out_keys_dev / out_vals_dev: device
+ * buffers of windows * n * batch u32 each; out_count_dev: one u32 = number of entries (zero digits produce none). */
+int zkb_debug_msm_entries(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
+                          int batch, void* out_keys_dev, void* out_vals_dev, void* out_count_dev);
 #define ZKB_G1_PARTIAL_BYTES 128
 #define ZKB_G2_PARTIAL_BYTES 256
 
@@ -247,6 +267,13 @@ int zkb_prove_partial(zkb_ctx* ctx, const zkb_pk* pk_shard, const zkb_r1cs* m, c
                       const uint8_t s[32], void* out_partial_dev);
 int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int world, const uint8_t r[32], const uint8_t s[32],
                       uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]);
+
+/* The same behind one call for a single-process host (no torch / NCCL): ctxs[i] is on GPU i, pk_shards[i] =
+ * zkb_pk_load_shard(ctxs[i], desc, validate, i, n_gpus), ms[i] = the matrices loaded on ctxs[i].  Every GPU proves its share from
+ * its own host thread; the partial records are gathered through host memory; ctxs[0] finishes. */
+int zkb_prove_multi(zkb_ctx* const* ctxs, const zkb_pk* const* pk_shards, const zkb_r1cs* const* ms, int n_gpus,
+                    const uint8_t* z_host, const uint8_t r[32], const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128],
+                    uint8_t out_c[64]);
 
 /* ---- the L2 batch circuit on the host: prover/src/l2_circuit.rs (8f.3) ----------------------
  * What `Groth16Prover::prove` (core/src/sequencer/settlement/prover.rs:350-425) does around the arkworks call, natively:

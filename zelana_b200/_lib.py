@@ -103,9 +103,14 @@ SIGNATURES = {
     "zkb_msm_g2": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
     "zkb_msm_g1_dev": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P]),
     "zkb_msm_g2_dev": (_I, [_P, _P, _SZ, _P, _SZ, _P, _P]),
+    "zkb_msm_g1_partial": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
+    "zkb_msm_g2_partial": (_I, [_P, _P, _SZ, _P, _SZ, _P]),
+    "zkb_msm_g1_multi": (_I, [C.POINTER(_P), C.POINTER(_P), _I, _P, _SZ, _P]),
+    "zkb_msm_g2_multi": (_I, [C.POINTER(_P), C.POINTER(_P), _I, _P, _SZ, _P]),
     "zkb_msm_g1_combine": (_I, [_P, _P, _I, _P]),
     "zkb_msm_g2_combine": (_I, [_P, _P, _I, _P]),
     "zkb_debug_msm_batch": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZ, _I, _P]),
+    "zkb_debug_msm_entries": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _I, _P, _P, _P]),
     "zkb_ntt": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_ntt_dev": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_r1cs_load": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(_P)]),
@@ -127,6 +132,7 @@ SIGNATURES = {
     "zkb_pk_synthetic_shard": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, _I, _I, C.POINTER(_P)]),
     "zkb_prove_partial": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "zkb_prove_combine": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "zkb_prove_multi": (_I, [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _I, _P, _P, _P, _P, _P, _P]),
     "zkb_l2_last_error": (C.c_char_p, []),
     "zkb_l2_circuit_create": (_I, [C.POINTER(L2Witness), C.POINTER(_P)]),
     "zkb_l2_circuit_free": (None, [_P]),

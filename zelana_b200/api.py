@@ -179,6 +179,19 @@ class Context:
         self._check(self.lib.zkb_msm_g2_dev(self.h, bases.h, offset, _devptr(scalars_dev), n,
                                             _devptr(out_affine_dev), _devptr(out_partial_dev)))
 
+    def msm_g1_partial(self, bases, scalars, out_partial_dev, offset=0):
+        """Host scalars -> this rank's projective partial sum in device memory (zkb_msm_g1_partial; asynchronous)."""
+        ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
+        n = len(ks) // 32 if ks is not None else 0
+        self._check(self.lib.zkb_msm_g1_partial(self.h, bases.h, offset, ps, n, _devptr(out_partial_dev)))
+        return ks   # keep the host buffer alive until the stream has consumed it
+
+    def msm_g2_partial(self, bases, scalars, out_partial_dev, offset=0):
+        ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
+        n = len(ks) // 32 if ks is not None else 0
+        self._check(self.lib.zkb_msm_g2_partial(self.h, bases.h, offset, ps, n, _devptr(out_partial_dev)))
+        return ks
+
     def msm_g1_combine(self, partials_dev, k, out_affine_dev):
         self._check(self.lib.zkb_msm_g1_combine(self.h, _devptr(partials_dev), k, _devptr(out_affine_dev)))
 
@@ -190,10 +203,25 @@ class Context:
         import torch
         sz = 64 if group == 1 else 128
         out = torch.zeros(batch * sz, dtype=torch.uint8, device=scalars_dev.device)
+        torch.cuda.synchronize()       # the library runs on its own non-blocking stream: torch's fill must be done first
         self._check(self.lib.zkb_debug_msm_batch(self.h, group, bases.h, offset, _devptr(scalars_dev), n, stride, batch, _devptr(out)))
         self.synchronize()
         o = bytes(out.cpu().numpy())
         return [o[sz * i:sz * (i + 1)] for i in range(batch)]
+
+    def debug_msm_entries(self, bases, scalars_dev, n, stride, batch, offset=0):
+        """Parity hook: the sorted (key, value) entry lists of the MSM front end -> (keys, vals) numpy uint32 arrays."""
+        import torch
+        c, nwin = bases.window()
+        cap = nwin * n * batch
+        keys = torch.zeros(cap, dtype=torch.int32, device=scalars_dev.device)
+        vals = torch.zeros(cap, dtype=torch.int32, device=scalars_dev.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=scalars_dev.device)
+        torch.cuda.synchronize()
+        self._check(self.lib.zkb_debug_msm_entries(self.h, bases.h, offset, _devptr(scalars_dev), n, stride, batch, _devptr(keys),
+                                                   _devptr(vals), _devptr(cnt)))
+        m = int(cnt.cpu().numpy().view(np.uint32)[0])
+        return keys.cpu().numpy().view(np.uint32)[:m].copy(), vals.cpu().numpy().view(np.uint32)[:m].copy()
 
     # ---- NTT
     def ntt(self, data, log_n, inverse=False, coset=False):
@@ -326,6 +354,37 @@ class Context:
         self._check(self.lib.zkb_prove(self.h, pk.h, r1cs.h, pz, pr, ps, oa.ctypes.data_as(C.c_void_p),
                                        ob.ctypes.data_as(C.c_void_p), oc.ctypes.data_as(C.c_void_p)))
         return oa.tobytes(), ob.tobytes(), oc.tobytes()
+
+
+def msm_multi(ctxs, bases, scalars, group=1):
+    """zkb_msm_g{1,2}_multi: one process, one Context per GPU, bases[i] = range i of the points on ctxs[i]; host scalars."""
+    lib = ctxs[0].lib
+    ps, ks = _buf(scalars) if len(scalars) else (C.c_void_p(0), None)
+    n = len(ks) // 32 if ks is not None else 0
+    k = len(ctxs)
+    ca = (C.c_void_p * k)(*[c.h for c in ctxs])
+    ba = (C.c_void_p * k)(*[b.h for b in bases])
+    out = np.empty(64 if group == 1 else 128, dtype=np.uint8)
+    fn = lib.zkb_msm_g1_multi if group == 1 else lib.zkb_msm_g2_multi
+    ctxs[0]._check(fn(ca, ba, k, ps, n, out.ctypes.data_as(C.c_void_p)))
+    return out.tobytes()
+
+
+def prove_multi(ctxs, pk_shards, r1cs_list, z_bytes, r_bytes, s_bytes):
+    """zkb_prove_multi: ONE proof over the GPUs of this process (one Context, key shard and matrices copy per GPU)."""
+    lib = ctxs[0].lib
+    k = len(ctxs)
+    pz, kz = _buf(z_bytes)
+    Context._check_z(r1cs_list[0], kz)
+    pr, kr = _buf(r_bytes)
+    ps, ks = _buf(s_bytes)
+    ca = (C.c_void_p * k)(*[c.h for c in ctxs])
+    pa = (C.c_void_p * k)(*[p.h for p in pk_shards])
+    ma = (C.c_void_p * k)(*[m.h for m in r1cs_list])
+    oa, ob, oc = np.empty(64, dtype=np.uint8), np.empty(128, dtype=np.uint8), np.empty(64, dtype=np.uint8)
+    ctxs[0]._check(lib.zkb_prove_multi(ca, pa, ma, k, pz, pr, ps, oa.ctypes.data_as(C.c_void_p), ob.ctypes.data_as(C.c_void_p),
+                                       oc.ctypes.data_as(C.c_void_p)))
+    return oa.tobytes(), ob.tobytes(), oc.tobytes()
 
 
 class _Bases:

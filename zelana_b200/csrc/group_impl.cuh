@@ -73,7 +73,7 @@ __global__ void affine_import_kernel(const uint32_t* in, Affine<F>* out, size_t 
     if (lhs != rhs) { atomicExch(bad, 2); return; }
     // same meaning of `validate` as the compressed loader and arkworks' Validate::Yes: G2 has a cofactor, so an on-curve
     // point must also be killed by r (G1 has cofactor 1: nothing to check)
-    if (SubgroupCheck<F>::NEEDED) {
+    if (SubgroupCheck<F>::NEEDED && validate != 2) {   // validate == 2: on-curve only (the curve-arithmetic parity hooks)
       const uint32_t r[8] = {FrCfg::M0, FrCfg::M1, FrCfg::M2, FrCfg::M3, FrCfg::M4, FrCfg::M5, FrCfg::M6, FrCfg::M7};
       if (!XYZZ<F>::from_affine(p).mul_words(r).is_inf()) { atomicExch(bad, 4); return; }
     }
@@ -270,7 +270,8 @@ int scalar_mul_impl(zkb_ctx* ctx, const uint8_t* points, const uint8_t* scalars,
   if (n == 0) return ZKB_OK;
   size_t pbytes = n * sizeof(Affine<F>);
   CUDA_TRY(ctx, ctx->tmp1.reserve(pbytes));
-  ZKB_TRY(import_points<F>(ctx, points, n, 1, ctx->tmp1.as<Affine<F>>()));
+  // on-curve only: keygen clears the G2 cofactor through this hook, i.e. multiplies points that are NOT in the subgroup yet
+  ZKB_TRY(import_points<F>(ctx, points, n, 2, ctx->tmp1.as<Affine<F>>()));
   CUDA_TRY(ctx, ctx->scal.reserve(n * 32));
   CUDA_TRY(ctx, ctx->tmp2.reserve(pbytes));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -286,7 +287,7 @@ template <class F>
 int point_sum_impl(zkb_ctx* ctx, const uint8_t* points, size_t n, uint8_t* out) {
   size_t pbytes = n * sizeof(Affine<F>);
   CUDA_TRY(ctx, ctx->tmp1.reserve(pbytes + sizeof(Affine<F>)));
-  ZKB_TRY(import_points<F>(ctx, points, n, 1, ctx->tmp1.as<Affine<F>>()));
+  ZKB_TRY(import_points<F>(ctx, points, n, 2, ctx->tmp1.as<Affine<F>>()));
   CUDA_TRY(ctx, ctx->res.reserve(512));
   point_sum_kernel<F><<<1, 32, 0, ctx->stream>>>(ctx->tmp1.as<Affine<F>>(), n, ctx->res.as<uint32_t>());
   ctx->launches++;
@@ -575,6 +576,30 @@ int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, si
   return ZKB_OK;
 }
 
+// parity hook for the entry sort (sort.cuh): the sorted (key, value) lists of a batched MSM front end, copied to out_keys /
+// out_vals (device, capacity nwin * n * batch words each); *out_count (device) = their number.
+template <class F>
+int msm_entries_debug_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                           size_t stride, int batch, void* out_keys, void* out_vals, void* out_count) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!bases || offset + n > bases->n || !scalars_dev || batch < 1 || n == 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_entries_debug: bad argument");
+  ZKB_TRY(set_device(ctx));
+  MsmLayout<F> L = msm_layout<F>(ctx->sm_count, bases->c, bases->nwin, n, 1, batch);
+  CUDA_TRY(ctx, ctx->msm_ws.reserve(L.bytes));
+  char* base = static_cast<char*>(ctx->msm_ws.p);
+  uint32_t* hdr = (uint32_t*)(base + L.o_hdr);
+  const uint32_t *sk = nullptr, *sv = nullptr;
+  EntrySource src{static_cast<const uint32_t*>(scalars_dev), n, stride, batch, L.c, L.nwin, L.nbuck, bases->n, offset, bases->inf_mask};
+  cudaError_t e = msm_sort_entries(src, L.sort, ctx->sm_count, hdr, (uint32_t*)(base + L.o_k0), (uint32_t*)(base + L.o_v0),
+                                   (uint32_t*)(base + L.o_k1), (uint32_t*)(base + L.o_v1), ctx->stream, &sk, &sv, &ctx->launches);
+  if (e != cudaSuccess) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "msm_sort_entries: %s", cudaGetErrorString(e));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_keys, sk, L.total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_vals, sv, L.total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_count, hdr + SortHeader::TOTAL, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
 // 32 x 255 fixed-base table (8-bit windows) of bases->p[idx]: delta_g1 / delta_g2 of a key, for the per-proof r, s multiples
 template <class F>
 int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t idx, void** out_table) {
@@ -592,30 +617,110 @@ int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, 
   return ZKB_OK;
 }
 
+// Host scalars -> queued MSM.  out_affine_dev / out_partial_dev: device memory, either may be null.  Large inputs upload in
+// slices on a second stream and accumulate each slice while the next one is in flight (msm_run_host_sliced).
+template <class F>
+int msm_host_enqueue(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+                     void* out_affine_dev, void* out_partial_dev) {
+  CUDA_TRY(ctx, ctx->scal.reserve(n * 32 + 32));
+  if (n >= (size_t(1) << 20) && ctx->msm_slices > 1) {
+    if (!bases || offset + n > bases->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
+    if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
+    cudaError_t e = msm_run_host_sliced<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset, scalars_host,
+                                           ctx->scal.as<uint32_t>(), n, ctx->msm_slices, static_cast<XYZZ<F>*>(out_partial_dev),
+                                           static_cast<uint32_t*>(out_affine_dev));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run_host_sliced: %s", cudaGetErrorString(e));
+    }
+    return ZKB_OK;
+  }
+  if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return msm_dev_impl<F>(ctx, bases, offset, ctx->scal.p, n, out_affine_dev, out_partial_dev);
+}
+
 template <class F>
 int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
                   uint8_t* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || (!scalars_host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: null argument");
   ZKB_TRY(set_device(ctx));
-  CUDA_TRY(ctx, ctx->scal.reserve(n * 32 + 32));
   CUDA_TRY(ctx, ctx->res.reserve(512));
-  if (n >= (size_t(1) << 20) && ctx->msm_slices > 1) {
-    // large: upload in slices on a second stream and accumulate each slice while the next one is in flight
-    if (!bases || offset + n > bases->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
-    if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
-    cudaError_t e = msm_run_host_sliced<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset, scalars_host,
-                                           ctx->scal.as<uint32_t>(), n, ctx->msm_slices, nullptr, ctx->res.as<uint32_t>());
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run_host_sliced: %s", cudaGetErrorString(e));
-    }
-  } else {
-    if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, scalars_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    ZKB_TRY((msm_dev_impl<F>(ctx, bases, offset, ctx->scal.p, n, ctx->res.p, nullptr)));
-  }
+  ZKB_TRY((msm_host_enqueue<F>(ctx, bases, offset, scalars_host, n, ctx->res.p, nullptr)));
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+// One rank's share of a range-sharded MSM from HOST scalars: the sliced upload pipeline, result = the projective partial sum
+// in device memory (for an all-gather) -- asynchronous on ctx's stream.
+template <class F>
+int msm_host_partial_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host, size_t n,
+                          void* out_partial_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!out_partial_dev || (!scalars_host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_partial: null argument");
+  ZKB_TRY(set_device(ctx));
+  return msm_host_enqueue<F>(ctx, bases, offset, scalars_host, n, nullptr, out_partial_dev);
+}
+
+// One process, one context per GPU: GPU i holds bases[i] = range i of the points (in order); the n host scalars are split the
+// same way.  Every GPU runs its partial MSM (own host thread, sliced upload), the n_gpus partial sums (128 / 256 B each) are
+// gathered through host memory and added on ctxs[0].
+template <class F>
+int msm_multi_impl(zkb_ctx* const* ctxs, const typename GroupOf<F>::Bases* const* bases, int n_gpus, const uint8_t* scalars_host,
+                   size_t n, uint8_t* out) {
+  if (!ctxs || n_gpus < 1 || !ctxs[0]) return ZKB_ERR_INVALID_ARG;
+  zkb_ctx* c0 = ctxs[0];
+  if (!bases || !out || (!scalars_host && n) || n_gpus > 64) ZKB_FAIL(c0, ZKB_ERR_INVALID_ARG, "msm_multi: bad argument");
+  size_t total = 0;
+  for (int i = 0; i < n_gpus; i++) {
+    if (!ctxs[i] || !bases[i]) ZKB_FAIL(c0, ZKB_ERR_INVALID_ARG, "msm_multi: null context or bases for GPU %d", i);
+    total += bases[i]->n;
+  }
+  if (total != n) ZKB_FAIL(c0, ZKB_ERR_SHAPE, "msm_multi: the bases handles hold %zu points, %zu scalars given", total, n);
+  constexpr size_t PB = sizeof(XYZZ<F>);
+  std::vector<uint8_t> parts(size_t(n_gpus) * PB);
+  std::vector<int> rc(size_t(n_gpus), ZKB_OK);
+  auto work = [&](int i, size_t off) {
+    zkb_ctx* ctx = ctxs[i];
+    rc[size_t(i)] = [&]() -> int {
+      ZKB_TRY(set_device(ctx));
+      CUDA_TRY(ctx, ctx->res.reserve(512));
+      ZKB_TRY((msm_host_enqueue<F>(ctx, bases[i], 0, scalars_host + off * 32, bases[i]->n, nullptr, ctx->res.p)));
+      CUDA_TRY(ctx, cudaMemcpyAsync(parts.data() + size_t(i) * PB, ctx->res.p, PB, cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+      return ZKB_OK;
+    }();
+  };
+  try {
+    struct Joiner {
+      std::vector<std::thread> th;
+      ~Joiner() {
+        for (auto& t : th)
+          if (t.joinable()) t.join();
+      }
+    } jn;
+    size_t off = bases[0]->n;
+    for (int i = 1; i < n_gpus; i++) {
+      jn.th.emplace_back(work, i, off);
+      off += bases[i]->n;
+    }
+    work(0, 0);
+  } catch (...) {
+    ZKB_FAIL(c0, ZKB_ERR_OOM, "msm_multi: could not start the per-GPU host threads");
+  }
+  for (int i = 0; i < n_gpus; i++)
+    if (rc[size_t(i)] != ZKB_OK) {
+      if (i) c0->err = ctxs[i]->err;
+      return rc[size_t(i)];
+    }
+  ZKB_TRY(set_device(c0));
+  CUDA_TRY(c0, c0->tmp1.reserve(parts.size()));
+  CUDA_TRY(c0, c0->res.reserve(512));
+  CUDA_TRY(c0, cudaMemcpyAsync(c0->tmp1.p, parts.data(), parts.size(), cudaMemcpyHostToDevice, c0->stream));
+  ZKB_TRY((msm_combine_impl<F>(c0, c0->tmp1.p, n_gpus, c0->res.p)));
+  CUDA_TRY(c0, cudaMemcpyAsync(out, c0->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, c0->stream));
+  CUDA_TRY(c0, cudaStreamSynchronize(c0->stream));
   return ZKB_OK;
 }
 
@@ -642,8 +747,11 @@ int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
   template int msm_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, void*, void*);              \
   template int msm_host_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const uint8_t*, size_t, uint8_t*);              \
   template int msm_combine_impl<F>(zkb_ctx*, const void*, int, void*);                                                      \
+  template int msm_host_partial_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const uint8_t*, size_t, void*);          \
+  template int msm_multi_impl<F>(zkb_ctx* const*, const GroupOf<F>::Bases* const*, int, const uint8_t*, size_t, uint8_t*);   \
   template int msm_batch_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*); \
   template int fixed_table_for_base<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, void**);                                  \
+  template int msm_entries_debug_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*, void*); \
   template void fixed_table_free<F>(zkb_ctx*);                                                                             \
   template int fixed_base_batch<F>(zkb_ctx*, const uint8_t*, const void*, size_t, uint8_t*);
 

@@ -14,6 +14,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/zkb200.h"
@@ -221,8 +222,14 @@ template <class F> int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bas
 template <class F> int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const uint8_t* scalars_host,
                                      size_t n, uint8_t* out);
 template <class F> int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out);
+template <class F> int msm_host_partial_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset,
+                                             const uint8_t* scalars_host, size_t n, void* out_partial_dev);
+template <class F> int msm_multi_impl(zkb_ctx* const* ctxs, const typename GroupOf<F>::Bases* const* bases, int n_gpus,
+                                      const uint8_t* scalars_host, size_t n, uint8_t* out);
 template <class F> int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
                                           size_t n, size_t stride, int batch, void* out_affine_dev, void* out_partial_dev);
+template <class F> int msm_entries_debug_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
+                                              size_t n, size_t stride, int batch, void* out_keys, void* out_vals, void* out_count);
 template <class F> int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t idx, void** out_table);
 template <class F> void fixed_table_free(zkb_ctx* ctx);
 // out_host[i] = scalars_dev[i] * generator  (canonical 32 B scalars on the device; raw canonical affine out; zero -> infinity)

@@ -424,10 +424,9 @@ __global__ void msm_combine_kernel(const XYZZ<F>* __restrict__ parts, int k, uin
 
 // ------------------------------------------------------------------------------------------- batched reduction
 // K scalar vectors against ONE table (a batch of small proofs sharing a key): bucket array = K x nbuck, keys = p * nbuck + b.
-// msm_bucket_seg_kernel runs over the flat array (S divides nbuck: segments never straddle two vectors); then one warp per
-// vector folds its nsp = nbuck / S segment records:  R_p = sum_s W[p,s] + S * sum_s s T[p,s].
-// Lane l owns the q = nsp / 32 consecutive segments s = l q + i:  sum_s s T_s = q sum_l l A_l + sum_l B_l  with
-// A_l = sum_i T_{lq+i}, B_l = sum_i i T_{lq+i} (running sums); sum_l l A_l = sum_{j>=1} (suffix sum of A at j): shuffles only.
+// msm_bucket_seg_kernel runs over the flat array (S divides nbuck: segments never straddle two vectors); then the nsp = nbuck / S
+// segment records of every vector are folded 32 at a time by warps (msm_fold_level_kernel), one or two levels:
+//   R_p = sum_s W[p,s] + S * sum_s s T[p,s].
 template <class F>
 __device__ __forceinline__ F shfl_field(const F& a, int src);
 template <>
@@ -456,27 +455,25 @@ __device__ __forceinline__ XYZZ<F> warp_sum_xyzz(XYZZ<F> v, int lane) {
   return v;
 }
 
+// One level of the fold.  Items are records (T, B, W) standing for m = 2^log_m consecutive segments each: T = sum of their
+// segment totals, B = sum_i i T_i over them (local index), W = sum of their weighted sums.  A warp combines `cnt` (<= 32)
+// consecutive items into one record standing for cnt * m segments:
+//   T' = sum_j T_j,   B' = m sum_j j T_j + sum_j B_j,   W' = sum_j W_j          (lane j holds item j)
+// with sum_j j T_j = sum_{j >= 1} (suffix sum of T at j): shuffles only, no scalar multiplications.  At the first level the
+// items are the segments themselves (Bin == nullptr: B = 0, m = 1).  `finish`: the group is a whole vector; write
+// R = W' + 2^seg_log B' to outT instead of the record.
 template <class F>
 __global__ void __launch_bounds__(32)
-msm_batch_fold_kernel(const XYZZ<F>* __restrict__ W, const XYZZ<F>* __restrict__ T, int nsp, int seg_log, XYZZ<F>* __restrict__ out) {
-  const int p = blockIdx.x, lane = threadIdx.x;
-  const XYZZ<F>* Wp = W + size_t(p) * nsp;
-  const XYZZ<F>* Tp = T + size_t(p) * nsp;
-  const int q = nsp >= 32 ? nsp >> 5 : 1;   // nsp is a power of two
-  const int s0 = lane * q;
-  XYZZ<F> A = XYZZ<F>::inf(), B = XYZZ<F>::inf(), Ws = XYZZ<F>::inf();
-  if (s0 < nsp) {
-    XYZZ<F> run = XYZZ<F>::inf();
-    for (int i = q - 1; i >= 1; i--) {
-      run.add(load_xyzz(Tp + s0 + i));
-      B.add(run);
-    }
-    A = run;
-    A.add(load_xyzz(Tp + s0));
-    for (int i = 0; i < q; i++) Ws.add(load_xyzz(Wp + s0 + i));
-  }
-  // suffix sums of A over the lanes, then their sum over lanes 1..31 = sum_l l A_l
-  XYZZ<F> sx = A;
+msm_fold_level_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__ Bin, const XYZZ<F>* __restrict__ Win, int cnt,
+                      int log_m, int finish, int seg_log, XYZZ<F>* __restrict__ outT, XYZZ<F>* __restrict__ outB,
+                      XYZZ<F>* __restrict__ outW) {
+  const size_t g = blockIdx.x;
+  const int lane = threadIdx.x;
+  const size_t item = g * size_t(cnt) + lane;
+  XYZZ<F> t = XYZZ<F>::inf();
+  if (lane < cnt) t = load_xyzz(Tin + item);
+  // suffix sums of T over the lanes; their sum over lanes 1..31 = sum_j j T_j; lane 0's suffix sum = T'
+  XYZZ<F> sx = t;
 #pragma unroll 1
   for (int d = 1; d < 32; d <<= 1) {
     XYZZ<F> o = shfl_xyzz(sx, (lane + d) & 31);
@@ -484,14 +481,26 @@ msm_batch_fold_kernel(const XYZZ<F>* __restrict__ W, const XYZZ<F>* __restrict__
   }
   XYZZ<F> z = lane >= 1 ? sx : XYZZ<F>::inf();
   z = warp_sum_xyzz(z, lane);
-  B = warp_sum_xyzz(B, lane);
-  Ws = warp_sum_xyzz(Ws, lane);
+  XYZZ<F> w = XYZZ<F>::inf();
+  if (lane < cnt) w = load_xyzz(Win + item);
+  w = warp_sum_xyzz(w, lane);
+  XYZZ<F> b = XYZZ<F>::inf();
+  if (Bin) {
+    if (lane < cnt) b = load_xyzz(Bin + item);
+    b = warp_sum_xyzz(b, lane);
+  }
   if (lane != 0) return;
-  for (int k = 1; k < q; k <<= 1) z = z.dbl();   // q sum_l l A_l
-  z.add(B);
-  for (int k = 0; k < seg_log; k++) z = z.dbl();  // S * (...)
-  z.add(Ws);
-  store_xyzz(out + p, z);
+  for (int k = 0; k < log_m; k++) z = z.dbl();
+  z.add(b);
+  if (finish) {
+    for (int k = 0; k < seg_log; k++) z = z.dbl();
+    z.add(w);
+    store_xyzz(outT + g, z);
+  } else {
+    store_xyzz(outT + g, sx);
+    store_xyzz(outB + g, z);
+    store_xyzz(outW + g, w);
+  }
 }
 
 // XYZZ -> canonical affine bytes, one thread per point (the K results of a batched MSM)
@@ -657,9 +666,27 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
   if (L.batch > 1) {
     // out_xyzz: `batch` partial sums; out_affine: `batch` canonical affine points
     P* res = out_xyzz ? out_xyzz : part;   // part holds 2 rows + 256 >= batch records only when batch <= 256: see msm_run_batch
-    const int nsp = int(L.nbuck >> L.seg_log);
-    msm_batch_fold_kernel<F><<<unsigned(L.batch), 32, 0, st>>>(W, Tt, nsp, L.seg_log, res);
-    ctx->launches += 2;
+    size_t cnt_items = size_t(L.nbuck >> L.seg_log);   // records per vector (a power of two)
+    const P *tin = Tt, *bin = nullptr, *win = W;
+    // intermediate records of a level: the buckets are dead once the segment kernel has run, so their array is the scratch
+    P* scratch = buckets;
+    int log_m = 0;
+    ctx->launches++;
+    while (true) {
+      const int cnt = cnt_items > 32 ? 32 : int(cnt_items);
+      const size_t groups = size_t(L.batch) * (cnt_items / cnt);
+      const int finish = cnt_items <= 32 ? 1 : 0;
+      P* oT = finish ? res : scratch;
+      P* oB = scratch + groups;
+      P* oW = scratch + 2 * groups;
+      msm_fold_level_kernel<F><<<unsigned(groups), 32, 0, st>>>(tin, bin, win, cnt, log_m, finish, L.seg_log, oT, oB, oW);
+      ctx->launches++;
+      if (finish) break;
+      tin = oT, bin = oB, win = oW;
+      scratch += 3 * groups;
+      cnt_items /= 32;
+      log_m += 5;
+    }
     if (out_affine) {
       xyzz_to_affine_bytes_kernel<F><<<unsigned((L.batch + 63) / 64), 64, 0, st>>>(res, size_t(L.batch), out_affine);
       ctx->launches++;

@@ -327,6 +327,20 @@ extern "C" int zkb_msm_g1_dev(zkb_ctx* ctx, const zkb_g1_bases* b, size_t off, c
 extern "C" int zkb_msm_g2_dev(zkb_ctx* ctx, const zkb_g2_bases* b, size_t off, const void* s, size_t n, void* oa, void* op) {
   return msm_dev_impl<Fq2>(ctx, b, off, s, n, oa, op);
 }
+extern "C" int zkb_msm_g1_partial(zkb_ctx* ctx, const zkb_g1_bases* b, size_t off, const uint8_t* s, size_t n, void* op) {
+  return msm_host_partial_impl<Fq>(ctx, b, off, s, n, op);
+}
+extern "C" int zkb_msm_g2_partial(zkb_ctx* ctx, const zkb_g2_bases* b, size_t off, const uint8_t* s, size_t n, void* op) {
+  return msm_host_partial_impl<Fq2>(ctx, b, off, s, n, op);
+}
+extern "C" int zkb_msm_g1_multi(zkb_ctx* const* ctxs, const zkb_g1_bases* const* bases, int n_gpus, const uint8_t* s, size_t n,
+                                uint8_t out[64]) {
+  return msm_multi_impl<Fq>(ctxs, bases, n_gpus, s, n, out);
+}
+extern "C" int zkb_msm_g2_multi(zkb_ctx* const* ctxs, const zkb_g2_bases* const* bases, int n_gpus, const uint8_t* s, size_t n,
+                                uint8_t out[128]) {
+  return msm_multi_impl<Fq2>(ctxs, bases, n_gpus, s, n, out);
+}
 extern "C" int zkb_msm_g1_combine(zkb_ctx* ctx, const void* parts, int k, void* out) { return msm_combine_impl<Fq>(ctx, parts, k, out); }
 extern "C" int zkb_msm_g2_combine(zkb_ctx* ctx, const void* parts, int k, void* out) { return msm_combine_impl<Fq2>(ctx, parts, k, out); }
 
@@ -343,6 +357,11 @@ extern "C" int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, s
   part = ctx->bpart.p;
   return group == 1 ? msm_batch_dev_impl<Fq>(ctx, static_cast<const zkb_g1_bases*>(bases), offset, scalars_dev, n, stride, batch, out_affine_dev, part)
                     : msm_batch_dev_impl<Fq2>(ctx, static_cast<const zkb_g2_bases*>(bases), offset, scalars_dev, n, stride, batch, out_affine_dev, part);
+}
+
+extern "C" int zkb_debug_msm_entries(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
+                                     int batch, void* out_keys_dev, void* out_vals_dev, void* out_count_dev) {
+  return msm_entries_debug_impl<Fq>(ctx, bases, offset, scalars_dev, n, stride, batch, out_keys_dev, out_vals_dev, out_count_dev);
 }
 
 // =============================================================================================== NTT
@@ -1300,4 +1319,57 @@ extern "C" int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int wor
   CUDA_TRY(ctx, cudaMemcpyAsync(out_c, o.oC, 64, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
+}
+
+// ONE proof over the GPUs of one process: context i holds shard i of the key (zkb_pk_load_shard(.., i, n_gpus))
+// and its own copy of the matrices; every GPU runs zkb_prove_partial from its own host thread, the 768-byte partial records are
+// gathered through host memory and ctxs[0] finishes the proof.  No torch, no NCCL: what a Rust GpuGroth16Prover with one
+// context per device calls from `BatchProver::prove` (core/src/sequencer/settlement/prover.rs:160-169, 350-425).
+extern "C" int zkb_prove_multi(zkb_ctx* const* ctxs, const zkb_pk* const* pk_shards, const zkb_r1cs* const* ms, int n_gpus,
+                               const uint8_t* z_host, const uint8_t r[32], const uint8_t s[32], uint8_t out_a[64], uint8_t out_b[128],
+                               uint8_t out_c[64]) {
+  if (!ctxs || n_gpus < 1 || !ctxs[0]) return ZKB_ERR_INVALID_ARG;
+  zkb_ctx* c0 = ctxs[0];
+  if (!pk_shards || !ms || !z_host || !r || !s || !out_a || !out_b || !out_c || n_gpus > 64)
+    ZKB_FAIL(c0, ZKB_ERR_INVALID_ARG, "zkb_prove_multi: bad argument");
+  for (int i = 0; i < n_gpus; i++) {
+    if (!ctxs[i] || !pk_shards[i] || !ms[i]) ZKB_FAIL(c0, ZKB_ERR_INVALID_ARG, "zkb_prove_multi: null handle for GPU %d", i);
+    if (pk_shards[i]->world != n_gpus || pk_shards[i]->shard != i)
+      ZKB_FAIL(c0, ZKB_ERR_SHAPE, "zkb_prove_multi: key handle %d is shard %d of %d, expected %d of %d", i, pk_shards[i]->shard,
+               pk_shards[i]->world, i, n_gpus);
+  }
+  std::vector<uint8_t> parts(size_t(n_gpus) * ZKB_PROVE_PARTIAL_BYTES);
+  std::vector<int> rc(size_t(n_gpus), ZKB_OK);
+  auto work = [&](int i) {
+    zkb_ctx* ctx = ctxs[i];
+    rc[size_t(i)] = [&]() -> int {
+      ZKB_TRY(set_device(ctx));
+      CUDA_TRY(ctx, ctx->tmp2.reserve(ZKB_PROVE_PARTIAL_BYTES));
+      ZKB_TRY(zkb_prove_partial(ctx, pk_shards[i], ms[i], z_host, r, s, ctx->tmp2.p));
+      CUDA_TRY(ctx, cudaMemcpy(parts.data() + size_t(i) * ZKB_PROVE_PARTIAL_BYTES, ctx->tmp2.p, ZKB_PROVE_PARTIAL_BYTES, cudaMemcpyDeviceToHost));
+      return ZKB_OK;
+    }();
+  };
+  try {
+    struct Joiner {
+      std::vector<std::thread> th;
+      ~Joiner() {
+        for (auto& t : th)
+          if (t.joinable()) t.join();
+      }
+    } jn;
+    for (int i = 1; i < n_gpus; i++) jn.th.emplace_back(work, i);
+    work(0);
+  } catch (...) {
+    ZKB_FAIL(c0, ZKB_ERR_OOM, "zkb_prove_multi: could not start the per-GPU host threads");
+  }
+  for (int i = 0; i < n_gpus; i++)
+    if (rc[size_t(i)] != ZKB_OK) {
+      if (i) c0->err = ctxs[i]->err;
+      return rc[size_t(i)];
+    }
+  ZKB_TRY(set_device(c0));
+  CUDA_TRY(c0, c0->tmp1.reserve(parts.size()));
+  CUDA_TRY(c0, cudaMemcpy(c0->tmp1.p, parts.data(), parts.size(), cudaMemcpyHostToDevice));
+  return zkb_prove_combine(c0, c0->tmp1.p, n_gpus, r, s, out_a, out_b, out_c);
 }
