@@ -346,11 +346,17 @@ def run_ours(args):
         host_np = host.numpy().view(np.uint8).reshape(-1)
         out_host = torch.empty(64, dtype=torch.uint8, pin_memory=True)
 
+        part_dev = engine._part
+        parts_dev = torch.empty(world * engine.partial_bytes, dtype=torch.uint8, device=dev)
+
         def step_e2e():
             if world == 1:
                 return ctx.msm_g1(bases, host_np)      # the C-ABI call a user makes: zkb_msm_g1(host scalars) -> 64 B
-            scal.copy_(host, non_blocking=True)
-            step_device()
+            # N > 1: the same sliced upload pipeline per rank through zkb_msm_g1_partial (host scalars in, projective partial
+            # sum out), NCCL all-gather of the N x 128 B partials, zkb_msm_g1_combine, 64 B back to the host
+            ctx.msm_g1_partial(bases, host_np, part_dev)
+            dist.all_gather_into_tensor(parts_dev, part_dev)
+            ctx.msm_g1_combine(parts_dev, world, out_aff)
             out_host.copy_(out_aff, non_blocking=True)
             stream.synchronize()
             return bytes(out_host.numpy())
@@ -605,13 +611,13 @@ def msm_window_for(n, point_bytes):
     return best
 
 
-def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak_mul32, lanes=16, per_gpu=512, timed_steps=20,
+def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak_mul32, lanes=16, per_gpu=2048, timed_steps=20,
                           cpu_baseline=True):
     """The other half of BASELINE.json's metric ("Groth16 proofs/s (L2 batch circuit)"): every GPU proves independent batches of
     the reference's own L2BlockCircuit (prover/src/l2_circuit.rs; the L2BlockCircuit::dummy() shape keygen.rs fixes: 6415
     constraints, domain 2^13) through ONE C call per step, zkb_l2_batch_prove: per proof `BatchProver::prove` end to end --
     witness assignment on the host (Poseidon folds, comparison bits) by a pool of `lanes` threads into pinned memory,
-    StdRng(batch_id) -> (r, s), GPU prove in sub-batches of 128 proofs with batched kernels (zkb_prove_batch_begin), Solana
+    StdRng(batch_id) -> (r, s), GPU prove in sub-batches of 256 proofs with batched kernels (zkb_prove_batch_begin), Solana
     byte layout.  The key is a real one: keygen.rs's flow (StdRng seed 0) with the setup on the GPU.  Every proof has its own
     batch id, hence its own roots, assignment and randomness; no communication between GPUs.  Aggregate proofs/s, wall clock
     around `timed_steps` steps, max over ranks."""
@@ -698,7 +704,7 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak
             "batched_equals_single": True, "roofline": roof, "cpu_baseline": cpu,
             "circuit": "L2BlockCircuit::dummy() shape (prover/src/l2_circuit.rs): %d constraints, %d witness variables, domain 2^13; "
                        "one zkb_l2_batch_prove call per step = %d x BatchProver::prove end to end (host witness assignment + GPU "
-                       "prove + Solana bytes), %d host threads per GPU, sub-batches of 128 proofs through batched kernels, real key "
+                       "prove + Solana bytes), %d host threads per GPU, sub-batches of 256 proofs through batched kernels, real key "
                        "from the GPU trusted setup (StdRng seed 0 as keygen.rs), independent proofs sharded over the GPUs with no "
                        "communication" % (circ.num_constraints, circ.num_witness, per_gpu, lanes)}
 

@@ -149,6 +149,11 @@ int zkb_msm_g2_combine(zkb_ctx* ctx, const void* partials_dev, int k, void* out_
  * (bases: the matching handle type). */
 int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
                         int batch, void* out_affine_dev);
+/* Parity hook for the comb-table MSM a batched prove uses for small keys: builds, on the bases handle, the table of every
+ * multiple a signed c-bit digit can select (d * 2^(c w) * P_i, 2 <= c <= 16: windows * len * 2^(c-1) points of HBM) and runs
+ * `batch` MSMs as plain sums of gathered points -> batch canonical affine points (device). */
+int zkb_debug_msm_comb(zkb_ctx* ctx, int group, void* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
+                       int batch, int c, void* out_affine_dev);
 /* Parity hook for the MSM front end (signed-digit extraction fused with the radix sort): the entries of `batch` scalar vectors
  * sorted by key = vector * 2^(c-1) + |digit| - 1, value = table index | sign << 31.  out_keys_dev / out_vals_dev: device
  * buffers of windows * n * batch u32 each; out_count_dev: one u32 = number of entries (zero digits produce none). */
@@ -341,7 +346,7 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
 
 /* ---- batches of independent L2 proofs on one GPU (BASELINE.json config 5; the forge coordinator's chunk-per-worker
  * parallelism, forge/crates/prover-coordinator/src/dispatcher.rs:290-330, inside one process) ------------------------------
- * A zkb_l2_batch owns a pool of `lanes` host threads and two device contexts.  A batch is cut into sub-batches (<= 128 proofs,
+ * A zkb_l2_batch owns a pool of `lanes` host threads and a few device contexts (env ZKB_L2_SLOTS, default 4).  A batch is cut into sub-batches (<= 256 proofs,
  * env ZKB_L2_SUBBATCH): the pool assigns a sub-batch's witnesses into pinned memory, zkb_prove_batch_begin proves it with one
  * set of batched kernels, and the next sub-batch is assigned meanwhile.  pk, m and c are shared, read-only.
  * proofs_out: n x 256 B.  status_out (may be NULL): per-proof zkb_status.  Returns the first error, ZKB_OK if all succeeded;

@@ -816,3 +816,87 @@ def test_msm_batch_equals_single_msms(ctx):
         got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda()[:, 5:], n - 500, n, K, offset=5)
         assert got == [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p, 5:n - 495], offset=5) for p in range(K)]
         bases.free()
+
+
+def test_msm_multi_c_abi_equals_single_msm(ctx):
+    """zkb_msm_g1_multi / zkb_msm_g2_multi (one process, one context per GPU, range-sharded bases, host
+    gather of the partial sums): same bytes as one MSM over all points.  Contexts sit on distinct GPUs when the box has them,
+    otherwise on the same one (the entry point does not care); also the >= 2^20 sliced-upload path per shard."""
+    import numpy as np
+    import torch
+    import zelana_b200
+    from zelana_b200.api import msm_multi
+    ndev = torch.cuda.device_count()
+    for group, n, world in ((1, 10001, 3), (2, 3001, 2), (1, (1 << 21) + 77, 2)):
+        k = _rand_fr_np(n, 90 + group)
+        s = _rand_fr_np(n, 92 + group)
+        s[5:50] = 0
+        gen_all = ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate
+        whole = gen_all(torch.from_numpy(k.view(np.int32)).cuda(), n)
+        want = (ctx.msm_g1 if group == 1 else ctx.msm_g2)(whole, s)
+        raw = whole.read()
+        whole.free()
+        sz = 64 if group == 1 else 128
+        ctxs = [zelana_b200.Context(i % ndev) for i in range(world)]
+        bounds = [n * i // world for i in range(world + 1)]
+        shards = [(c.g1_bases if group == 1 else c.g2_bases)(raw[sz * bounds[i]:sz * bounds[i + 1]])
+                  for i, c in enumerate(ctxs)]
+        assert msm_multi(ctxs, shards, s, group=group) == want
+        assert msm_multi(ctxs, shards, s, group=group) == want          # buffers reused
+        for b in shards:
+            b.free()
+        for c in ctxs:
+            c.close()
+
+
+def test_prove_multi_c_abi_equals_prove(ctx, mimc_setup):
+    """zkb_prove_multi: ONE proof over the contexts of one process (key sharded by range, matrices replicated, partial records
+    gathered through host memory) == zkb_prove."""
+    import torch
+    import zelana_b200
+    from zelana_b200.api import prove_multi
+    r1cs, z, pk = mimc_setup
+    parts = pk_parts(pk)
+    m = ctx.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+    dpk = ctx.proving_key(**parts)
+    r, s = fr_bytes([123456789]), fr_bytes([R - 2])
+    want = ctx.prove(dpk, m, fr_bytes(z), r, s)
+    ndev = torch.cuda.device_count()
+    for world in (1, 2, 3):
+        ctxs = [zelana_b200.Context(i % ndev) for i in range(world)]
+        pks = [c.proving_key_shard(i, world, **parts) for i, c in enumerate(ctxs)]
+        ms = [c.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c) for c in ctxs]
+        assert prove_multi(ctxs, pks, ms, fr_bytes(z), r, s) == want
+        for x in pks + ms:
+            x.free()
+        for c in ctxs:
+            c.close()
+    m.free()
+    dpk.free()
+
+
+@pytest.mark.parametrize("c", [3, 8, 11])
+def test_msm_comb_tables_equal_single_msms(ctx, c):
+    """The comb-table MSM of a batched prove (every digit multiple d * 2^(c w) * P_i resident in HBM, an MSM = a sum of
+    gathered points: no buckets, no sort): K scalar vectors == K separate bucket-method MSMs, G1 and G2, with zero / one /
+    r - 1 scalars, an all-zero vector, infinity bases, and a sub-range with a stride."""
+    import numpy as np
+    import torch
+    n, K = 700, 5
+    k = _rand_fr_np(n, 95)
+    k[10:20] = 0                     # [0] G = infinity: bases the key marks as absent
+    for group in (1, 2):
+        gen = ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate
+        msm = ctx.msm_g1 if group == 1 else ctx.msm_g2
+        bases = gen(torch.from_numpy(k.view(np.int32)).cuda(), n)
+        sc = _rand_fr_np(n * K, 96 + group).reshape(K, n, 8)
+        sc[1] = 0
+        sc[2, ::2] = 0
+        sc[3, :, 1:] = 0
+        sc[3, :, 0] = 1
+        sc[4, :100] = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint32)
+        sd = torch.from_numpy(sc.view(np.int32).copy()).cuda()
+        assert ctx.debug_msm_comb(group, bases, sd, n, n, K, c) == [msm(bases, sc[p]) for p in range(K)]
+        assert ctx.debug_msm_comb(group, bases, sd[:, 7:], n - 300, n, K, c, offset=7) == \
+            [msm(bases, sc[p, 7:n - 293], offset=7) for p in range(K)]
+        bases.free()

@@ -110,6 +110,7 @@ SIGNATURES = {
     "zkb_msm_g1_combine": (_I, [_P, _P, _I, _P]),
     "zkb_msm_g2_combine": (_I, [_P, _P, _I, _P]),
     "zkb_debug_msm_batch": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZ, _I, _P]),
+    "zkb_debug_msm_comb": (_I, [_P, _I, _P, _SZ, _P, _SZ, _SZ, _I, _I, _P]),
     "zkb_debug_msm_entries": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _I, _P, _P, _P]),
     "zkb_ntt": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_ntt_dev": (_I, [_P, _P, _P, _I, _I, _I]),

@@ -209,6 +209,17 @@ class Context:
         o = bytes(out.cpu().numpy())
         return [o[sz * i:sz * (i + 1)] for i in range(batch)]
 
+    def debug_msm_comb(self, group, bases, scalars_dev, n, stride, batch, c, offset=0):
+        """Parity hook: `batch` MSMs through the comb table (every digit multiple resident) -> canonical affine byte strings."""
+        import torch
+        sz = 64 if group == 1 else 128
+        out = torch.zeros(batch * sz, dtype=torch.uint8, device=scalars_dev.device)
+        torch.cuda.synchronize()
+        self._check(self.lib.zkb_debug_msm_comb(self.h, group, bases.h, offset, _devptr(scalars_dev), n, stride, batch, c, _devptr(out)))
+        self.synchronize()
+        o = bytes(out.cpu().numpy())
+        return [o[sz * i:sz * (i + 1)] for i in range(batch)]
+
     def debug_msm_entries(self, bases, scalars_dev, n, stride, batch, offset=0):
         """Parity hook: the sorted (key, value) entry lists of the MSM front end -> (keys, vals) numpy uint32 arrays."""
         import torch

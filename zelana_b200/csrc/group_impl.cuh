@@ -308,7 +308,15 @@ int bases_alloc(zkb_ctx* ctx, size_t n, typename GroupOf<F>::Bases** out) {
   if (c <= 0 || double(msm_windows_for(c)) * double(n) >= 2147483648.0)
     ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: no window width fits %zu points in %zu MB of free device memory", n, free_b >> 20);
   int nwin = msm_windows_for(c);
-  H* h = new (std::nothrow) H{ctx->device, nullptr, n, c, nwin, nullptr};
+  H* h = new (std::nothrow) H();
+  if (h) {
+    h->device = ctx->device;
+    h->p = nullptr;
+    h->n = n;
+    h->c = c;
+    h->nwin = nwin;
+    h->inf_mask = nullptr;
+  }
   if (!h) ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases: host allocation failed");
   if (n) {
     cudaError_t e = cudaMalloc(&h->p, size_t(nwin) * n * sizeof(Affine<F>));
@@ -537,6 +545,7 @@ void bases_free_impl(typename GroupOf<F>::Bases* b) {
   g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);  // captured prove graphs hold these pointers
   if (b->p) cudaFree(b->p);
   if (b->inf_mask) cudaFree(b->inf_mask);
+  if (b->comb) cudaFree(b->comb);
   delete b;
 }
 
@@ -597,6 +606,77 @@ int msm_entries_debug_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases
   CUDA_TRY(ctx, cudaMemcpyAsync(out_vals, sv, L.total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_count, hdr + SortHeader::TOTAL, 4, cudaMemcpyDeviceToDevice, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
+template <class F>
+size_t bases_comb_bytes(const typename GroupOf<F>::Bases* b, int c) {
+  return b ? b->n * size_t(msm_windows_for(c)) * (size_t(1) << (c - 1)) * sizeof(Affine<F>) : 0;
+}
+
+// Builds the comb table for window width c.  The window tables 2^(c w) P_i must exist for the same c: when the handle was
+// built with another width they are rebuilt here into a temporary.
+template <class F>
+int bases_build_comb(zkb_ctx* ctx, typename GroupOf<F>::Bases* b, int c) {
+  if (!b || c < 2 || c > 16) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_build_comb: bad argument");
+  if (b->comb && b->comb_c == c) return ZKB_OK;
+  if (b->n == 0) return ZKB_OK;
+  ZKB_TRY(set_device(ctx));
+  const int nwin = msm_windows_for(c);
+  Affine<F>* wt = nullptr;     // window tables for width c
+  bool own_wt = false;
+  if (b->c == c) {
+    wt = b->p;
+  } else {
+    CUDA_TRY(ctx, cudaMalloc(&wt, size_t(nwin) * b->n * sizeof(Affine<F>)));
+    own_wt = true;
+    CUDA_TRY(ctx, cudaMemcpyAsync(wt, b->p, b->n * sizeof(Affine<F>), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (nwin > 1) window_tables_kernel<F><<<blocks_for(b->n, 128), 128, 0, ctx->stream>>>(wt, b->n, c, nwin);
+    ctx->launches++;
+  }
+  Affine<F>* comb = nullptr;
+  cudaError_t e = cudaMalloc(&comb, bases_comb_bytes<F>(b, c));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (own_wt) cudaFree(wt);
+    ZKB_FAIL(ctx, ZKB_ERR_OOM, "bases_build_comb: cudaMalloc(%zu) failed", bases_comb_bytes<F>(b, c));
+  }
+  comb_build_kernel<F><<<blocks_for(b->n * size_t(nwin), 64), 64, 0, ctx->stream>>>(wt, b->n, nwin, c, comb);
+  ctx->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (own_wt) cudaFree(wt);
+  if (e != cudaSuccess) {
+    cudaFree(comb);
+    ZKB_FAIL(ctx, ZKB_ERR_CUDA, "comb_build_kernel: %s", cudaGetErrorString(e));
+  }
+  if (b->comb) cudaFree(b->comb);
+  b->comb = comb;
+  b->comb_c = c;
+  b->comb_nwin = nwin;
+  return ZKB_OK;
+}
+
+template <class F>
+int msm_comb_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev, size_t n,
+                      size_t stride, int batch, void* out_partial_dev, void* out_affine_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (!bases || !bases->comb || offset + n > bases->n || (!scalars_dev && n) || batch < 1 || stride < n || !out_partial_dev)
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_comb: bad bases range, scalars or batch (or no comb table)");
+  if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_comb: bases live on device %d, ctx on %d", bases->device, ctx->device);
+  ZKB_TRY(set_device(ctx));
+  cudaError_t e = msm_run_comb<F>(ctx, bases->comb, bases->comb_c, bases->comb_nwin, bases->inf_mask, offset,
+                                  static_cast<const uint32_t*>(scalars_dev), n, stride, batch, static_cast<XYZZ<F>*>(out_partial_dev));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ZKB_FAIL(ctx, e == cudaErrorMemoryAllocation ? ZKB_ERR_OOM : ZKB_ERR_CUDA, "msm_run_comb: %s", cudaGetErrorString(e));
+  }
+  if (out_affine_dev) {
+    xyzz_to_affine_bytes_kernel<F><<<blocks_for(size_t(batch), 64), 64, 0, ctx->stream>>>(static_cast<const XYZZ<F>*>(out_partial_dev),
+                                                                                       size_t(batch), static_cast<uint32_t*>(out_affine_dev));
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
   return ZKB_OK;
 }
 
@@ -751,6 +831,9 @@ int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
   template int msm_multi_impl<F>(zkb_ctx* const*, const GroupOf<F>::Bases* const*, int, const uint8_t*, size_t, uint8_t*);   \
   template int msm_batch_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*); \
   template int fixed_table_for_base<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, void**);                                  \
+  template int bases_build_comb<F>(zkb_ctx*, GroupOf<F>::Bases*, int);                                                        \
+  template size_t bases_comb_bytes<F>(const GroupOf<F>::Bases*, int);                                                         \
+  template int msm_comb_dev_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*); \
   template int msm_entries_debug_impl<F>(zkb_ctx*, const GroupOf<F>::Bases*, size_t, const void*, size_t, size_t, int, void*, void*, void*); \
   template void fixed_table_free<F>(zkb_ctx*);                                                                             \
   template int fixed_base_batch<F>(zkb_ctx*, const uint8_t*, const void*, size_t, uint8_t*);

@@ -139,12 +139,16 @@ struct zkb_ctx {
 // Device-resident bases with their window tables: p[j * n + i] = 2^(c j) * base_i, j < nwin (msm.cuh).
 // inf_mask[i] != 0: base i is the point at infinity (a variable absent from that query's matrix: half of b_query in
 // practice) -- the MSM drops its entries before the sort instead of carrying them as idle lanes through the accumulation.
+// comb / comb_c / comb_nwin: the optional table of ALL digit multiples (msm.cuh comb_build_kernel), built for small keys by the
+// first batched prove.
 struct zkb_g1_bases {
   int device;
   zkb::Affine<zkb::Fq>* p;
   size_t n;
   int c, nwin;
   uint8_t* inf_mask;
+  zkb::Affine<zkb::Fq>* comb = nullptr;
+  int comb_c = 0, comb_nwin = 0;
 };
 struct zkb_g2_bases {
   int device;
@@ -152,6 +156,8 @@ struct zkb_g2_bases {
   size_t n;
   int c, nwin;
   uint8_t* inf_mask;
+  zkb::Affine<zkb::Fq2>* comb = nullptr;
+  int comb_c = 0, comb_nwin = 0;
 };
 
 namespace zkb {
@@ -230,6 +236,12 @@ template <class F> int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F
                                           size_t n, size_t stride, int batch, void* out_affine_dev, void* out_partial_dev);
 template <class F> int msm_entries_debug_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
                                               size_t n, size_t stride, int batch, void* out_keys, void* out_vals, void* out_count);
+// comb table of every digit multiple for window width c (needs the window tables of the SAME c: the handle is rebuilt if not);
+// comb_msm: `batch` MSMs through it
+template <class F> int bases_build_comb(zkb_ctx* ctx, typename GroupOf<F>::Bases* bases, int c);
+template <class F> size_t bases_comb_bytes(const typename GroupOf<F>::Bases* bases, int c);
+template <class F> int msm_comb_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t offset, const void* scalars_dev,
+                                         size_t n, size_t stride, int batch, void* out_partial_dev, void* out_affine_dev = nullptr);
 template <class F> int fixed_table_for_base(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t idx, void** out_table);
 template <class F> void fixed_table_free(zkb_ctx* ctx);
 // out_host[i] = scalars_dev[i] * generator  (canonical 32 B scalars on the device; raw canonical affine out; zero -> infinity)
@@ -304,5 +316,6 @@ struct zkb_pk {
   // nv / nw / nh keep describing the WHOLE key.  Unsharded: offsets 0.
   size_t off_a = 0, off_l = 0, off_h = 0;   // a_ext, b1_ext and b2_ext share off_a
   int shard = 0, world = 1;
+  int comb_state = 0;   // 0: not decided, 1: comb tables built for all five query vectors, -1: too large, bucket path
   void *fb_delta1 = nullptr, *fb_delta2 = nullptr;  // fixed-base tables of delta_g1 / delta_g2 (built by the first batched prove)
 };

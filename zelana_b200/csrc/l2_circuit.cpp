@@ -1338,10 +1338,10 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
 // ================================================================================================ batches of proofs
 // BASELINE.json config 5 ("batch of 64 independent L2 proofs"; the forge coordinator's chunk-per-worker dispatch,
 // forge/crates/prover-coordinator/src/dispatcher.rs:290-330, inside one process).  Round 1 ran many small proofs side by side,
-// each a chain of ~100 short kernels at 0.02-0.1 waves.  Now a batch is cut into sub-batches of up to ZKB_L2_SUBBATCH (128)
+// each a chain of ~100 short kernels at 0.02-0.1 waves.  Now a batch is cut into sub-batches of up to ZKB_L2_SUBBATCH (256)
 // proofs; a sub-batch is ASSIGNED on the host by a pool of `lanes` worker threads (Poseidon folds, comparison bits: 0.6 ms
 // per proof per core) straight into pinned memory and PROVED on the GPU by one zkb_prove_batch_begin: batched mat-vecs and
-// NTTs, five batched MSMs sharing the key's window tables, one finishing kernel.  Two device slots alternate, so the
+// NTTs, five batched MSMs sharing the key's window tables, one finishing kernel.  A few device slots (ZKB_L2_SLOTS, default 4) rotate, so the
 // assignment of sub-batch j+1 runs while the GPU proves sub-batch j.  Key, matrices and circuit are shared, read-only.
 
 namespace {
@@ -1427,11 +1427,28 @@ struct BatchSlot {
 
 }  // namespace
 
+constexpr int L2_MAX_SLOTS = 8;
+
+// device slots in flight per batch object: env ZKB_L2_SLOTS (2..8), default 4.  More than two, because a sub-batch ends in
+// latency-bound kernels (bucket folds, the two scalar-multiplication chains) that only overlap with ANOTHER sub-batch's
+// accumulation kernels.
+static int l2_slot_count() {
+  static const int n = [] {
+    if (const char* e = getenv("ZKB_L2_SLOTS")) {
+      int v = atoi(e);
+      if (v >= 2 && v <= L2_MAX_SLOTS) return v;
+    }
+    return 4;
+  }();
+  return n;
+}
+
 struct zkb_l2_batch {
   int device = 0;
   int lanes = 1;
+  int nslots = 2;
   std::unique_ptr<WorkerPool> pool;
-  BatchSlot slots[2];
+  BatchSlot slots[L2_MAX_SLOTS];
   std::mutex mu;   // one zkb_l2_batch_prove at a time per batch object
 };
 
@@ -1442,7 +1459,9 @@ int zkb_l2_batch_create(int device, int lanes, zkb_l2_batch** out) {
     std::unique_ptr<zkb_l2_batch> b(new zkb_l2_batch());
     b->device = device;
     b->lanes = lanes;
-    for (auto& s : b->slots) {
+    b->nslots = l2_slot_count();
+    for (int k = 0; k < b->nslots; ++k) {
+      BatchSlot& s = b->slots[k];
       int rc = zkb_ctx_create(device, &s.ctx);
       if (rc != ZKB_OK) {
         g_l2_error = "zkb_l2_batch_create: zkb_ctx_create failed";
@@ -1481,9 +1500,9 @@ static size_t l2_subbatch(size_t n) {
       long v = atol(e);
       if (v >= 1 && v <= 4096) return size_t(v);
     }
-    return size_t(128);
+    return size_t(256);
   }();
-  size_t kb = (n + 1) / 2;   // at least two sub-batches per call, so that assignment and proving overlap
+  size_t kb = (n + 3) / 4;   // at least four sub-batches per call, so that assignment and proving overlap
   if (kb < 16) kb = 16;
   if (kb > cap) kb = cap;
   return kb;
@@ -1531,7 +1550,7 @@ int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, con
     };
     const size_t kb = l2_subbatch(n);
     for (size_t j = 0; j * kb < n; ++j) {
-      BatchSlot& s = b->slots[j & 1];
+      BatchSlot& s = b->slots[j % size_t(b->nslots)];
       finish(s);
       s.base = j * kb;
       s.count = n - s.base < kb ? n - s.base : kb;
@@ -1597,8 +1616,11 @@ int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, con
         s.busy = true;
       }
     }
-    finish(b->slots[0]);
-    finish(b->slots[1]);
+    {
+      // drain in submission order: the slot after the last one used holds the oldest sub-batch
+      const size_t nsub = (n + kb - 1) / kb;
+      for (int k = 0; k < b->nslots; ++k) finish(b->slots[(nsub + size_t(k)) % size_t(b->nslots)]);
+    }
     if (status_out)
       for (size_t i = 0; i < n; ++i) status_out[i] = status[i];
     if (first_rc != ZKB_OK) {

@@ -455,51 +455,77 @@ __device__ __forceinline__ XYZZ<F> warp_sum_xyzz(XYZZ<F> v, int lane) {
   return v;
 }
 
-// One level of the fold.  Items are records (T, B, W) standing for m = 2^log_m consecutive segments each: T = sum of their
-// segment totals, B = sum_i i T_i over them (local index), W = sum of their weighted sums.  A warp combines `cnt` (<= 32)
-// consecutive items into one record standing for cnt * m segments:
-//   T' = sum_j T_j,   B' = m sum_j j T_j + sum_j B_j,   W' = sum_j W_j          (lane j holds item j)
-// with sum_j j T_j = sum_{j >= 1} (suffix sum of T at j): shuffles only, no scalar multiplications.  At the first level the
-// items are the segments themselves (Bin == nullptr: B = 0, m = 1).  `finish`: the group is a whole vector; write
-// R = W' + 2^seg_log B' to outT instead of the record.
+// Fold records.  A record (T, B, W) stands for m = 2^log_m consecutive segments: T = sum of their segment totals,
+// B = sum_i i T_i over them (local index), W = sum of their weighted sums.  Combining `cnt` consecutive records j = 0..cnt-1:
+//   T' = sum_j T_j,   B' = m sum_j j T_j + sum_j B_j,   W' = sum_j W_j.
+// At the first level the records are the segments themselves (Bin == nullptr: B = 0, m = 1).
+
+// Sequential version, one THREAD per group of `cnt` (small, e.g. 4) records: keeps the segment kernel's chains short
+// (segments of 8 buckets instead of 32) without quadrupling the number of records the warp levels have to fold.
 template <class F>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
+msm_fold_seq_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__ Win, size_t groups, int cnt,
+                    XYZZ<F>* __restrict__ outT, XYZZ<F>* __restrict__ outB, XYZZ<F>* __restrict__ outW) {
+  const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const XYZZ<F>* t = Tin + g * cnt;
+  const XYZZ<F>* w = Win + g * cnt;
+  XYZZ<F> run = XYZZ<F>::inf(), b = XYZZ<F>::inf(), ws = XYZZ<F>::inf();
+  for (int j = cnt - 1; j >= 1; j--) {   // b = sum_j j T_j by running sums
+    run.add(load_xyzz(t + j));
+    b.add(run);
+  }
+  run.add(load_xyzz(t));
+  for (int j = 0; j < cnt; j++) ws.add(load_xyzz(w + j));
+  store_xyzz(outT + g, run);
+  store_xyzz(outB + g, b);
+  store_xyzz(outW + g, ws);
+}
+
+// Warp version: a block of three warps combines `cnt` (<= 32) consecutive records, lane j of every warp holding record j.
+// Warp 0: suffix sums of T over the lanes (5 shuffle steps); their sum over lanes 1..31 is sum_j j T_j and lane 0's suffix sum
+// is T' -- no scalar multiplications.  Warps 1 and 2 tree-sum W and B meanwhile (three independent chains side by side
+// instead of one after the other).  `finish`: the group is a whole vector; write R = W' + 2^seg_log B' to outT.
+template <class F>
+__global__ void __launch_bounds__(96)
 msm_fold_level_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__ Bin, const XYZZ<F>* __restrict__ Win, int cnt,
                       int log_m, int finish, int seg_log, XYZZ<F>* __restrict__ outT, XYZZ<F>* __restrict__ outB,
                       XYZZ<F>* __restrict__ outW) {
+  __shared__ XYZZ<F> sh[2];
   const size_t g = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t item = g * size_t(cnt) + lane;
-  XYZZ<F> t = XYZZ<F>::inf();
-  if (lane < cnt) t = load_xyzz(Tin + item);
-  // suffix sums of T over the lanes; their sum over lanes 1..31 = sum_j j T_j; lane 0's suffix sum = T'
-  XYZZ<F> sx = t;
+  XYZZ<F> tsum = XYZZ<F>::inf(), z = XYZZ<F>::inf();
+  if (warp == 0) {
+    XYZZ<F> sx = XYZZ<F>::inf();
+    if (lane < cnt) sx = load_xyzz(Tin + item);
 #pragma unroll 1
-  for (int d = 1; d < 32; d <<= 1) {
-    XYZZ<F> o = shfl_xyzz(sx, (lane + d) & 31);
-    if (lane + d < 32) sx.add(o);
+    for (int d = 1; d < 32; d <<= 1) {
+      XYZZ<F> o = shfl_xyzz(sx, (lane + d) & 31);
+      if (lane + d < 32) sx.add(o);
+    }
+    tsum = sx;   // lane 0: T'
+    z = lane >= 1 ? sx : XYZZ<F>::inf();
+    z = warp_sum_xyzz(z, lane);
+  } else {
+    const XYZZ<F>* src = warp == 1 ? Win : Bin;
+    XYZZ<F> v = XYZZ<F>::inf();
+    if (src && lane < cnt) v = load_xyzz(src + item);
+    if (src) v = warp_sum_xyzz(v, lane);
+    if (lane == 0) sh[warp - 1] = v;
   }
-  XYZZ<F> z = lane >= 1 ? sx : XYZZ<F>::inf();
-  z = warp_sum_xyzz(z, lane);
-  XYZZ<F> w = XYZZ<F>::inf();
-  if (lane < cnt) w = load_xyzz(Win + item);
-  w = warp_sum_xyzz(w, lane);
-  XYZZ<F> b = XYZZ<F>::inf();
-  if (Bin) {
-    if (lane < cnt) b = load_xyzz(Bin + item);
-    b = warp_sum_xyzz(b, lane);
-  }
-  if (lane != 0) return;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   for (int k = 0; k < log_m; k++) z = z.dbl();
-  z.add(b);
+  z.add(sh[1]);
   if (finish) {
     for (int k = 0; k < seg_log; k++) z = z.dbl();
-    z.add(w);
+    z.add(sh[0]);
     store_xyzz(outT + g, z);
   } else {
-    store_xyzz(outT + g, sx);
+    store_xyzz(outT + g, tsum);
     store_xyzz(outB + g, z);
-    store_xyzz(outW + g, w);
+    store_xyzz(outW + g, sh[0]);
   }
 }
 
@@ -509,6 +535,107 @@ __global__ void xyzz_to_affine_bytes_kernel(const XYZZ<F>* __restrict__ in, size
   size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   store_affine_canonical<F>(load_xyzz(in + i).to_affine_vartime(), out + i * (sizeof(Affine<F>) / 4));
+}
+
+// ------------------------------------------------------------------------------------------- comb tables (small keys)
+// A batch of small proofs shares ONE key, and a B200 has 180 GB of HBM: for a key of a few thousand points the table can hold
+// every multiple a signed c-bit digit can ask for,
+//     comb[((i * nwin + w) << (c-1)) + d - 1] = d * 2^(c w) * P_i ,   1 <= d <= 2^(c-1),
+// so that a (scalar, window) pair is ONE gathered affine point and an MSM is a plain sum of gathered points: no buckets, no
+// sort, no bucket reduction, no heads -- those were half of the GPU time of a batch of L2-circuit proofs (profiles/
+// r02_launches_batch256.txt).  c = 12 for the L2 circuit's five query vectors: 22 windows, ~110 GB.
+// Built once per key from the window tables (2^(c w) P_i is already there): one thread per (point, window) walks the
+// multiples by mixed additions and converts 16 at a time to affine with one shared inversion.
+template <class F>
+__global__ void __launch_bounds__(64)
+comb_build_kernel(const Affine<F>* __restrict__ wtable, size_t n, int nwin, int c, Affine<F>* __restrict__ comb) {
+  constexpr int GROUP = 16;
+  const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= n * size_t(nwin)) return;
+  const size_t i = t / nwin;
+  const int w = int(t - i * nwin);
+  const Affine<F> base = load_affine(wtable + size_t(w) * n + i);
+  Affine<F>* dst = comb + (t << (c - 1));
+  const int count = 1 << (c - 1);
+  XYZZ<F> cur = XYZZ<F>::inf();
+  XYZZ<F> pts[GROUP];
+  F prefix[GROUP];
+  for (int d0 = 0; d0 < count; d0 += GROUP) {
+    const int g = count - d0 < GROUP ? count - d0 : GROUP;
+    F pr = F::one();
+    for (int k = 0; k < g; k++) {
+      cur.madd(base);                        // (d0 + k + 1) * base
+      pts[k] = cur;
+      prefix[k] = pr;
+      if (!cur.is_inf()) pr = pr * cur.zzz;
+    }
+    F inv = pr.inverse();
+    for (int k = g - 1; k >= 0; k--) {
+      Affine<F> a = Affine<F>::inf();
+      if (!pts[k].is_inf()) {
+        F zi3 = inv * prefix[k];            // 1 / zzz_k
+        inv = inv * pts[k].zzz;
+        F zi = zi3 * pts[k].zz;             // 1 / z
+        F zi2 = zi.sqr();
+        a = {pts[k].x * zi2, pts[k].y * zi3};
+      }
+      store_affine(dst + d0 + k, a);
+    }
+  }
+}
+
+// sum over the points [first + lo, first + hi) of one scalar vector of  digit_w(s_i) * 2^(c w) * P_i  as gathered comb points.
+// grid (blocks per vector, vectors); each thread owns `ppt` consecutive points; the gather of the next table point is in
+// flight while the previous one is added.  partial[vector * gridDim.x + block] = the block's sum.
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS >= 128 ? 4 : 1)   // G1: 128 registers, 4 blocks per SM like msm_accumulate_kernel
+comb_accumulate_kernel(const Affine<F>* __restrict__ comb, int c, int nwin, const uint8_t* __restrict__ inf_mask, size_t first,
+                       const uint32_t* __restrict__ scalars, size_t n, size_t stride, int ppt, XYZZ<F>* __restrict__ partial) {
+  __shared__ XYZZ<F> sh[THREADS];
+  const size_t p = blockIdx.y;
+  const size_t lo = (size_t(blockIdx.x) * THREADS + threadIdx.x) * size_t(ppt);
+  size_t hi = lo + size_t(ppt);
+  if (hi > n) hi = n;
+  XYZZ<F> acc = XYZZ<F>::inf();
+  Affine<F> pend = Affine<F>::inf();
+  uint32_t pend_neg = 0;
+  bool have = false;
+  for (size_t i = lo; i < hi; i++) {
+    if (inf_mask && inf_mask[first + i]) continue;
+    DigitWalker dw;
+    dw.load(scalars + (p * stride + i) * 8);
+    const Affine<F>* row = comb + (((first + i) * size_t(nwin)) << (c - 1));
+    for (int w = 0; w < nwin; w++) {
+      uint32_t neg;
+      const uint32_t v = dw.next(w, c, neg);
+      if (!v) continue;
+      Affine<F> cur = load_affine(row + (size_t(w) << (c - 1)) + (v - 1));
+      if (have) {
+        if (pend_neg) pend.y = pend.y.neg();
+        acc.madd(pend);
+      }
+      pend = cur;
+      pend_neg = neg;
+      have = true;
+    }
+  }
+  if (have) {
+    if (pend_neg) pend.y = pend.y.neg();
+    acc.madd(pend);
+  }
+  XYZZ<F> tot = block_sum<F, THREADS>(acc, sh);
+  if (threadIdx.x == 0) store_xyzz(partial + p * gridDim.x + blockIdx.x, tot);
+}
+
+// out[p] = sum of the `nb` (<= 32) block sums of vector p: one warp per vector
+template <class F>
+__global__ void __launch_bounds__(32)
+comb_finish_kernel(const XYZZ<F>* __restrict__ partial, int nb, XYZZ<F>* __restrict__ out) {
+  const int lane = threadIdx.x;
+  XYZZ<F> v = XYZZ<F>::inf();
+  if (lane < nb) v = load_xyzz(partial + size_t(blockIdx.x) * nb + lane);
+  v = warp_sum_xyzz(v, lane);
+  if (lane == 0) store_xyzz(out + blockIdx.x, v);
 }
 
 // ------------------------------------------------------------------------------------------- driver
@@ -569,8 +696,8 @@ static MsmLayout<F> msm_layout(int sm_count, int c, int nwin, size_t n_slice, in
   L.seg_log = c - 1 - 17;
   L.seg_log = L.seg_log < 1 ? 1 : (L.seg_log > MSM_SEG_LOG_MAX ? MSM_SEG_LOG_MAX : L.seg_log);
   if (batch > 1) {
-    // batched: one warp folds nbuck / S segment records per vector; S = 32 keeps that at <= 2^(c-6) records
-    L.seg_log = c - 1 < MSM_SEG_LOG_MAX ? c - 1 : MSM_SEG_LOG_MAX;
+    // batched: segments of 8 buckets (a 16-addition chain per thread, batch * 2^(c-4) threads), then the per-vector folds
+    L.seg_log = c - 1 < 3 ? c - 1 : 3;
   }
   if (c - 1 < L.seg_log) L.seg_log = c - 1;
   const size_t S = size_t(1) << L.seg_log;
@@ -672,6 +799,15 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
     P* scratch = buckets;
     int log_m = 0;
     ctx->launches++;
+    if (cnt_items >= 128) {   // sequential pre-fold of 4 records per thread: 4x fewer records for the warp levels
+      const size_t groups = size_t(L.batch) * (cnt_items / 4);
+      msm_fold_seq_kernel<F><<<unsigned((groups + 63) / 64), 64, 0, st>>>(tin, win, groups, 4, scratch, scratch + groups, scratch + 2 * groups);
+      ctx->launches++;
+      tin = scratch, bin = scratch + groups, win = scratch + 2 * groups;
+      scratch += 3 * groups;
+      cnt_items /= 4;
+      log_m = 2;
+    }
     while (true) {
       const int cnt = cnt_items > 32 ? 32 : int(cnt_items);
       const size_t groups = size_t(L.batch) * (cnt_items / cnt);
@@ -679,7 +815,7 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
       P* oT = finish ? res : scratch;
       P* oB = scratch + groups;
       P* oW = scratch + 2 * groups;
-      msm_fold_level_kernel<F><<<unsigned(groups), 32, 0, st>>>(tin, bin, win, cnt, log_m, finish, L.seg_log, oT, oB, oW);
+      msm_fold_level_kernel<F><<<unsigned(groups), 96, 0, st>>>(tin, bin, win, cnt, log_m, finish, L.seg_log, oT, oB, oW);
       ctx->launches++;
       if (finish) break;
       tin = oT, bin = oB, win = oW;
@@ -745,6 +881,42 @@ cudaError_t msm_run_batch(zkb_ctx* ctx, const Affine<F>* table, size_t table_n, 
   e = msm_accumulate_slice<F>(ctx, L, table, table_n, inf_mask, first, scalars, n, stride, true);
   if (e != cudaSuccess) return e;
   return msm_reduce<F>(ctx, L, out_xyzz, out_affine);
+}
+
+// `batch` MSMs over the comb table of the bases (see comb_build_kernel): out_xyzz: batch x XYZZ (required).
+template <class F>
+cudaError_t msm_run_comb(zkb_ctx* ctx, const Affine<F>* comb, int c, int nwin, const uint8_t* inf_mask, size_t first,
+                         const uint32_t* scalars, size_t n, size_t stride, int batch, XYZZ<F>* out_xyzz) {
+  using T = MsmTraits<F>;
+  using P = XYZZ<F>;
+  cudaStream_t st = ctx->stream;
+  if (batch < 1 || !out_xyzz) return cudaErrorInvalidValue;
+  if (n == 0) {
+    cudaMemsetAsync(out_xyzz, 0, sizeof(P) * batch, st);
+    return cudaGetLastError();
+  }
+  // about two resident waves of threads over the whole batch, at most 32 blocks per vector (one warp finishes a vector)
+  const size_t resident = size_t(ctx->sm_count) * T::THREADS_PER_SM;
+  size_t nb = (2 * resident + size_t(batch) * T::ACC_THREADS - 1) / (size_t(batch) * T::ACC_THREADS);
+  const size_t nb_max = (n + T::ACC_THREADS - 1) / T::ACC_THREADS;
+  if (nb > nb_max) nb = nb_max;
+  if (nb > 32) nb = 32;
+  if (nb < 1) nb = 1;
+  const int ppt = int((n + nb * T::ACC_THREADS - 1) / (nb * T::ACC_THREADS));
+  cudaError_t e = ctx->msm_ws.reserve(size_t(batch) * nb * sizeof(P));
+  if (e != cudaSuccess) return e;
+  P* partial = static_cast<P*>(ctx->msm_ws.p);
+  {
+    ProfScope ps(ctx, GroupOf<F>::PH0 + 2);
+    comb_accumulate_kernel<F, T::ACC_THREADS><<<dim3(unsigned(nb), unsigned(batch)), T::ACC_THREADS, 0, st>>>(
+        comb, c, nwin, inf_mask, first, scalars, n, stride, ppt, partial);
+  }
+  {
+    ProfScope ps(ctx, GroupOf<F>::PH0 + 3);
+    comb_finish_kernel<F><<<unsigned(batch), 32, 0, st>>>(partial, int(nb), out_xyzz);
+  }
+  ctx->launches += 2;
+  return cudaGetLastError();
 }
 
 // Host-scalar MSM pipelined against the PCIe copy: the scalars go up in `nslices` slices on a second stream; slice k is

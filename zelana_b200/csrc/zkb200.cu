@@ -359,6 +359,23 @@ extern "C" int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, s
                     : msm_batch_dev_impl<Fq2>(ctx, static_cast<const zkb_g2_bases*>(bases), offset, scalars_dev, n, stride, batch, out_affine_dev, part);
 }
 
+// parity hook for the comb-table MSM (msm.cuh comb_*): builds the table of every digit multiple for window width c on `bases`
+// (kept on the handle) and runs `batch` MSMs through it -> batch canonical affine points (device).
+extern "C" int zkb_debug_msm_comb(zkb_ctx* ctx, int group, void* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
+                                  int batch, int c, void* out_affine_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if ((group != 1 && group != 2) || !bases || !out_affine_dev || batch < 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_debug_msm_comb: bad argument");
+  ZKB_TRY(set_device(ctx));
+  const size_t psz = group == 1 ? sizeof(XYZZ<Fq>) : sizeof(XYZZ<Fq2>);
+  CUDA_TRY(ctx, ctx->bpart.reserve(size_t(batch) * psz));
+  if (group == 1) {
+    ZKB_TRY(bases_build_comb<Fq>(ctx, static_cast<zkb_g1_bases*>(bases), c));
+    return msm_comb_dev_impl<Fq>(ctx, static_cast<zkb_g1_bases*>(bases), offset, scalars_dev, n, stride, batch, ctx->bpart.p, out_affine_dev);
+  }
+  ZKB_TRY(bases_build_comb<Fq2>(ctx, static_cast<zkb_g2_bases*>(bases), c));
+  return msm_comb_dev_impl<Fq2>(ctx, static_cast<zkb_g2_bases*>(bases), offset, scalars_dev, n, stride, batch, ctx->bpart.p, out_affine_dev);
+}
+
 extern "C" int zkb_debug_msm_entries(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset, const void* scalars_dev, size_t n, size_t stride,
                                      int batch, void* out_keys_dev, void* out_vals_dev, void* out_count_dev) {
   return msm_entries_debug_impl<Fq>(ctx, bases, offset, scalars_dev, n, stride, batch, out_keys_dev, out_vals_dev, out_count_dev);
@@ -1181,6 +1198,51 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
     pk->fb_delta2 = t2;
     pk->fb_delta1 = t1;
   }
+  if (pk->comb_state == 0) {
+    // Small key, large HBM: tables of every digit multiple for all five query vectors (msm.cuh comb_build_kernel) turn each
+    // MSM into a sum of gathered points.  MEASURED AND NOT ADOPTED as the default (profiles/r02_comb_tables_rejected.txt): with
+    // one thread per range of points the work per thread follows the scalars (a full-size scalar is 22 additions, a bit is
+    // one) and warps wait for their slowest lane -- 4.2 G additions/s against the 6.3 G/s of the equal-chunk bucket
+    // accumulation, 4 400 instead of 5 070 proofs/s.  Opt in with ZKB_COMB=1 (widest window <= 12 whose tables fit 60 % of the
+    // free memory; ZKB_COMB_MAX_GB caps it).
+    int chosen = 0;
+    const char* on = getenv("ZKB_COMB");
+    if (on && on[0] == '1') {
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+      double budget = double(free_b) * 0.6;
+      if (const char* cap = getenv("ZKB_COMB_MAX_GB")) {
+        double g = atof(cap) * 1e9;
+        if (g >= 0 && g < budget) budget = g;
+      }
+      for (int c = 12; c >= 8 && !chosen; c--) {
+        double tot = double(bases_comb_bytes<Fq>(pk->a_ext, c)) + double(bases_comb_bytes<Fq>(pk->b1_ext, c)) +
+                     double(bases_comb_bytes<Fq>(pk->l_ext, c)) + double(bases_comb_bytes<Fq>(pk->h, c)) +
+                     double(bases_comb_bytes<Fq2>(pk->b2_ext, c));
+        if (tot <= budget) chosen = c;
+      }
+    }
+    if (chosen) {
+      int rc = bases_build_comb<Fq>(ctx, pk->a_ext, chosen);
+      if (rc == ZKB_OK) rc = bases_build_comb<Fq>(ctx, pk->b1_ext, chosen);
+      if (rc == ZKB_OK) rc = bases_build_comb<Fq>(ctx, pk->l_ext, chosen);
+      if (rc == ZKB_OK) rc = bases_build_comb<Fq>(ctx, pk->h, chosen);
+      if (rc == ZKB_OK) rc = bases_build_comb<Fq2>(ctx, pk->b2_ext, chosen);
+      if (rc != ZKB_OK) {   // a failed build (out of memory) falls back to the bucket method and gives the memory back
+        auto drop1 = [](zkb_g1_bases* b) {
+          if (b && b->comb) cudaFree(b->comb);
+          if (b) b->comb = nullptr, b->comb_c = 0;
+        };
+        drop1(pk->a_ext), drop1(pk->b1_ext), drop1(pk->l_ext), drop1(pk->h);
+        if (pk->b2_ext && pk->b2_ext->comb) cudaFree(pk->b2_ext->comb);
+        if (pk->b2_ext) pk->b2_ext->comb = nullptr, pk->b2_ext->comb_c = 0;
+        cudaGetLastError();
+      }
+      pk->comb_state = rc == ZKB_OK ? 1 : -1;
+    } else {
+      pk->comb_state = -1;
+    }
+  }
   CUDA_TRY(ctx, ctx->bz.reserve(K * nv * 32));
   CUDA_TRY(ctx, ctx->bzm.reserve(K * nv * 32));
   CUDA_TRY(ctx, ctx->bw3.reserve(3 * K * n * 32));
@@ -1222,16 +1284,23 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
     if (rc != ZKB_OK) lane_rc = rc;
   };
   const int Ki = int(K);
-  on_lane(0, [&] { return msm_batch_dev_impl<Fq2>(ctx, pk->b2_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pB2); });
-  on_lane(1, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->a_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pA); });
-  on_lane(2, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->b1_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pB1); });
-  on_lane(3, [&] { return msm_batch_dev_impl<Fq>(ctx, pk->l_ext, 0, z + ni, nw, nv, Ki, nullptr, o.pL); });
+  const size_t hn = pk->nh < n ? pk->nh : n;
+  const bool comb = pk->comb_state == 1;
+  auto msm1 = [&](const zkb_g1_bases* b, const Fr* sc, size_t cnt, size_t stride, XYZZ<Fq>* out) {
+    return comb ? msm_comb_dev_impl<Fq>(ctx, b, 0, sc, cnt, stride, Ki, out) : msm_batch_dev_impl<Fq>(ctx, b, 0, sc, cnt, stride, Ki, nullptr, out);
+  };
+  on_lane(0, [&] {
+    return comb ? msm_comb_dev_impl<Fq2>(ctx, pk->b2_ext, 0, z + 1, nv - 1, nv, Ki, o.pB2)
+                : msm_batch_dev_impl<Fq2>(ctx, pk->b2_ext, 0, z + 1, nv - 1, nv, Ki, nullptr, o.pB2);
+  });
+  on_lane(1, [&] { return msm1(pk->a_ext, z + 1, nv - 1, nv, o.pA); });
+  on_lane(2, [&] { return msm1(pk->b1_ext, z + 1, nv - 1, nv, o.pB1); });
+  on_lane(3, [&] { return msm1(pk->l_ext, z + ni, nw, nv, o.pL); });
   int mrc = ZKB_OK;
   if (lane_rc == ZKB_OK) {
     mrc = witness_map_batch_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, Ki, z, ctx->bzm.as<Fr>(), ctx->bw3.as<Fr>(),
                                 ctx->bh.as<Fr>());
-    size_t hn = pk->nh < n ? pk->nh : n;
-    if (mrc == ZKB_OK) mrc = msm_batch_dev_impl<Fq>(ctx, pk->h, 0, ctx->bh.as<Fr>(), hn, n, Ki, nullptr, o.pH);
+    if (mrc == ZKB_OK) mrc = msm1(pk->h, ctx->bh.as<Fr>(), hn, n, o.pH);
   }
   bool joined = true;
   for (int i = 0; i < 5; i++)
