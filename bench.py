@@ -510,13 +510,14 @@ def compact_config_lines(np, torch, zelana_b200, ctx, stream, dev, peak_int):
 
 
 def mimc_r1cs_numpy(np, num_perm, seed, rounds=91):
-    """Synthetic R1CS shaped like forge/circuits/zelana_lib/src/poseidon.nr:30-46 (MiMC-7: 4 constraints per round), built
+    """Synthetic R1CS of forge/circuits/zelana_lib/src/poseidon.nr:19-46 (MiMC-7 with the reference's round constants
+    (i+1)^3 + (i+1): 4 constraints per round), built
     with numpy index arithmetic (tests/helpers.py::mimc7_chain is the small, loop-built twin checked against the oracle).
     -> (num_instance, num_witness, (A, B, C) CSR triples, z as uint8[nv, 32])."""
     import random
     R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
     rnd = random.Random(seed)
-    consts = [rnd.randrange(R) for _ in range(rounds)]
+    consts = [(i + 1) ** 3 + (i + 1) for i in range(rounds)]    # the reference's round constants (poseidon.nr:19-27)
     x0, key = rnd.randrange(R), rnd.randrange(R)
     G = num_perm * rounds
     nv = 4 + 4 * G

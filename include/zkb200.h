@@ -169,6 +169,23 @@ int zkb_debug_msm_entries(zkb_ctx* ctx, const zkb_g1_bases* bases, size_t offset
 int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, int log_n, int direction, int coset);
 int zkb_ntt_dev(zkb_ctx* ctx, const void* in_dev, void* out_dev, int log_n, int direction, int coset);
 
+/* ---- MiMC-7 over Fr and the depth-32 account Merkle tree of the forge stack ----------------------------
+ * The hash: forge/circuits/zelana_lib/src/poseidon.nr:15-94 (c_i = (i+1)^3 + (i+1), 91 rounds of x -> (x + c_i)^7, sponge over
+ * [arity, v_1 .. v_arity]) = core/src/sequencer/storage/account_tree.rs:48-125, where the sequencer evaluates it with BigUint
+ * for every tree node it touches.  Field elements: 32 B little-endian canonical, like everywhere in this header (the reference
+ * stores tree nodes big-endian: account_tree.rs:187-203 -- the host mirror zelana_b200/account_tree.py converts).
+ * zkb_mimc_hash: out[i] = hash_arity(in[i * arity ..]) for n independent hashes, 1 <= arity <= 6 (hash_2 = a tree node,
+ * hash_4 = an account leaf `compute_account_leaf`, account_tree.rs:109-125): one level of a batched tree update is one call.
+ * zkb_mimc_merkle_roots: out[i] = root reached from leaves[i] along siblings[i * depth ..] with index bits[i * depth ..]
+ * (one byte each, 1 = the running node is the RIGHT child) = AccountMerklePath::compute_root (account_tree.rs:222-237).
+ * _dev variants: device buffers, asynchronous on ctx's stream. */
+int zkb_mimc_hash(zkb_ctx* ctx, int arity, const uint8_t* in_host, size_t n, uint8_t* out_host);
+int zkb_mimc_hash_dev(zkb_ctx* ctx, int arity, const void* in_dev, size_t n, void* out_dev);
+int zkb_mimc_merkle_roots(zkb_ctx* ctx, const uint8_t* leaves, const uint8_t* siblings, const uint8_t* bits, size_t n, int depth,
+                          uint8_t* out);
+int zkb_mimc_merkle_roots_dev(zkb_ctx* ctx, const void* leaves_dev, const void* siblings_dev, const uint8_t* bits_dev, size_t n,
+                              int depth, void* out_dev);
+
 /* ---- R1CS matrices + witness map: LibsnarkReduction::witness_map_from_matrices (row a4) ----- */
 typedef struct {
   const uint64_t* row_ptr; /* num_constraints + 1 offsets into col/coeff */

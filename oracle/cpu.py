@@ -44,6 +44,8 @@ def lib():
         L.orc_g1_bases_free.argtypes = [_P]
         L.orc_msm_g1_pre.argtypes = [_P, _SZ, _P, _SZ, _I, _P]
         L.orc_ntt.argtypes = [_P, _I, _I, _I, _I]
+        L.orc_mimc_hash.argtypes = [_I, _P, _SZ, _I, _P]
+        L.orc_mimc_merkle_roots.argtypes = [_P, _P, _P, _SZ, _I, _I, _P]
         L.orc_poly_eval.argtypes = [_P, _SZ, _P, _SZ, _I, _P]
         L.orc_root_of_unity.argtypes = [_I, _P]
         L.orc_witness_map.restype = _I
@@ -164,6 +166,23 @@ def root_of_unity(log_n):
     out = np.empty(32, dtype=np.uint8)
     lib().orc_root_of_unity(log_n, _ptr(out))
     return int.from_bytes(out.tobytes(), "little")
+
+
+def mimc_hash(arity, data, threads=0):
+    """n x hash_arity of the forge stack's MiMC-7 (n x arity x 32 B LE in, n x 32 B out)."""
+    a = _np(data)
+    n = len(a) // (32 * arity)
+    out = np.empty(max(n, 1) * 32, dtype=np.uint8)
+    lib().orc_mimc_hash(arity, _ptr(a), n, threads or max_threads(), _ptr(out))
+    return out[:n * 32].tobytes()
+
+
+def mimc_merkle_roots(leaves, siblings, bits, depth=32, threads=0):
+    L, S, B = _np(leaves), _np(siblings), _np(bits)
+    n = len(L) // 32
+    out = np.empty(max(n, 1) * 32, dtype=np.uint8)
+    lib().orc_mimc_merkle_roots(_ptr(L), _ptr(S), _ptr(B), n, depth, threads or max_threads(), _ptr(out))
+    return out[:n * 32].tobytes()
 
 
 def csr_arrays(rows):

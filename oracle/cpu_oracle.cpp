@@ -665,6 +665,47 @@ void orc_poly_eval(const uint8_t* coeffs, size_t n, const uint8_t* points, size_
 // w_n = 5^((r-1)/n), the generator ark-poly's Radix2EvaluationDomain::new(n) uses; canonical bytes
 void orc_root_of_unity(int logn, uint8_t out[32]) { fr_root_of_unity(logn).to_canonical(out); }
 
+// MiMC-7 of the forge stack, restated from forge/circuits/zelana_lib/src/poseidon.nr:19-59 and
+// core/src/sequencer/storage/account_tree.rs:48-125,222-237 (checker at sizes Python cannot reach + CPU baseline).
+static Fr mimc_permute0(Fr x, const Fr* rc) {
+  for (int i = 0; i < 91; i++) {
+    Fr t = x + rc[i];
+    Fr t2 = t * t, t4 = t2 * t2;
+    x = t4 * t2 * t;
+  }
+  return x;
+}
+static void mimc_constants(Fr* rc) {
+  for (u64 i = 0; i < 91; i++) rc[i] = Fr::from_u64((i + 1) * (i + 1) * (i + 1) + (i + 1));
+}
+void orc_mimc_hash(int arity, const uint8_t* in, size_t n, int threads, uint8_t* out) {
+  Fr rc[91];
+  mimc_constants(rc);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) {
+    Fr st = mimc_permute0(Fr::from_u64((u64)arity), rc);
+    for (int k = 0; k < arity; k++) st = mimc_permute0(st + Fr::from_canonical(in + 32 * (i * arity + k)), rc);
+    st.to_canonical(out + 32 * i);
+  }
+}
+void orc_mimc_merkle_roots(const uint8_t* leaves, const uint8_t* siblings, const uint8_t* bits, size_t n, int depth, int threads,
+                           uint8_t* out) {
+  Fr rc[91];
+  mimc_constants(rc);
+#pragma omp parallel for num_threads(threads) schedule(static)
+  for (size_t i = 0; i < n; i++) {
+    Fr cur = Fr::from_canonical(leaves + 32 * i);
+    for (int l = 0; l < depth; l++) {
+      Fr sib = Fr::from_canonical(siblings + 32 * (i * depth + l));
+      bool right = bits[i * depth + l] != 0;
+      Fr st = mimc_permute0(Fr::from_u64(2), rc);   // as the reference does: every hash_2 absorbs its arity again
+      st = mimc_permute0(st + (right ? sib : cur), rc);
+      cur = mimc_permute0(st + (right ? cur : sib), rc);
+    }
+    cur.to_canonical(out + 32 * i);
+  }
+}
+
 int orc_witness_map(uint64_t nc, uint64_t ni, uint64_t nw, const u64* a_rp, const uint32_t* a_col, const uint8_t* a_co,
                     const u64* b_rp, const uint32_t* b_col, const uint8_t* b_co, const u64* c_rp, const uint32_t* c_col,
                     const uint8_t* c_co, const uint8_t* z, uint8_t* h_out, int threads) {

@@ -47,7 +47,7 @@ def mimc7_chain(num_perm, seed, rounds=91):
     per round: t = x + k + c_i ; t2 = t*t ; t4 = t2*t2 ; t6 = t4*t2 ; out = t6*t).  One public output.
     Returns (R1CS, z) with a satisfying assignment."""
     rnd = random.Random(seed)
-    consts = [rnd.randrange(R) for _ in range(rounds)]
+    consts = [(i + 1) ** 3 + (i + 1) for i in range(rounds)]    # the reference's round constants (poseidon.nr:19-27)
     a, b, c = [], [], []
     # variables: 0 = ONE, 1 = public output ; witness from index 2
     z = [1, 0]

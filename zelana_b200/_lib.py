@@ -114,6 +114,10 @@ SIGNATURES = {
     "zkb_debug_msm_entries": (_I, [_P, _P, _SZ, _P, _SZ, _SZ, _I, _P, _P, _P]),
     "zkb_ntt": (_I, [_P, _P, _P, _I, _I, _I]),
     "zkb_ntt_dev": (_I, [_P, _P, _P, _I, _I, _I]),
+    "zkb_mimc_hash": (_I, [_P, _I, _P, _SZ, _P]),
+    "zkb_mimc_hash_dev": (_I, [_P, _I, _P, _SZ, _P]),
+    "zkb_mimc_merkle_roots": (_I, [_P, _P, _P, _P, _SZ, _I, _P]),
+    "zkb_mimc_merkle_roots_dev": (_I, [_P, _P, _P, _P, _SZ, _I, _P]),
     "zkb_r1cs_load": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(_P)]),
     "zkb_r1cs_free": (None, [_P]),
     "zkb_r1cs_log_domain": (_I, [_P]),

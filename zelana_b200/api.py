@@ -245,6 +245,38 @@ class Context:
     def ntt_dev(self, in_dev, out_dev, log_n, inverse=False, coset=False):
         self._check(self.lib.zkb_ntt_dev(self.h, _devptr(in_dev), _devptr(out_dev), log_n, int(inverse), int(coset)))
 
+    # ---- MiMC-7 / account Merkle tree (forge stack)
+    def mimc_hash(self, arity, data):
+        """n independent hash_arity(...) of the forge stack's MiMC-7 (poseidon.nr:62-94): data = n x arity x 32 B LE -> n x 32 B."""
+        if len(data) == 0:
+            return b""
+        p, k = _buf(data)
+        if arity < 1 or len(k) % (32 * arity):
+            raise ZkbError(-3, "mimc_hash: %d bytes is not a whole number of %d-element inputs" % (len(k), arity))
+        n = len(k) // (32 * arity)
+        out = np.empty(n * 32, dtype=np.uint8)
+        self._check(self.lib.zkb_mimc_hash(self.h, arity, p, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def mimc_hash_dev(self, arity, in_dev, n, out_dev):
+        self._check(self.lib.zkb_mimc_hash_dev(self.h, arity, _devptr(in_dev), n, _devptr(out_dev)))
+
+    def mimc_merkle_roots(self, leaves, siblings, bits, depth=32):
+        """n roots: leaves n x 32 B, siblings n x depth x 32 B, bits n x depth bytes (1 = running node is the right child)."""
+        pl, kl = _buf(leaves)
+        n = len(kl) // 32
+        ps, ks = _buf(siblings) if depth else (C.c_void_p(0), b"")
+        pb, kb = _buf(bits) if depth else (C.c_void_p(0), b"")
+        if len(ks) != n * depth * 32 or len(kb) != n * depth:
+            raise ZkbError(-6, "mimc_merkle_roots: %d leaves need %d sibling bytes and %d index bytes" % (n, n * depth * 32, n * depth))
+        out = np.empty(n * 32, dtype=np.uint8)
+        self._check(self.lib.zkb_mimc_merkle_roots(self.h, pl, ps, pb, n, depth, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def mimc_merkle_roots_dev(self, leaves_dev, siblings_dev, bits_dev, n, depth, out_dev):
+        self._check(self.lib.zkb_mimc_merkle_roots_dev(self.h, _devptr(leaves_dev), _devptr(siblings_dev), _devptr(bits_dev), n, depth,
+                                                       _devptr(out_dev)))
+
     # ---- Groth16
     def r1cs(self, num_instance, num_witness, a, b, c):
         return R1csMatrices(self, num_instance, num_witness, a, b, c)

@@ -18,6 +18,7 @@ struct NttTables {
 };
 
 struct FrState {
+  Fr* mimc_states = nullptr;  // [arity] = permute(arity): the state every hash_arity starts from (Montgomery), arity 0..7
   Fr* wr_fwd = nullptr;  // omega_(2^LRMAX)^e
   Fr* wr_inv = nullptr;
   std::map<int, NttTables> tables;
@@ -218,6 +219,98 @@ __global__ void setup_h_scalars_kernel(const Fr* __restrict__ c, size_t count, F
   store_fr(out + i, (fr_pow_u64(ldg_fr(c + 0), (unsigned long long)i) * ldg_fr(c + 7)).from_mont());
 }
 
+// ---- MiMC-7 over Fr: the hash of the forge stack -----------------------------------------------------------
+// forge/circuits/zelana_lib/src/poseidon.nr:15-59 = core/src/sequencer/storage/account_tree.rs:48-90 (BigUint there):
+//   round constant c_i = (i+1)^3 + (i+1);  permutation (key 0): 91 rounds x -> (x + c_i)^7;  sponge: state = permute(state + input),
+//   starting from 0;  hash_N(v_1..v_N) absorbs the arity N first (poseidon.nr:62-94).
+// 4 products per round, 364 per permutation, N + 1 permutations per hash -- and the first one (state 0 + arity) is the same
+// for every hash of that arity: computed once per context (mimc_states_kernel), so a hash_2 costs two permutations, not three.
+// Values are kept in Montgomery form between rounds.
+constexpr int MIMC_ROUNDS = 91;
+
+__device__ __forceinline__ void mimc_load_constants(Fr* rc) {   // rc: MIMC_ROUNDS entries of shared memory
+  for (int i = threadIdx.x; i < MIMC_ROUNDS; i += blockDim.x) {
+    const uint32_t k = uint32_t(i + 1);
+    Fr c = Fr::zero();
+    c.v[0] = k * k * k + k;   // <= 91^3 + 91: one limb
+    rc[i] = c.to_mont();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ Fr mimc_permute0(Fr x, const Fr* rc) {
+#pragma unroll 1
+  for (int i = 0; i < MIMC_ROUNDS; i++) {
+    Fr t = x + rc[i];
+    Fr t2 = t * t;
+    Fr t4 = t2 * t2;
+    x = t4 * t2 * t;
+  }
+  return x;   // + key, and the key is 0
+}
+
+__device__ __forceinline__ Fr mimc_arity_state(int arity, const Fr* rc) {
+  Fr a = Fr::zero();
+  a.v[0] = uint32_t(arity);
+  return mimc_permute0(a.to_mont(), rc);
+}
+
+// states[a] = permute(a) for a < 8: computed once per context (thread a)
+__global__ void mimc_states_kernel(Fr* states) {
+  __shared__ Fr rc[MIMC_ROUNDS];
+  mimc_load_constants(rc);
+  if (threadIdx.x < 8) states[threadIdx.x] = mimc_arity_state(int(threadIdx.x), rc);
+}
+
+// out[i] = hash_arity(in[i * arity .. (i + 1) * arity)), canonical in and out
+__global__ void __launch_bounds__(128)
+mimc_hash_kernel(const Fr* __restrict__ in, int arity, size_t n, const Fr* __restrict__ states, Fr* __restrict__ out, int* bad) {
+  __shared__ Fr rc[MIMC_ROUNDS];
+  mimc_load_constants(rc);
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr state = ldg_fr(states + arity);
+  for (int k = 0; k < arity; k++) {
+    Fr v = load_fr(in + i * arity + k);
+    if (!fr_is_canonical(v)) {
+      atomicExch(bad, 1);
+      return;
+    }
+    state = mimc_permute0(state + v.to_mont(), rc);
+  }
+  store_fr(out + i, state.from_mont());
+}
+
+// out[i] = the root reached from leaves[i] along siblings[i * depth ..] with index bits bits[i * depth ..] (1 = the running
+// node is the RIGHT child): AccountMerklePath::compute_root (account_tree.rs:222-237) = compute_merkle_root (merkle.nr:29-52)
+__global__ void __launch_bounds__(128)
+mimc_merkle_root_kernel(const Fr* __restrict__ leaves, const Fr* __restrict__ siblings, const uint8_t* __restrict__ bits, size_t n,
+                        int depth, const Fr* __restrict__ states, Fr* __restrict__ out, int* bad) {
+  __shared__ Fr rc[MIMC_ROUNDS];
+  mimc_load_constants(rc);
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr h2 = ldg_fr(states + 2);   // the state every hash_2 starts from
+  Fr cur = load_fr(leaves + i);
+  if (!fr_is_canonical(cur)) {
+    atomicExch(bad, 1);
+    return;
+  }
+  cur = cur.to_mont();
+  for (int l = 0; l < depth; l++) {
+    Fr sib = load_fr(siblings + i * depth + l);
+    if (!fr_is_canonical(sib)) {
+      atomicExch(bad, 1);
+      return;
+    }
+    sib = sib.to_mont();
+    const bool right = bits[i * depth + l] != 0;
+    Fr st = mimc_permute0(h2 + (right ? sib : cur), rc);
+    cur = mimc_permute0(st + (right ? cur : sib), rc);
+  }
+  store_fr(out + i, cur.from_mont());
+}
+
 int ensure_wr(zkb_ctx* ctx, FrState* S) {
   if (S->wr_fwd) return ZKB_OK;
   const uint32_t cnt = 1u << (NTT_LRMAX - 1);
@@ -293,6 +386,7 @@ void fr_state_free(zkb_ctx* ctx) {
   if (!ctx->fr_state) return;
   FrState* S = static_cast<FrState*>(ctx->fr_state);
   g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
+  if (S->mimc_states) cudaFree(S->mimc_states);
   if (S->wr_fwd) cudaFree(S->wr_fwd);
   if (S->wr_inv) cudaFree(S->wr_inv);
   for (auto& kv : S->tables) cudaFree(kv.second.mem);
@@ -313,6 +407,38 @@ int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return check_flag(ctx, "zkb_field_op");
+}
+
+static int ensure_mimc_states(zkb_ctx* ctx, const Fr** out) {
+  FrState* S = state(ctx);
+  if (!S->mimc_states) {
+    CUDA_TRY(ctx, cudaMalloc(&S->mimc_states, 8 * sizeof(Fr)));
+    mimc_states_kernel<<<1, 128, 0, ctx->stream>>>(S->mimc_states);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
+  *out = S->mimc_states;
+  return ZKB_OK;
+}
+
+int mimc_hash_dev(zkb_ctx* ctx, int arity, const Fr* in, size_t n, Fr* out) {
+  if (!n) return ZKB_OK;
+  const Fr* states = nullptr;
+  ZKB_TRY(ensure_mimc_states(ctx, &states));
+  mimc_hash_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(in, arity, n, states, out, ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
+int mimc_merkle_roots_dev(zkb_ctx* ctx, const Fr* leaves, const Fr* siblings, const uint8_t* bits, size_t n, int depth, Fr* out) {
+  if (!n) return ZKB_OK;
+  const Fr* states = nullptr;
+  ZKB_TRY(ensure_mimc_states(ctx, &states));
+  mimc_merkle_root_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(leaves, siblings, bits, n, depth, states, out, ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
 }
 
 int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n) {

@@ -274,7 +274,10 @@ struct CsrDev {
   size_t nnz = 0;
 };
 int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
-int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);  // flags non-canonical input in ctx->flag
+int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);
+// MiMC-7 (forge stack): n hashes of `arity` elements; n Merkle roots along depth-long paths.  Flag non-canonical input in ctx->flag.
+int mimc_hash_dev(zkb_ctx* ctx, int arity, const Fr* in, size_t n, Fr* out);
+int mimc_merkle_roots_dev(zkb_ctx* ctx, const Fr* leaves, const Fr* siblings, const uint8_t* bits, size_t n, int depth, Fr* out);  // flags non-canonical input in ctx->flag
 int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset);
 int ntt_batch_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset, int batch);
 void fr_state_free(zkb_ctx* ctx);

@@ -404,6 +404,64 @@ extern "C" int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, 
   return ZKB_OK;
 }
 
+// =============================================================================================== MiMC-7 / account Merkle tree
+extern "C" int zkb_mimc_hash_dev(zkb_ctx* ctx, int arity, const void* in_dev, size_t n, void* out_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (arity < 1 || arity > 6 || (n && (!in_dev || !out_dev))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_hash: arity %d outside [1, 6] or null buffer", arity);
+  ZKB_TRY(set_device(ctx));
+  ZKB_TRY(clear_flag(ctx));
+  ZKB_TRY(mimc_hash_dev(ctx, arity, static_cast<const Fr*>(in_dev), n, static_cast<Fr*>(out_dev)));
+  return ZKB_OK;   // asynchronous: a non-canonical input surfaces at the next call that checks the flag (the host variant does)
+}
+
+extern "C" int zkb_mimc_hash(zkb_ctx* ctx, int arity, const uint8_t* in_host, size_t n, uint8_t* out_host) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (arity < 1 || arity > 6 || (n && (!in_host || !out_host))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_hash: arity %d outside [1, 6] or null buffer", arity);
+  if (!n) return ZKB_OK;
+  ZKB_TRY(set_device(ctx));
+  CUDA_TRY(ctx, ctx->tmp0.reserve(n * size_t(arity) * 32));
+  CUDA_TRY(ctx, ctx->tmp2.reserve(n * 32));
+  ZKB_TRY(clear_flag(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, in_host, n * size_t(arity) * 32, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_TRY(mimc_hash_dev(ctx, arity, ctx->tmp0.as<Fr>(), n, ctx->tmp2.as<Fr>()));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_host, ctx->tmp2.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_flag(ctx, "zkb_mimc_hash");
+}
+
+extern "C" int zkb_mimc_merkle_roots_dev(zkb_ctx* ctx, const void* leaves_dev, const void* siblings_dev, const uint8_t* bits_dev, size_t n,
+                                         int depth, void* out_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (depth < 0 || depth > 64 || (n && (!leaves_dev || !out_dev || (depth && (!siblings_dev || !bits_dev)))))
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_merkle_roots: depth %d outside [0, 64] or null buffer", depth);
+  ZKB_TRY(set_device(ctx));
+  ZKB_TRY(clear_flag(ctx));
+  return mimc_merkle_roots_dev(ctx, static_cast<const Fr*>(leaves_dev), static_cast<const Fr*>(siblings_dev), bits_dev, n, depth,
+                               static_cast<Fr*>(out_dev));
+}
+
+extern "C" int zkb_mimc_merkle_roots(zkb_ctx* ctx, const uint8_t* leaves, const uint8_t* siblings, const uint8_t* bits, size_t n, int depth,
+                                     uint8_t* out) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (depth < 0 || depth > 64 || (n && (!leaves || !out || (depth && (!siblings || !bits)))))
+    ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_merkle_roots: depth %d outside [0, 64] or null buffer", depth);
+  if (!n) return ZKB_OK;
+  ZKB_TRY(set_device(ctx));
+  const size_t nd = n * size_t(depth);
+  CUDA_TRY(ctx, ctx->tmp0.reserve(n * 32));
+  CUDA_TRY(ctx, ctx->tmp1.reserve(nd * 32 + 32));
+  CUDA_TRY(ctx, ctx->tmp2.reserve(n * 32));
+  CUDA_TRY(ctx, ctx->scal.reserve(nd + 32));
+  ZKB_TRY(clear_flag(ctx));
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, leaves, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (nd) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp1.p, siblings, nd * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scal.p, bits, nd, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  ZKB_TRY(mimc_merkle_roots_dev(ctx, ctx->tmp0.as<Fr>(), ctx->tmp1.as<Fr>(), ctx->scal.as<uint8_t>(), n, depth, ctx->tmp2.as<Fr>()));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp2.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  return check_flag(ctx, "zkb_mimc_merkle_roots");
+}
+
 // =============================================================================================== R1CS + witness map
 namespace {
 
