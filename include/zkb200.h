@@ -353,6 +353,15 @@ int zkb_l2_roots(const zkb_l2_witness* witness, uint64_t batch_id, const uint8_t
                  zkb_l2_public_inputs* out);
 /* Poseidon(get_poseidon_config()) of n <= 3 field elements (32 B LE, reduced mod r): fresh sponge, absorb, squeeze one. */
 int zkb_l2_poseidon_hash(const uint8_t* elems, size_t n, uint8_t out[32]);
+/* The same hash for n independent inputs on the GPU (the account / transfer / withdrawal LEAF hashes of
+ * l2_circuit.rs:315-330,477-490 are independent; the folds over them are sequential chains and stay on the host).
+ * in: n x arity x 32 B (reduced mod r like the host function), 0 <= arity <= 3; out: n x 32 B.  _dev: device buffers, async. */
+int zkb_l2_poseidon_hash_batch(zkb_ctx* ctx, int arity, const uint8_t* in_host, size_t n, uint8_t* out_host);
+int zkb_l2_poseidon_hash_batch_dev(zkb_ctx* ctx, int arity, const void* in_dev, size_t n, void* out_dev);
+/* the same n hashes on `threads` host threads (the native sponge the witness walkers use): host baseline / convenience */
+int zkb_l2_poseidon_hash_batch_host(int arity, const uint8_t* in, size_t n, int threads, uint8_t* out);
+/* get_poseidon_config() as canonical bytes: ark_out = 64 rounds x 3 lanes x 32 B, mds_out = 3 x 3 x 32 B (row-major). */
+int zkb_l2_poseidon_params(uint8_t* ark_out, uint8_t* mds_out);
 /* `StdRng::seed_from_u64(batch_id)` then `Fr::rand` twice (prover.rs:354 + ark-groth16 prove): canonical r, s. */
 int zkb_l2_prover_randomness(uint64_t batch_id, uint8_t r[32], uint8_t s[32]);
 /* `impl BatchProver for Groth16Prover { fn prove }` (prover.rs:350-425): proof_out = -A || B || C, 256 B

@@ -348,3 +348,51 @@ def test_roots_edge_cases_zero_amounts_u64_limits_and_refusals():
         with pytest.raises(ZkbError) as e:              # overspend / unknown sender / recipient beyond 64 bits
             P.satisfying_inputs(bad)
         assert e.value.code == -3
+
+
+def test_exported_poseidon_parameters_equal_the_oracle_generator():
+    """zkb_l2_poseidon_params (what the GPU hash kernel uploads) == oracle find_poseidon_ark_and_mds(254, 2, 8, 56)."""
+    import ctypes as C
+    import zelana_b200
+    lib = zelana_b200.load_library()
+    ark, mds = C.create_string_buffer(64 * 3 * 32), C.create_string_buffer(9 * 32)
+    assert lib.zkb_l2_poseidon_params(ark, mds) == 0
+    cfg = O.get_poseidon_config()
+    want_ark = b"".join(int(v).to_bytes(32, "little") for row in cfg.ark for v in row)
+    want_mds = b"".join(int(v).to_bytes(32, "little") for row in cfg.mds for v in row)
+    assert ark.raw == want_ark and mds.raw == want_mds
+    # host batch entry == one-at-a-time entry
+    import random
+    rnd = random.Random(4)
+    vals = [rnd.randrange(1 << 256) for _ in range(3 * 50)]
+    buf = b"".join(v.to_bytes(32, "little") for v in vals)
+    out = C.create_string_buffer(50 * 32)
+    assert lib.zkb_l2_poseidon_hash_batch_host(3, buf, 50, 4, out) == 0
+    one = C.create_string_buffer(32)
+    for i in (0, 17, 49):
+        assert lib.zkb_l2_poseidon_hash(buf[96 * i:96 * i + 96], 3, one) == 0
+        assert out.raw[32 * i:32 * i + 32] == one.raw
+
+
+@pytest.mark.gpu
+def test_gpu_poseidon_hash_batch_equals_host_hashes():
+    """zkb_l2_poseidon_hash_batch (GPU, n independent leaf hashes) == the native host sponge, arities 0..3, including inputs
+    >= r (reduced mod r as Fr::from_le_bytes_mod_order does) -- and == the oracle's PoseidonSponge for a few."""
+    import ctypes as C
+    import random
+    import zelana_b200
+    lib = zelana_b200.load_library()
+    ctx = zelana_b200.Context(0)
+    rnd = random.Random(6)
+    for arity in (1, 2, 3):
+        n = 1000
+        vals = [rnd.randrange(1 << 256) if i % 7 == 0 else rnd.randrange(R) for i in range(n * arity)]
+        vals[:arity] = [0] * arity
+        buf = b"".join(v.to_bytes(32, "little") for v in vals)
+        host = C.create_string_buffer(n * 32)
+        assert lib.zkb_l2_poseidon_hash_batch_host(arity, buf, n, 4, host) == 0
+        assert ctx.l2_poseidon_hash_batch(arity, buf) == host.raw
+        for i in (1, 500):
+            assert int.from_bytes(host.raw[32 * i:32 * i + 32], "little") == O.poseidon_hash([v % R for v in vals[arity * i:arity * i + arity]])
+    assert len(ctx.l2_poseidon_hash_batch(0, b"", n=3)) == 96
+    ctx.close()

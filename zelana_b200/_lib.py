@@ -146,6 +146,10 @@ SIGNATURES = {
     "zkb_l2_circuit_is_satisfied": (_I, [_P, _P, C.POINTER(_I), C.POINTER(C.c_uint64)]),
     "zkb_l2_roots": (_I, [C.POINTER(L2Witness), C.c_uint64, _P, C.POINTER(L2PublicInputs)]),
     "zkb_l2_poseidon_hash": (_I, [_P, _SZ, _P]),
+    "zkb_l2_poseidon_hash_batch": (_I, [_P, _I, _P, _SZ, _P]),
+    "zkb_l2_poseidon_hash_batch_dev": (_I, [_P, _I, _P, _SZ, _P]),
+    "zkb_l2_poseidon_hash_batch_host": (_I, [_I, _P, _SZ, _I, _P]),
+    "zkb_l2_poseidon_params": (_I, [_P, _P]),
     "zkb_l2_prover_randomness": (_I, [C.c_uint64, _P, _P]),
     "zkb_l2_prove": (_I, [_P, _P, _P, _P, C.POINTER(L2PublicInputs), C.POINTER(L2Witness), _P]),
     "zkb_l2_batch_create": (_I, [_I, _I, C.POINTER(_P)]),

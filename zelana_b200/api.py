@@ -245,6 +245,23 @@ class Context:
     def ntt_dev(self, in_dev, out_dev, log_n, inverse=False, coset=False):
         self._check(self.lib.zkb_ntt_dev(self.h, _devptr(in_dev), _devptr(out_dev), log_n, int(inverse), int(coset)))
 
+    # ---- the L2 circuit's Poseidon, batched
+    def l2_poseidon_hash_batch(self, arity, data, n=None):
+        """n independent Poseidon hashes of `arity` (0..3) elements each with the L2 circuit's parameters -> n x 32 B."""
+        if arity:
+            p, k = _buf(data)
+            n = len(k) // (32 * arity)
+        else:
+            p, k = C.c_void_p(0), None
+        if not n:
+            return b""
+        out = np.empty(n * 32, dtype=np.uint8)
+        self._check(self.lib.zkb_l2_poseidon_hash_batch(self.h, arity, p, n, out.ctypes.data_as(C.c_void_p)))
+        return out.tobytes()
+
+    def l2_poseidon_hash_batch_dev(self, arity, in_dev, n, out_dev):
+        self._check(self.lib.zkb_l2_poseidon_hash_batch_dev(self.h, arity, _devptr(in_dev), n, _devptr(out_dev)))
+
     # ---- MiMC-7 / account Merkle tree (forge stack)
     def mimc_hash(self, arity, data):
         """n independent hash_arity(...) of the forge stack's MiMC-7 (poseidon.nr:62-94): data = n x arity x 32 B LE -> n x 32 B."""

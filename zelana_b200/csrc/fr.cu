@@ -18,6 +18,7 @@ struct NttTables {
 };
 
 struct FrState {
+  Fr* poseidon = nullptr;     // 64 x 3 round constants then the 3 x 3 MDS matrix of the L2 circuit's Poseidon (Montgomery)
   Fr* mimc_states = nullptr;  // [arity] = permute(arity): the state every hash_arity starts from (Montgomery), arity 0..7
   Fr* wr_fwd = nullptr;  // omega_(2^LRMAX)^e
   Fr* wr_inv = nullptr;
@@ -311,6 +312,60 @@ mimc_merkle_root_kernel(const Fr* __restrict__ leaves, const Fr* __restrict__ si
   store_fr(out + i, cur.from_mont());
 }
 
+// ---- Poseidon of the L2 batch circuit: n independent hashes (prover/src/l2_circuit.rs:315-330,477-490: the account, transfer and
+// withdrawal LEAF hashes are independent; the folds over them are chains) ------------------------------------------------------
+// ark-crypto-primitives 0.5.0 PoseidonSponge with get_poseidon_config() (l2_circuit.rs:68-83): state 3 = capacity 1 + rate 2,
+// 8 full + 56 partial rounds of x^5, round = add constants, S-box (all lanes / lane 0), MDS.  hash(e_1..e_k), k <= 3: fresh
+// sponge, absorb (a permutation when the rate is full), permute, squeeze state[1] -- zkb_l2_poseidon_hash on the host.
+constexpr int POS_T = 3, POS_FULL = 8, POS_PARTIAL = 56, POS_ROUNDS = 64;
+
+__device__ __forceinline__ void poseidon_permute(Fr st[POS_T], const Fr* __restrict__ ark, const Fr* __restrict__ mds) {
+#pragma unroll 1
+  for (int r = 0; r < POS_ROUNDS; r++) {
+    const bool full = r < POS_FULL / 2 || r >= POS_FULL / 2 + POS_PARTIAL;
+#pragma unroll
+    for (int i = 0; i < POS_T; i++) st[i] = st[i] + ark[r * POS_T + i];
+#pragma unroll
+    for (int i = 0; i < POS_T; i++) {
+      if (i == 0 || full) {
+        Fr x2 = st[i] * st[i];
+        st[i] = x2 * x2 * st[i];
+      }
+    }
+    Fr nw[POS_T];
+#pragma unroll
+    for (int i = 0; i < POS_T; i++) nw[i] = st[0] * mds[i * POS_T] + st[1] * mds[i * POS_T + 1] + st[2] * mds[i * POS_T + 2];
+#pragma unroll
+    for (int i = 0; i < POS_T; i++) st[i] = nw[i];
+  }
+}
+
+// in: n x arity canonical elements (values >= r are reduced, as Fr::from_le_bytes_mod_order does); out: n canonical hashes
+__global__ void __launch_bounds__(128)
+poseidon_hash_kernel(const Fr* __restrict__ in, int arity, size_t n, const Fr* __restrict__ params, Fr* __restrict__ out) {
+  __shared__ Fr sp[POS_ROUNDS * POS_T + POS_T * POS_T];
+  for (int k = threadIdx.x; k < POS_ROUNDS * POS_T + POS_T * POS_T; k += blockDim.x) sp[k] = params[k];
+  __syncthreads();
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr* ark = sp;
+  const Fr* mds = sp + POS_ROUNDS * POS_T;
+  Fr st[POS_T] = {Fr::zero(), Fr::zero(), Fr::zero()};
+  int start = 0;
+  for (int k = 0; k < arity; k++) {
+    if (start == 2) {
+      poseidon_permute(st, ark, mds);
+      start = 0;
+    }
+    Fr v = load_fr(in + i * arity + k);
+    while (!fr_is_canonical(v)) v = v - Fr::modulus();   // < 2^256 < 6 r: mod-order reduction of a 32-byte value
+    st[1 + start] = st[1 + start] + v.to_mont();
+    start++;
+  }
+  poseidon_permute(st, ark, mds);
+  store_fr(out + i, st[1].from_mont());
+}
+
 int ensure_wr(zkb_ctx* ctx, FrState* S) {
   if (S->wr_fwd) return ZKB_OK;
   const uint32_t cnt = 1u << (NTT_LRMAX - 1);
@@ -387,6 +442,7 @@ void fr_state_free(zkb_ctx* ctx) {
   FrState* S = static_cast<FrState*>(ctx->fr_state);
   g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
   if (S->mimc_states) cudaFree(S->mimc_states);
+  if (S->poseidon) cudaFree(S->poseidon);
   if (S->wr_fwd) cudaFree(S->wr_fwd);
   if (S->wr_inv) cudaFree(S->wr_inv);
   for (auto& kv : S->tables) cudaFree(kv.second.mem);
@@ -407,6 +463,33 @@ int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t
   CUDA_TRY(ctx, cudaGetLastError());
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->tmp2.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return check_flag(ctx, "zkb_field_op");
+}
+
+int poseidon_hash_dev(zkb_ctx* ctx, const uint8_t* params_canonical, int arity, const Fr* in, size_t n, Fr* out) {
+  FrState* S = state(ctx);
+  constexpr size_t NP = POS_ROUNDS * POS_T + POS_T * POS_T;
+  if (!S->poseidon) {
+    if (!params_canonical) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "poseidon: parameters not loaded");
+    Fr* raw = nullptr;
+    CUDA_TRY(ctx, cudaMalloc(&raw, NP * sizeof(Fr)));
+    cudaError_t e = cudaMalloc(&S->poseidon, NP * sizeof(Fr));
+    if (e != cudaSuccess) {
+      cudaFree(raw);
+      S->poseidon = nullptr;
+      CUDA_TRY(ctx, e);
+    }
+    ZKB_TRY(clear_flag(ctx));
+    cudaMemcpyAsync(raw, params_canonical, NP * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream);
+    int rc = fr_to_mont(ctx, raw, S->poseidon, NP);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(raw);
+    if (rc != ZKB_OK) return rc;
+  }
+  if (!n) return ZKB_OK;
+  poseidon_hash_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(in, arity, n, S->poseidon, out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
 }
 
 static int ensure_mimc_states(zkb_ctx* ctx, const Fr** out) {

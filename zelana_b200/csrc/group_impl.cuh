@@ -352,7 +352,7 @@ int bases_load_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int validate, t
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || (!host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_load: bad argument");
   *out = nullptr;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   H* h = nullptr;
   ZKB_TRY(bases_alloc<F>(ctx, n, &h));
   if (n) {
@@ -376,7 +376,7 @@ int bases_load_compressed_impl(zkb_ctx* ctx, const uint8_t* host, size_t n, int 
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || (!host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_load_compressed: bad argument");
   *out = nullptr;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   H* h = nullptr;
   ZKB_TRY(bases_alloc<F>(ctx, n, &h));
   if (n) {
@@ -496,7 +496,7 @@ int bases_generate_impl(zkb_ctx* ctx, const void* k_dev, size_t n, typename Grou
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || (!k_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_generate: bad argument");
   *out = nullptr;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   ZKB_TRY(ensure_fixed_table<F>(ctx));
   H* h = nullptr;
   ZKB_TRY(bases_alloc<F>(ctx, n, &h));
@@ -528,7 +528,7 @@ int bases_read_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* b, size_t of
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!b || !out_host || offset + n > b->n) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_read: bad range");
   if (n == 0) return ZKB_OK;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, ctx->tmp0.reserve(n * sizeof(Affine<F>)));
   affine_export_kernel<F><<<blocks_for(n, 128), 128, 0, ctx->stream>>>(b->p + offset, ctx->tmp0.as<uint32_t>(), n);
   ctx->launches++;
@@ -541,7 +541,7 @@ int bases_read_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* b, size_t of
 template <class F>
 void bases_free_impl(typename GroupOf<F>::Bases* b) {
   if (!b) return;
-  cudaSetDevice(b->device);
+  DeviceGuard dg(b->device);
   g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);  // captured prove graphs hold these pointers
   if (b->p) cudaFree(b->p);
   if (b->inf_mask) cudaFree(b->inf_mask);
@@ -555,7 +555,7 @@ int msm_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t o
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!bases || offset + n > bases->n || (!scalars_dev && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bad bases range or scalars");
   if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: bases live on device %d, ctx on %d", bases->device, ctx->device);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaError_t e = msm_run<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset, static_cast<const uint32_t*>(scalars_dev), n,
                              static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
   if (e != cudaSuccess) {
@@ -574,7 +574,7 @@ int msm_batch_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, si
   if (!bases || offset + n > bases->n || (!scalars_dev && n) || batch < 1 || stride < n)
     ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_batch: bad bases range, scalars or batch");
   if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_batch: bases live on device %d, ctx on %d", bases->device, ctx->device);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaError_t e = msm_run_batch<F>(ctx, bases->p, bases->n, bases->inf_mask, bases->c, bases->nwin, offset,
                                    static_cast<const uint32_t*>(scalars_dev), n, stride, batch,
                                    static_cast<XYZZ<F>*>(out_partial_dev), static_cast<uint32_t*>(out_affine_dev));
@@ -592,7 +592,7 @@ int msm_entries_debug_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases
                            size_t stride, int batch, void* out_keys, void* out_vals, void* out_count) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!bases || offset + n > bases->n || !scalars_dev || batch < 1 || n == 0) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_entries_debug: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   MsmLayout<F> L = msm_layout<F>(ctx->sm_count, bases->c, bases->nwin, n, 1, batch);
   CUDA_TRY(ctx, ctx->msm_ws.reserve(L.bytes));
   char* base = static_cast<char*>(ctx->msm_ws.p);
@@ -621,7 +621,7 @@ int bases_build_comb(zkb_ctx* ctx, typename GroupOf<F>::Bases* b, int c) {
   if (!b || c < 2 || c > 16) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "bases_build_comb: bad argument");
   if (b->comb && b->comb_c == c) return ZKB_OK;
   if (b->n == 0) return ZKB_OK;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   const int nwin = msm_windows_for(c);
   Affine<F>* wt = nullptr;     // window tables for width c
   bool own_wt = false;
@@ -664,7 +664,7 @@ int msm_comb_dev_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, siz
   if (!bases || !bases->comb || offset + n > bases->n || (!scalars_dev && n) || batch < 1 || stride < n || !out_partial_dev)
     ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_comb: bad bases range, scalars or batch (or no comb table)");
   if (bases->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_comb: bases live on device %d, ctx on %d", bases->device, ctx->device);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaError_t e = msm_run_comb<F>(ctx, bases->comb, bases->comb_c, bases->comb_nwin, bases->inf_mask, offset,
                                   static_cast<const uint32_t*>(scalars_dev), n, stride, batch, static_cast<XYZZ<F>*>(out_partial_dev));
   if (e != cudaSuccess) {
@@ -724,7 +724,7 @@ int msm_host_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases, size_t 
                   uint8_t* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || (!scalars_host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm: null argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, ctx->res.reserve(512));
   ZKB_TRY((msm_host_enqueue<F>(ctx, bases, offset, scalars_host, n, ctx->res.p, nullptr)));
   CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->res.p, sizeof(Affine<F>), cudaMemcpyDeviceToHost, ctx->stream));
@@ -739,7 +739,7 @@ int msm_host_partial_impl(zkb_ctx* ctx, const typename GroupOf<F>::Bases* bases,
                           void* out_partial_dev) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out_partial_dev || (!scalars_host && n)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_partial: null argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   return msm_host_enqueue<F>(ctx, bases, offset, scalars_host, n, nullptr, out_partial_dev);
 }
 
@@ -764,7 +764,7 @@ int msm_multi_impl(zkb_ctx* const* ctxs, const typename GroupOf<F>::Bases* const
   auto work = [&](int i, size_t off) {
     zkb_ctx* ctx = ctxs[i];
     rc[size_t(i)] = [&]() -> int {
-      ZKB_TRY(set_device(ctx));
+      ZKB_ON_DEVICE(ctx);
       CUDA_TRY(ctx, ctx->res.reserve(512));
       ZKB_TRY((msm_host_enqueue<F>(ctx, bases[i], 0, scalars_host + off * 32, bases[i]->n, nullptr, ctx->res.p)));
       CUDA_TRY(ctx, cudaMemcpyAsync(parts.data() + size_t(i) * PB, ctx->res.p, PB, cudaMemcpyDeviceToHost, ctx->stream));
@@ -794,7 +794,7 @@ int msm_multi_impl(zkb_ctx* const* ctxs, const typename GroupOf<F>::Bases* const
       if (i) c0->err = ctxs[i]->err;
       return rc[size_t(i)];
     }
-  ZKB_TRY(set_device(c0));
+  ZKB_ON_DEVICE(c0);
   CUDA_TRY(c0, c0->tmp1.reserve(parts.size()));
   CUDA_TRY(c0, c0->res.reserve(512));
   CUDA_TRY(c0, cudaMemcpyAsync(c0->tmp1.p, parts.data(), parts.size(), cudaMemcpyHostToDevice, c0->stream));
@@ -808,7 +808,7 @@ template <class F>
 int msm_combine_impl(zkb_ctx* ctx, const void* parts, int k, void* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!parts || k <= 0 || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "msm_combine: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   msm_combine_kernel<F><<<1, 32, 0, ctx->stream>>>(static_cast<const XYZZ<F>*>(parts), k, static_cast<uint32_t*>(out));
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());

@@ -207,6 +207,29 @@ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // zkb200.cu
 int set_device(zkb_ctx* ctx);
+
+// Every entry point runs on its context's device and puts the calling thread's current device back when it returns: a host
+// that drives several GPUs from one thread (or mixes this library with another CUDA library, as the tests do with torch) must
+// not find its current device changed behind its back.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+  }
+  explicit DeviceGuard(int device) : DeviceGuard() { cudaSetDevice(device); }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ZKB_ON_DEVICE(ctx)   \
+  zkb::DeviceGuard _zkb_dg;  \
+  ZKB_TRY(zkb::set_device(ctx))
 int clear_flag(zkb_ctx* ctx);
 int check_flag(zkb_ctx* ctx, const char* what);  // synchronises the stream
 
@@ -276,6 +299,8 @@ struct CsrDev {
 int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);
 // MiMC-7 (forge stack): n hashes of `arity` elements; n Merkle roots along depth-long paths.  Flag non-canonical input in ctx->flag.
+// Poseidon of the L2 circuit: params_canonical = 64 x 3 round constants | 3 x 3 MDS (canonical bytes; needed on the first call)
+int poseidon_hash_dev(zkb_ctx* ctx, const uint8_t* params_canonical, int arity, const Fr* in, size_t n, Fr* out);
 int mimc_hash_dev(zkb_ctx* ctx, int arity, const Fr* in, size_t n, Fr* out);
 int mimc_merkle_roots_dev(zkb_ctx* ctx, const Fr* leaves, const Fr* siblings, const uint8_t* bits, size_t n, int depth, Fr* out);  // flags non-canonical input in ctx->flag
 int ntt_dev_impl(zkb_ctx* ctx, const Fr* in, Fr* out, int logn, int inverse, int coset);

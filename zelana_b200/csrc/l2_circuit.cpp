@@ -1274,6 +1274,45 @@ int zkb_l2_poseidon_hash(const uint8_t* elems, size_t n, uint8_t out[32]) {
   return ZKB_OK;
 }
 
+// get_poseidon_config() (prover/src/l2_circuit.rs:68-83: find_poseidon_ark_and_mds for 254 bits, rate 2, 8 full + 56 partial
+// rounds) as canonical bytes: ark_out = 64 rounds x 3 lanes x 32 B, mds_out = 3 x 3 x 32 B (row-major).  What the GPU hash
+// kernel behind zkb_l2_poseidon_hash_batch uploads; also a parity hook against the oracle's parameter generator.
+int zkb_l2_poseidon_params(uint8_t* ark_out, uint8_t* mds_out) {
+  if (!ark_out || !mds_out) return ZKB_ERR_INVALID_ARG;
+  try {
+    const l2::PoseidonConfig& cfg = l2::config();
+    for (int r = 0; r < l2::ROUNDS; ++r)
+      for (int i = 0; i < l2::T; ++i) l2::to_le_bytes(cfg.ark[r][i], ark_out + 32 * (r * l2::T + i));
+    for (int i = 0; i < l2::T; ++i)
+      for (int j = 0; j < l2::T; ++j) l2::to_le_bytes(cfg.mds[i][j], mds_out + 32 * (i * l2::T + j));
+    return ZKB_OK;
+  }
+  ZKB_L2_CATCH_ALL()
+}
+
+// n independent hashes on `threads` host threads with the native sponge the witness walkers use: the host side of the
+// GPU-versus-host measurement of the leaf hashes (tools/poseidon_leaf_bench.py), and a batch convenience for hosts.
+int zkb_l2_poseidon_hash_batch_host(int arity, const uint8_t* in, size_t n, int threads, uint8_t* out) {
+  if (arity < 0 || arity > 3 || (n && (!out || (arity && !in))) || threads < 1 || threads > 256) return ZKB_ERR_INVALID_ARG;
+  try {
+    auto work = [&](size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; ++i) {
+        l2::Fr e[3];
+        for (int k = 0; k < arity; ++k) e[k] = l2::from_le_bytes_mod_order(in + 32 * (i * size_t(arity) + k), 32);
+        l2::Fr h = arity == 0 ? l2::hash_native({}) : arity == 1 ? l2::hash_native({e[0]})
+                   : arity == 2 ? l2::hash_native({e[0], e[1]}) : l2::hash_native({e[0], e[1], e[2]});
+        l2::to_le_bytes(h, out + 32 * i);
+      }
+    };
+    JoinGuard jg;
+    const size_t step = (n + size_t(threads) - 1) / size_t(threads);
+    for (int t = 1; t < threads; ++t) jg.th.emplace_back(work, std::min(n, step * size_t(t)), std::min(n, step * size_t(t + 1)));
+    work(0, std::min(n, step));
+    return ZKB_OK;
+  }
+  ZKB_L2_CATCH_ALL()
+}
+
 int zkb_l2_prover_randomness(uint64_t batch_id, uint8_t r[32], uint8_t s[32]) {
   if (!r || !s) return ZKB_ERR_INVALID_ARG;
   l2::StdRng rng(batch_id);

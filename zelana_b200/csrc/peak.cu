@@ -62,7 +62,7 @@ using namespace zkb;
 extern "C" int zkb_bench_int32_peak(zkb_ctx* ctx, int variant, int iters, double* mul32_per_s, double* elapsed_ms) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (variant < 0 || variant > 1 || iters <= 0 || !mul32_per_s) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_bench_int32_peak: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, ctx->tmp0.reserve(4096));
   std::vector<uint32_t> seed(64);
   for (int i = 0; i < 64; i++) seed[i] = 0x9e3779b9u * (i + 1);

@@ -195,14 +195,26 @@ __device__ __forceinline__ uint32_t tile_lookback(uint32_t* state, uint32_t tile
   }
   st_volatile_u32(mine, count | SORT_FLAG_AGG);
   uint32_t prev = 0;
-  for (long long t = (long long)tile - 1;; t--) {
-    const uint32_t* theirs = state + size_t(t) * SORT_BINS + b;
-    uint32_t v;
-    do {
-      v = ld_volatile_u32(theirs);
-    } while ((v >> 30) == 0u);
-    prev += v & SORT_VAL_MASK;
-    if ((v >> 30) == 2u) break;
+  // Walk back over the predecessors eight at a time: the eight loads are independent, so a walk of w tiles costs ~w / 8 memory
+  // round trips instead of w (one thread per bin walks alone; with ~600 tiles in flight the serial walk was most of a tile's
+  // time).  A word that is still unpublished (flag 0) is re-read until it is.
+  long long t = (long long)tile - 1;
+  bool done = false;
+  while (!done) {
+    uint32_t v[8];
+    const int cnt = t + 1 < 8 ? int(t + 1) : 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k < cnt) v[k] = ld_volatile_u32(state + size_t(t - k) * SORT_BINS + b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k < cnt && !done) {
+        while ((v[k] >> 30) == 0u) v[k] = ld_volatile_u32(state + size_t(t - k) * SORT_BINS + b);
+        prev += v[k] & SORT_VAL_MASK;
+        if ((v[k] >> 30) == 2u) done = true;
+      }
+    }
+    t -= cnt;   // tile 0 publishes an inclusive word, so the walk always ends at or before it
   }
   st_volatile_u32(mine, (prev + count) | SORT_FLAG_INC);
   return prev;

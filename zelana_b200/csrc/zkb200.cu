@@ -82,6 +82,7 @@ extern "C" int zkb_ctx_create(int device, zkb_ctx** out) {
   zkb_ctx* ctx = new (std::nothrow) zkb_ctx();
   if (!ctx) return ZKB_ERR_OOM;
   ctx->device = device;
+  DeviceGuard dg;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
@@ -99,7 +100,7 @@ extern "C" int zkb_ctx_create(int device, zkb_ctx** out) {
 
 extern "C" int zkb_ctx_set_stream(zkb_ctx* ctx, void* cuda_stream) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   if (ctx->own_stream && ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
@@ -116,14 +117,14 @@ extern "C" int zkb_ctx_set_stream(zkb_ctx* ctx, void* cuda_stream) {
 
 extern "C" int zkb_ctx_synchronize(zkb_ctx* ctx) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   return ZKB_OK;
 }
 
 extern "C" void zkb_ctx_destroy(zkb_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard dg(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& g : ctx->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -219,7 +220,7 @@ extern "C" int zkb_prof_enable(zkb_ctx* ctx, int on) {
 }
 
 static int prof_collect(zkb_ctx* ctx) {
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   for (auto& sp : ctx->prof.pending) {
     float ms = 0.f;
@@ -260,21 +261,21 @@ extern "C" int zkb_field_op(zkb_ctx* ctx, int field, int op, const uint8_t* a, c
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (field < 0 || field > 1 || op < 0 || op > 4 || !a || !out || (op <= 2 && !b)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_field_op: bad argument");
   if (n == 0) return ZKB_OK;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   return field == 0 ? fr_field_op(ctx, op, a, b, n, out) : fq_field_op(ctx, op, a, b, n, out);
 }
 
 extern "C" int zkb_scalar_mul(zkb_ctx* ctx, int group, const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if ((group != 1 && group != 2) || !points || !scalars || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_scalar_mul: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   return group == 1 ? scalar_mul_impl<Fq>(ctx, points, scalars, n, out) : scalar_mul_impl<Fq2>(ctx, points, scalars, n, out);
 }
 
 extern "C" int zkb_point_sum(zkb_ctx* ctx, int group, const uint8_t* points, size_t n, uint8_t* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if ((group != 1 && group != 2) || (!points && n) || !out) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_point_sum: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   return group == 1 ? point_sum_impl<Fq>(ctx, points, n, out) : point_sum_impl<Fq2>(ctx, points, n, out);
 }
 
@@ -350,7 +351,7 @@ extern "C" int zkb_debug_msm_batch(zkb_ctx* ctx, int group, const void* bases, s
                                    size_t stride, int batch, void* out_affine_dev) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if ((group != 1 && group != 2) || !bases || !out_affine_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_debug_msm_batch: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   void* part = nullptr;
   const size_t psz = group == 1 ? sizeof(XYZZ<Fq>) : sizeof(XYZZ<Fq2>);
   CUDA_TRY(ctx, ctx->bpart.reserve(size_t(batch > 0 ? batch : 1) * psz));
@@ -365,7 +366,7 @@ extern "C" int zkb_debug_msm_comb(zkb_ctx* ctx, int group, void* bases, size_t o
                                   int batch, int c, void* out_affine_dev) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if ((group != 1 && group != 2) || !bases || !out_affine_dev || batch < 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_debug_msm_comb: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   const size_t psz = group == 1 ? sizeof(XYZZ<Fq>) : sizeof(XYZZ<Fq2>);
   CUDA_TRY(ctx, ctx->bpart.reserve(size_t(batch) * psz));
   if (group == 1) {
@@ -385,7 +386,7 @@ extern "C" int zkb_debug_msm_entries(zkb_ctx* ctx, const zkb_g1_bases* bases, si
 extern "C" int zkb_ntt_dev(zkb_ctx* ctx, const void* in_dev, void* out_dev, int log_n, int direction, int coset) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!in_dev || !out_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: null buffer");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   return ntt_dev_impl(ctx, static_cast<const Fr*>(in_dev), static_cast<Fr*>(out_dev), log_n, direction, coset);
 }
 
@@ -393,7 +394,7 @@ extern "C" int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, 
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!in_host || !out_host) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: null buffer");
   if (log_n < 0 || log_n > 28) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "ntt: log_n %d outside [0, 28]", log_n);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   size_t bytes = (size_t(1) << log_n) * 32;
   CUDA_TRY(ctx, ctx->scal.reserve(bytes));
   CUDA_TRY(ctx, ctx->tmp2.reserve(bytes));
@@ -404,11 +405,45 @@ extern "C" int zkb_ntt(zkb_ctx* ctx, const uint8_t* in_host, uint8_t* out_host, 
   return ZKB_OK;
 }
 
+// =============================================================================================== L2-circuit Poseidon, batched
+static int poseidon_params(zkb_ctx* ctx, std::vector<uint8_t>& buf) {
+  buf.resize((64 * 3 + 9) * 32);
+  if (zkb_l2_poseidon_params(buf.data(), buf.data() + 64 * 3 * 32) != ZKB_OK) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "poseidon parameters unavailable");
+  return ZKB_OK;
+}
+
+extern "C" int zkb_l2_poseidon_hash_batch_dev(zkb_ctx* ctx, int arity, const void* in_dev, size_t n, void* out_dev) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (arity < 0 || arity > 3 || (n && (!out_dev || (arity && !in_dev)))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_l2_poseidon_hash_batch: arity %d outside [0, 3] or null buffer", arity);
+  ZKB_ON_DEVICE(ctx);
+  std::vector<uint8_t> prm;
+  try {
+    ZKB_TRY(poseidon_params(ctx, prm));
+  } catch (const std::bad_alloc&) {
+    ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_l2_poseidon_hash_batch: host allocation failed");
+  }
+  return poseidon_hash_dev(ctx, prm.data(), arity, static_cast<const Fr*>(in_dev), n, static_cast<Fr*>(out_dev));
+}
+
+extern "C" int zkb_l2_poseidon_hash_batch(zkb_ctx* ctx, int arity, const uint8_t* in_host, size_t n, uint8_t* out_host) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (arity < 0 || arity > 3 || (n && (!out_host || (arity && !in_host)))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_l2_poseidon_hash_batch: arity %d outside [0, 3] or null buffer", arity);
+  if (!n) return ZKB_OK;
+  ZKB_ON_DEVICE(ctx);
+  CUDA_TRY(ctx, ctx->tmp0.reserve(n * size_t(arity ? arity : 1) * 32));
+  CUDA_TRY(ctx, ctx->tmp2.reserve(n * 32));
+  if (arity) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->tmp0.p, in_host, n * size_t(arity) * 32, cudaMemcpyHostToDevice, ctx->stream));
+  ZKB_TRY(zkb_l2_poseidon_hash_batch_dev(ctx, arity, ctx->tmp0.p, n, ctx->tmp2.p));
+  CUDA_TRY(ctx, cudaMemcpyAsync(out_host, ctx->tmp2.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+  return ZKB_OK;
+}
+
 // =============================================================================================== MiMC-7 / account Merkle tree
 extern "C" int zkb_mimc_hash_dev(zkb_ctx* ctx, int arity, const void* in_dev, size_t n, void* out_dev) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (arity < 1 || arity > 6 || (n && (!in_dev || !out_dev))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_hash: arity %d outside [1, 6] or null buffer", arity);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   ZKB_TRY(clear_flag(ctx));
   ZKB_TRY(mimc_hash_dev(ctx, arity, static_cast<const Fr*>(in_dev), n, static_cast<Fr*>(out_dev)));
   return ZKB_OK;   // asynchronous: a non-canonical input surfaces at the next call that checks the flag (the host variant does)
@@ -418,7 +453,7 @@ extern "C" int zkb_mimc_hash(zkb_ctx* ctx, int arity, const uint8_t* in_host, si
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (arity < 1 || arity > 6 || (n && (!in_host || !out_host))) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_hash: arity %d outside [1, 6] or null buffer", arity);
   if (!n) return ZKB_OK;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   CUDA_TRY(ctx, ctx->tmp0.reserve(n * size_t(arity) * 32));
   CUDA_TRY(ctx, ctx->tmp2.reserve(n * 32));
   ZKB_TRY(clear_flag(ctx));
@@ -433,7 +468,7 @@ extern "C" int zkb_mimc_merkle_roots_dev(zkb_ctx* ctx, const void* leaves_dev, c
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (depth < 0 || depth > 64 || (n && (!leaves_dev || !out_dev || (depth && (!siblings_dev || !bits_dev)))))
     ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_merkle_roots: depth %d outside [0, 64] or null buffer", depth);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   ZKB_TRY(clear_flag(ctx));
   return mimc_merkle_roots_dev(ctx, static_cast<const Fr*>(leaves_dev), static_cast<const Fr*>(siblings_dev), bits_dev, n, depth,
                                static_cast<Fr*>(out_dev));
@@ -445,7 +480,7 @@ extern "C" int zkb_mimc_merkle_roots(zkb_ctx* ctx, const uint8_t* leaves, const 
   if (depth < 0 || depth > 64 || (n && (!leaves || !out || (depth && (!siblings || !bits)))))
     ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_mimc_merkle_roots: depth %d outside [0, 64] or null buffer", depth);
   if (!n) return ZKB_OK;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   const size_t nd = n * size_t(depth);
   CUDA_TRY(ctx, ctx->tmp0.reserve(n * 32));
   CUDA_TRY(ctx, ctx->tmp1.reserve(nd * 32 + 32));
@@ -510,7 +545,7 @@ extern "C" int zkb_r1cs_load(zkb_ctx* ctx, const zkb_r1cs_desc* desc, zkb_r1cs**
   int lg = 0;
   while ((uint64_t(1) << lg) < dom) lg++;
   if (lg > 28) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "r1cs: domain 2^%d exceeds Fr two-adicity 28", lg);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   zkb_r1cs* m = new (std::nothrow) zkb_r1cs();
   if (!m) ZKB_FAIL(ctx, ZKB_ERR_OOM, "r1cs: host allocation failed");
   m->device = ctx->device;
@@ -532,7 +567,7 @@ extern "C" int zkb_r1cs_load(zkb_ctx* ctx, const zkb_r1cs_desc* desc, zkb_r1cs**
 
 extern "C" void zkb_r1cs_free(zkb_r1cs* m) {
   if (!m) return;
-  cudaSetDevice(m->device);
+  DeviceGuard dg(m->device);
   csr_free(m->a);
   csr_free(m->b);
   csr_free(m->c);
@@ -565,7 +600,7 @@ extern "C" int zkb_witness_map(zkb_ctx* ctx, const zkb_r1cs* m, const uint8_t* z
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!m || !z_host || !h_out_host) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_witness_map: null argument");
   if (m->device != ctx->device) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_witness_map: matrices on another device");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   const size_t n = size_t(1) << m->log_domain, nv = m->ni + m->nw;
   ZKB_TRY(reserve_prove_bufs(ctx, n, nv, m->nw));
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pz.p, z_host, nv * 32, cudaMemcpyHostToDevice, ctx->stream));
@@ -640,7 +675,7 @@ int pk_load_common(zkb_ctx* ctx, const zkb_pk_desc* d, int validate, int shard, 
   if (d->a_len < 1 || d->b_g1_len != d->a_len || d->b_g2_len != d->a_len)
     ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load: a/b_g1/b_g2 query lengths %zu/%zu/%zu disagree", d->a_len, d->b_g1_len, d->b_g2_len);
   if (d->l_len > d->a_len - 1) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load: l_query longer than the witness");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   zkb_pk* pk = new (std::nothrow) zkb_pk();
   if (!pk) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_load: host allocation failed");
   pk->device = ctx->device;
@@ -718,7 +753,7 @@ extern "C" int zkb_pk_load_compressed(zkb_ctx* ctx, const uint8_t* bytes, size_t
   if (n_a < 1 || n_b1 != n_a || n_b2 != n_a)
     ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: a/b_g1/b_g2 query lengths %zu/%zu/%zu disagree", n_a, n_b1, n_b2);
   if (n_l > n_a - 1) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_load_compressed: l_query longer than the witness");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   zkb_pk* pk = new (std::nothrow) zkb_pk();
   if (!pk) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_load_compressed: host allocation failed");
   pk->device = ctx->device;
@@ -795,7 +830,7 @@ extern "C" int zkb_pk_synthetic_shard(zkb_ctx* ctx, size_t num_vars, size_t num_
   size_t need = num_vars + 2 > h_len ? num_vars + 2 : h_len;
   if (k_len < need + 4) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_pk_synthetic: need %zu scalars, got %zu", need + 4, k_len);
   *out = nullptr;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   zkb_pk* pk = new (std::nothrow) zkb_pk();
   if (!pk) ZKB_FAIL(ctx, ZKB_ERR_OOM, "zkb_pk_synthetic: host allocation failed");
   pk->device = ctx->device;
@@ -880,7 +915,7 @@ extern "C" int zkb_setup(zkb_ctx* ctx, const zkb_r1cs_desc* d, const zkb_setup_p
   while ((uint64_t(1) << lg) < nc + ni) lg++;
   if (lg > 28) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_setup: domain 2^%d exceeds Fr two-adicity 28", lg);
   const size_t n = size_t(1) << lg;
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaStream_t st = ctx->stream;
 
   CscHost csc[3];
@@ -1179,7 +1214,7 @@ int prove_enqueue(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8
   const size_t n = size_t(1) << m->log_domain;
   if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: key has %zu variables, circuit has %zu", who, pk->nv, nv);
   if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "%s: l_query has %zu points, circuit has %zu witness variables", who, pk->nw, nw);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaStream_t st = ctx->stream;
   ZKB_TRY(reserve_prove_bufs(ctx, n, nv, nw));
   Fr* rs = ctx->prs.as<Fr>();
@@ -1239,7 +1274,7 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
   const size_t n = size_t(1) << m->log_domain;
   if (pk->nv != nv) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove_batch: key has %zu variables, circuit has %zu", pk->nv, nv);
   if (pk->nw != nw) ZKB_FAIL(ctx, ZKB_ERR_SHAPE, "zkb_prove_batch: l_query has %zu points, circuit has %zu witness variables", pk->nw, nw);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaStream_t st = ctx->stream;
   ZKB_TRY(ensure_lanes(ctx));
   if (!pk->fb_delta1) {
@@ -1258,11 +1293,11 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
   }
   if (pk->comb_state == 0) {
     // Small key, large HBM: tables of every digit multiple for all five query vectors (msm.cuh comb_build_kernel) turn each
-    // MSM into a sum of gathered points.  MEASURED AND NOT ADOPTED as the default (profiles/r02_comb_tables_rejected.txt): with
-    // one thread per range of points the work per thread follows the scalars (a full-size scalar is 22 additions, a bit is
-    // one) and warps wait for their slowest lane -- 4.2 G additions/s against the 6.3 G/s of the equal-chunk bucket
-    // accumulation, 4 400 instead of 5 070 proofs/s.  Opt in with ZKB_COMB=1 (widest window <= 12 whose tables fit 60 % of the
-    // free memory; ZKB_COMB_MAX_GB caps it).
+    // MSM into a sum of gathered points: no buckets, no sort, no bucket reduction.  MEASURED AND NOT ADOPTED as the default
+    // (profiles/r02_comb_tables_rejected.txt): even with the entries compacted and dealt out evenly the gathers from a
+    // 75 + 35 GB table run the additions at 5.4 G/s (G1) and less than half the bucket kernel's rate (G2, 128-byte points);
+    // the sub-batch takes 49.0 ms of kernels against 49.3 ms for the bucket method -- no gain for 110 GB of HBM.
+    // Opt in with ZKB_COMB=1 (widest window <= 12 whose tables fit 60 % of the free memory; ZKB_COMB_MAX_GB caps it).
     int chosen = 0;
     const char* on = getenv("ZKB_COMB");
     if (on && on[0] == '1') {
@@ -1383,7 +1418,7 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
 extern "C" int zkb_prove_batch_end(zkb_ctx* ctx, size_t K, uint8_t* out) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!out || K * 256 > ctx->bpinned_cap) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch_end: no batch of %zu proofs in flight", K);
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   int rc = check_flag(ctx, "witness assignment");   // waits for the stream
   if (rc != ZKB_OK) return rc;
   memcpy(out, ctx->bpinned, K * 256);
@@ -1431,7 +1466,7 @@ extern "C" int zkb_prove_combine(zkb_ctx* ctx, const void* partials_dev, int wor
                                  uint8_t out_a[64], uint8_t out_b[128], uint8_t out_c[64]) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!partials_dev || world < 1 || !r || !s || !out_a || !out_b || !out_c) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_combine: bad argument");
-  ZKB_TRY(set_device(ctx));
+  ZKB_ON_DEVICE(ctx);
   cudaStream_t st = ctx->stream;
   CUDA_TRY(ctx, ctx->prs.reserve(64));
   CUDA_TRY(ctx, ctx->ppts.reserve(4 * sizeof(XYZZ<Fq>) + sizeof(XYZZ<Fq2>) + 64 + 128 + 64 + sizeof(XYZZ<Fq>)));
@@ -1470,7 +1505,7 @@ extern "C" int zkb_prove_multi(zkb_ctx* const* ctxs, const zkb_pk* const* pk_sha
   auto work = [&](int i) {
     zkb_ctx* ctx = ctxs[i];
     rc[size_t(i)] = [&]() -> int {
-      ZKB_TRY(set_device(ctx));
+      ZKB_ON_DEVICE(ctx);
       CUDA_TRY(ctx, ctx->tmp2.reserve(ZKB_PROVE_PARTIAL_BYTES));
       ZKB_TRY(zkb_prove_partial(ctx, pk_shards[i], ms[i], z_host, r, s, ctx->tmp2.p));
       CUDA_TRY(ctx, cudaMemcpy(parts.data() + size_t(i) * ZKB_PROVE_PARTIAL_BYTES, ctx->tmp2.p, ZKB_PROVE_PARTIAL_BYTES, cudaMemcpyDeviceToHost));
@@ -1495,7 +1530,7 @@ extern "C" int zkb_prove_multi(zkb_ctx* const* ctxs, const zkb_pk* const* pk_sha
       if (i) c0->err = ctxs[i]->err;
       return rc[size_t(i)];
     }
-  ZKB_TRY(set_device(c0));
+  ZKB_ON_DEVICE(c0);
   CUDA_TRY(c0, c0->tmp1.reserve(parts.size()));
   CUDA_TRY(c0, cudaMemcpy(c0->tmp1.p, parts.data(), parts.size(), cudaMemcpyHostToDevice));
   return zkb_prove_combine(c0, c0->tmp1.p, n_gpus, r, s, out_a, out_b, out_c);
