@@ -112,6 +112,42 @@ struct DigitWalker {
   }
 };
 
+// The same recoding with the scalar's words parked in shared memory, word-major (word k of thread t at w[k * stride + t]: bank
+// = t, conflict-free): a window is two shared-memory loads instead of the sixteen predicated selects that keep a dynamically
+// indexed scalar in registers -- the entry kernels were bound by exactly those ALU instructions (pass 0: ALU pipe 78 % busy,
+// profiles/r02_ncu_sort_pass0.txt).
+struct SmemDigitWalker {
+  const uint32_t* w;
+  int stride;
+  uint32_t carry;
+  __device__ __forceinline__ void park(uint32_t* base, int stride_, int t, const uint32_t* p) {
+    const uint4* sp = reinterpret_cast<const uint4*>(p);
+    uint4 lo = sp[0], hi = sp[1];
+    uint32_t* d = base + t;
+    d[0] = lo.x; d[stride_] = lo.y; d[2 * stride_] = lo.z; d[3 * stride_] = lo.w;
+    d[4 * stride_] = hi.x; d[5 * stride_] = hi.y; d[6 * stride_] = hi.z; d[7 * stride_] = hi.w;
+    d[8 * stride_] = 0;
+    w = d;
+    stride = stride_;
+    carry = 0;
+  }
+  __device__ __forceinline__ uint32_t next(int win, int c, uint32_t& neg) {
+    const int bit = win * c;
+    const int word = bit >> 5, sh = bit & 31;   // word <= 7: the last window starts below bit 255
+    const uint32_t lo = w[word * stride], hi = w[(word + 1) * stride];
+    uint32_t v = (__funnelshift_r(lo, hi, sh) & ((1u << c) - 1u)) + carry;
+    neg = 0;
+    if (v > (1u << (c - 1))) {
+      v = (1u << c) - v;
+      neg = 1;
+      carry = 1;
+    } else {
+      carry = 0;
+    }
+    return v;
+  }
+};
+
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -125,14 +161,15 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
 static __global__ void __launch_bounds__(256)
 msm_entry_hist_kernel(EntrySource src, SortPlan plan, uint32_t* __restrict__ hdr) {
   __shared__ uint32_t sh[SORT_MAX_PASSES * SORT_BINS];
+  __shared__ uint32_t words[9 * 256];
   for (int i = threadIdx.x; i < SORT_MAX_PASSES * SORT_BINS; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const size_t npts = size_t(src.batch) * src.n;
   for (size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x; g < npts; g += size_t(gridDim.x) * blockDim.x) {
     const size_t p = g / src.n, i = g - p * src.n;
     if (src.inf_mask && src.inf_mask[src.first + i]) continue;
-    DigitWalker dw;
-    dw.load(src.scalars + (p * src.stride + i) * 8);
+    SmemDigitWalker dw;   // each thread reads back only the words it parked itself: no barrier needed
+    dw.park(words, 256, threadIdx.x, src.scalars + (p * src.stride + i) * 8);
     const uint32_t koff = uint32_t(p) * src.nbuck;
     for (int w = 0; w < src.nwin; w++) {
       uint32_t neg;
@@ -227,6 +264,7 @@ msm_entry_pass0_kernel(EntrySource src, int shift, int bits, uint32_t* __restric
                        uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
   extern __shared__ uint32_t p0_stage[];
   __shared__ uint32_t cnt[SORT_BINS], cnt2[SORT_BINS], start[SORT_BINS], gofs[SORT_BINS], tmp[SORT_BINS / 32];
+  __shared__ uint32_t words[9 * SORT_P0_THREADS];
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
   uint32_t* skeys = p0_stage;
@@ -245,10 +283,10 @@ msm_entry_pass0_kernel(EntrySource src, int shift, int bits, uint32_t* __restric
     i = g - p * src.n;
     if (src.inf_mask && src.inf_mask[src.first + i]) live = false;
   }
-  DigitWalker dw;
+  SmemDigitWalker dw;
   const uint32_t koff = uint32_t(p) * src.nbuck;
   if (live) {
-    dw.load(src.scalars + (p * src.stride + i) * 8);
+    dw.park(words, SORT_P0_THREADS, tid, src.scalars + (p * src.stride + i) * 8);
     for (int w = 0; w < src.nwin; w++) {
       uint32_t neg;
       uint32_t v = dw.next(w, src.c, neg);
