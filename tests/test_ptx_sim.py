@@ -11,7 +11,7 @@ from oracle.bn254 import P, R
 SRC = open(os.path.join(ROOT, "zelana_b200", "csrc", "fp.cuh")).read()
 BLOCKS = ptx_sim.extract_asm_blocks(SRC)
 # file order: reduce_once, add, sub(2), modulus_minus, mont_step first, mont_step next, mont_step reduce, final merge
-B_REDUCE, B_ADD, B_SUB1, B_SUB2, B_NEG, B_FIRST, B_NEXT, B_RED, B_MERGE = BLOCKS[:9]
+B_REDUCE, B_ADD, B_SUB1, B_SUB2, B_NEG, B_FIRST, B_NEXT, B_RED, B_MERGE, B_PROD_ADD = BLOCKS[:10]
 
 
 def words(x):
@@ -72,6 +72,68 @@ def mont_mul(a, b, mod):
     r = unwords([out["r.v[%d]" % i] for i in range(8)])
     assert r < 2 * mod
     return reduce_once(r, mod)
+
+
+def mont_mul_add_mul(a, b, c, d, mod):
+    """Fp::mul_add_mul: every step = product row of a * b_i, product row of c * d_i on top, ONE reduction row."""
+    cf = cfg(mod)
+    aw, bw, cw, dw = words(a), words(b), words(c), words(d)
+    E, O = [None] * 8, [None] * 8
+
+    def step(first, X, Y, i):
+        env = dict(cf)
+        env.update({"a[%d]" % k: aw[k] for k in range(8)})
+        env["b"] = bw[i]
+        if not first:
+            env.update({"X[%d]" % k: X[k] for k in range(8)})
+            env.update({"Y[%d]" % k: Y[k] for k in range(8)})
+        out = ptx_sim.run_asm(*(B_FIRST if first else B_NEXT), env)
+        for k in range(8):
+            X[k], Y[k] = out["X[%d]" % k], out["Y[%d]" % k]
+        before = unwords(X) + (unwords(Y) << 32)
+        env = {"a[%d]" % k: cw[k] for k in range(8)}
+        env["b"] = dw[i]
+        env.update({"X[%d]" % k: X[k] for k in range(8)})
+        env.update({"Y[%d]" % k: Y[k] for k in range(8)})
+        out = ptx_sim.run_asm(*B_PROD_ADD, env)
+        for k in range(8):
+            X[k], Y[k] = out["X[%d]" % k], out["Y[%d]" % k]
+        assert unwords(X) + (unwords(Y) << 32) == before + c * dw[i], "a carry was lost in the second product row"
+        env = dict(cf)
+        env["m"] = (X[0] * cf["C::INV"]) & 0xFFFFFFFF
+        env.update({"X[%d]" % k: X[k] for k in range(8)})
+        env.update({"Y[%d]" % k: Y[k] for k in range(8)})
+        before = unwords(X) + (unwords(Y) << 32)
+        out = ptx_sim.run_asm(*B_RED, env)
+        for k in range(8):
+            X[k], Y[k] = out["X[%d]" % k], out["Y[%d]" % k]
+        assert X[0] == 0 and unwords(X) + (unwords(Y) << 32) == before + env["m"] * mod, "a carry was lost in the reduction row"
+
+    step(True, E, O, 0)
+    for i in range(1, 8):
+        if i & 1:
+            step(False, O, E, i)
+        else:
+            step(False, E, O, i)
+    env = {"E[%d]" % i: E[i] for i in range(8)}
+    env.update({"O[%d]" % i: O[i] for i in range(8)})
+    out = ptx_sim.run_asm(*B_MERGE, env)
+    r = unwords([out["r.v[%d]" % i] for i in range(8)])
+    assert r == (unwords(O) >> 32) + unwords(E) < 3 * mod + 8, "merge overflowed 256 bits or the 3p bound fails"
+    return reduce_once(reduce_once(r, mod), mod)
+
+
+@pytest.mark.parametrize("mod", [P, R])
+def test_mul_add_mul_ptx(mod):
+    """The lazy-reduction product of the XYZZ formulas: (a b + c d) / R mod p with ONE Montgomery reduction, operands up to
+    p itself (p - y for y = 0), every intermediate sum checked against exact integers."""
+    rnd = random.Random(17)
+    rinv = pow(1 << 256, -1, mod)
+    edge = [0, 1, mod - 1, mod, (1 << 256) % mod, mod >> 1]
+    cases = [(a, b, c, d) for a in edge for b in edge for c in (0, mod - 1, mod) for d in (1, mod - 1, mod)]
+    cases += [tuple(rnd.randrange(mod) for _ in range(4)) for _ in range(300)]
+    for a, b, c, d in cases:
+        assert mont_mul_add_mul(a, b, c, d, mod) == (a * b + c * d) * rinv % mod, (a, b, c, d)
 
 
 @pytest.mark.parametrize("mod", [P, R])

@@ -20,11 +20,9 @@ struct Fq2 {
   friend __device__ __forceinline__ Fq2 operator+(const Fq2& a, const Fq2& b) { return {a.c0 + b.c0, a.c1 + b.c1}; }
   friend __device__ __forceinline__ Fq2 operator-(const Fq2& a, const Fq2& b) { return {a.c0 - b.c0, a.c1 - b.c1}; }
   friend __device__ __forceinline__ Fq2 operator*(const Fq2& a, const Fq2& b) {
-    // Karatsuba: 3 base-field products
-    Fq v0 = a.c0 * b.c0;
-    Fq v1 = a.c1 * b.c1;
-    Fq s = (a.c0 + a.c1) * (b.c0 + b.c1);
-    return {v0 - v1, s - v0 - v1};
+    // c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0: each ONE Montgomery pass over two products (Fp::mul_add_mul, lazy reduction):
+    // 2 x 200 multiply-accumulates and no additions, against Karatsuba's 3 x 136 plus five modular additions (~445).
+    return {Fq::mul_add_mul(a.c0, b.c0, Fq::modulus_minus(a.c1), b.c1), Fq::mul_add_mul(a.c0, b.c1, a.c1, b.c0)};
   }
   __device__ __forceinline__ Fq2 sqr() const {
     Fq t = c0 * c1;
@@ -43,6 +41,14 @@ struct Fq2 {
   __device__ __forceinline__ Fq2 to_mont() const { return {c0.to_mont(), c1.to_mont()}; }
   __device__ __forceinline__ Fq2 from_mont() const { return {c0.from_mont(), c1.from_mont()}; }
 };
+
+// a b - c d.  Fq: one Montgomery pass over both products (Fp::mul_add_mul with p - c: lazy reduction, 200 multiply-accumulates
+// instead of 272) -- the last line of every XYZZ formula, y3 = R (Q - x3) - y1 PPP, is of this shape.  Fq2: the Karatsuba
+// products already share work; nothing to gain.
+__device__ __forceinline__ Fq mul_sub_mul(const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
+  return Fq::mul_add_mul(a, b, Fq::modulus_minus(c), d);   // c = 0 gives p: allowed (operands <= p)
+}
+__device__ __forceinline__ Fq2 mul_sub_mul(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return a * b - c * d; }
 
 // ---------------------------------------------------------------------------------- points
 // Affine point, coordinates in Montgomery form.  Infinity is (0, 0) -- not on y^2 = x^3 + b for b != 0 --
@@ -78,7 +84,7 @@ struct XYZZ {
     F M = xx.dbl() + xx;
     XYZZ r;
     r.x = M.sqr() - S.dbl();
-    r.y = M * (S - r.x) - W * p.y;
+    r.y = mul_sub_mul(M, S - r.x, W, p.y);
     r.zz = V;
     r.zzz = W;
     return r;
@@ -96,7 +102,7 @@ struct XYZZ {
     F M = xx.dbl() + xx;
     XYZZ r;
     r.x = M.sqr() - S.dbl();
-    r.y = M * (S - r.x) - W * y;
+    r.y = mul_sub_mul(M, S - r.x, W, y);
     r.zz = V * zz;
     r.zzz = W * zzz;
     return r;
@@ -122,7 +128,7 @@ struct XYZZ {
     F PPP = P * PP;
     F Q = x * PP;
     F X3 = R.sqr() - PPP - Q.dbl();
-    y = R * (Q - X3) - y * PPP;
+    y = mul_sub_mul(R, Q - X3, y, PPP);
     x = X3;
     zz = zz * PP;
     zzz = zzz * PPP;
@@ -150,7 +156,7 @@ struct XYZZ {
     F PPP = P * PP;
     F Q = U1 * PP;
     F X3 = R.sqr() - PPP - Q.dbl();
-    y = R * (Q - X3) - S1 * PPP;
+    y = mul_sub_mul(R, Q - X3, S1, PPP);
     x = X3;
     zz = zz * q.zz * PP;
     zzz = zzz * q.zzz * PPP;

@@ -190,7 +190,7 @@ struct alignas(16) Fp {
   //          even accumulator whose low word is already zero (roles swap every step).
   // then the reduction: m = X[0]*INV ; X += m*p_even ; Y += m*p_odd  (now X[0] == 0).
   template <bool FIRST>
-  static __device__ __forceinline__ void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b) {
+  static __device__ __forceinline__ void mont_prod(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b) {
     if (FIRST) {
       asm("mul.lo.u32 %0, %16, %24;\n\t mul.hi.u32 %1, %16, %24;\n\t"
           "mul.lo.u32 %2, %18, %24;\n\t mul.hi.u32 %3, %18, %24;\n\t"
@@ -224,6 +224,9 @@ struct alignas(16) Fp {
           : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
             "r"(b));
     }
+  }
+  // the reduction row: m = X[0]*INV ; X += m*p_even ; Y += m*p_odd  (now X[0] == 0)
+  static __device__ __forceinline__ void mont_reduce_row(uint32_t* X, uint32_t* Y) {
     uint32_t m = X[0] * C::INV;
     asm("mad.lo.cc.u32 %8, %16, %18, %8;\n\t madc.hi.cc.u32 %9, %16, %18, %9;\n\t"
         "madc.lo.cc.u32 %10, %16, %20, %10;\n\t madc.hi.cc.u32 %11, %16, %20, %11;\n\t"
@@ -240,18 +243,14 @@ struct alignas(16) Fp {
         : "r"(m), "n"(C::M0), "n"(C::M1), "n"(C::M2), "n"(C::M3), "n"(C::M4), "n"(C::M5), "n"(C::M6),
           "n"(C::M7));
   }
+  template <bool FIRST>
+  static __device__ __forceinline__ void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b) {
+    mont_prod<FIRST>(X, Y, a, b);
+    mont_reduce_row(X, Y);
+  }
 
-  friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
-    uint32_t E[8], O[8];
-    mont_step<true>(E, O, a.v, b.v[0]);
-    mont_step<false>(O, E, a.v, b.v[1]);
-    mont_step<false>(E, O, a.v, b.v[2]);
-    mont_step<false>(O, E, a.v, b.v[3]);
-    mont_step<false>(E, O, a.v, b.v[4]);
-    mont_step<false>(O, E, a.v, b.v[5]);
-    mont_step<false>(E, O, a.v, b.v[6]);
-    mont_step<false>(O, E, a.v, b.v[7]);
-    // last step's roles: X = O (low word zero), Y = E.  result = (X >> 32) + Y
+  // after eight steps the roles are X = O (low word zero), Y = E: value = (X >> 32) + Y, below 2^256 by the magnitude bound
+  static __device__ __forceinline__ Fp mont_merge(const uint32_t* E, const uint32_t* O) {
     Fp r;
     asm("add.cc.u32 %0, %8, %16;\n\t"
         "addc.cc.u32 %1, %9, %17;\n\t"
@@ -265,6 +264,65 @@ struct alignas(16) Fp {
           "=r"(r.v[6]), "=r"(r.v[7])
         : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
           "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+    return r;
+  }
+
+  friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
+    uint32_t E[8], O[8];
+    mont_step<true>(E, O, a.v, b.v[0]);
+    mont_step<false>(O, E, a.v, b.v[1]);
+    mont_step<false>(E, O, a.v, b.v[2]);
+    mont_step<false>(O, E, a.v, b.v[3]);
+    mont_step<false>(E, O, a.v, b.v[4]);
+    mont_step<false>(O, E, a.v, b.v[5]);
+    mont_step<false>(E, O, a.v, b.v[6]);
+    mont_step<false>(O, E, a.v, b.v[7]);
+    Fp r = mont_merge(E, O);
+    reduce_once(r);   // < 2p
+    return r;
+  }
+
+  // ---- a*b + c*d in ONE Montgomery pass (lazy reduction) -------------------------------------------
+  // (X, Y) += c * d_i on top of a step's product row, before its reduction row: even words of c into the even lanes (carry out
+  // of word 7 into Y[7] = word 8), odd words into the odd lanes.  Magnitudes: with a, c <= p the running value stays below
+  // 3p (1 + 1/2^32) and a step's sum below 3 * 2^32 * p < 2^288, the nine words the two accumulators span -- no carry is lost.
+  static __device__ __forceinline__ void mont_prod_add(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %16, %24, %0;\n\t madc.hi.cc.u32 %1, %16, %24, %1;\n\t"
+        "madc.lo.cc.u32 %2, %18, %24, %2;\n\t madc.hi.cc.u32 %3, %18, %24, %3;\n\t"
+        "madc.lo.cc.u32 %4, %20, %24, %4;\n\t madc.hi.cc.u32 %5, %20, %24, %5;\n\t"
+        "madc.lo.cc.u32 %6, %22, %24, %6;\n\t madc.hi.cc.u32 %7, %22, %24, %7;\n\t"
+        "addc.u32 %15, %15, 0;\n\t"
+        "mad.lo.cc.u32 %8, %17, %24, %8;\n\t madc.hi.cc.u32 %9, %17, %24, %9;\n\t"
+        "madc.lo.cc.u32 %10, %19, %24, %10;\n\t madc.hi.cc.u32 %11, %19, %24, %11;\n\t"
+        "madc.lo.cc.u32 %12, %21, %24, %12;\n\t madc.hi.cc.u32 %13, %21, %24, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %24, %14;\n\t madc.hi.u32 %15, %23, %24, %15;"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]),
+          "+r"(X[7]), "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]),
+          "+r"(Y[6]), "+r"(Y[7])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b));
+  }
+  template <bool FIRST>
+  static __device__ __forceinline__ void mont_step2(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t b, const uint32_t* c,
+                                                    uint32_t d) {
+    mont_prod<FIRST>(X, Y, a, b);
+    mont_prod_add(X, Y, c, d);
+    mont_reduce_row(X, Y);
+  }
+  // (a*b + c*d) / R mod p for a, b, c, d <= p: two products, ONE reduction (200 multiply-accumulates instead of 272).
+  // The XYZZ formulas end in  y3 = R (Q - x3) - y1 PPP = R (Q - x3) + (p - y1) PPP: that is this.
+  static __device__ __forceinline__ Fp mul_add_mul(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    uint32_t E[8], O[8];
+    mont_step2<true>(E, O, a.v, b.v[0], c.v, d.v[0]);
+    mont_step2<false>(O, E, a.v, b.v[1], c.v, d.v[1]);
+    mont_step2<false>(E, O, a.v, b.v[2], c.v, d.v[2]);
+    mont_step2<false>(O, E, a.v, b.v[3], c.v, d.v[3]);
+    mont_step2<false>(E, O, a.v, b.v[4], c.v, d.v[4]);
+    mont_step2<false>(O, E, a.v, b.v[5], c.v, d.v[5]);
+    mont_step2<false>(E, O, a.v, b.v[6], c.v, d.v[6]);
+    mont_step2<false>(O, E, a.v, b.v[7], c.v, d.v[7]);
+    Fp r = mont_merge(E, O);
+    reduce_once(r);   // < 3p (1 + 2^-32): two conditional subtractions
     reduce_once(r);
     return r;
   }
