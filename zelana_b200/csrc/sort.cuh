@@ -13,7 +13,7 @@
 //   msm_entry_pass0_kernel  reads the scalars again, extracts the digits in registers, ranks the tile's entries by the lowest
 //                           radix digit (shared-memory atomics: the first pass need not be stable), stages them in shared
 //                           memory in bin order and writes bin-contiguous runs: the unsorted key / value arrays never exist
-//   sort_pass_kernel        the remaining passes: stable (warp match-any ranking, warp-striped items), 4096 pairs per tile,
+//   sort_pass_kernel        the remaining passes: stable (warps find equal digits through shared-memory masks, warp-striped items), 4096 pairs per tile,
 //                           staged through shared memory, coalesced runs out
 // Tiles take their index from an atomic counter and chain their per-bin counts with a decoupled look-back (flag and value in
 // one 32-bit word, so a single store publishes both): one read and one write of every pair per pass, 7 bits per pass.
@@ -262,13 +262,12 @@ __device__ __forceinline__ uint32_t tile_lookback(uint32_t* state, uint32_t tile
 static __global__ void __launch_bounds__(SORT_P0_THREADS)
 msm_entry_pass0_kernel(EntrySource src, int shift, int bits, uint32_t* __restrict__ hdr, uint32_t* __restrict__ state,
                        uint32_t* __restrict__ out_keys, uint32_t* __restrict__ out_vals) {
-  extern __shared__ uint32_t p0_stage[];
+  extern __shared__ uint2 p0_stage[];   // (key, value) pairs in bin order: one 8-byte access per pair
   __shared__ uint32_t cnt[SORT_BINS], cnt2[SORT_BINS], start[SORT_BINS], gofs[SORT_BINS], tmp[SORT_BINS / 32];
   __shared__ uint32_t words[9 * SORT_P0_THREADS];
   __shared__ uint32_t s_tile;
   const int tid = threadIdx.x;
-  uint32_t* skeys = p0_stage;
-  uint32_t* svals = p0_stage + size_t(blockDim.x) * src.nwin;
+  uint2* skv = p0_stage;
   if (tid == 0) s_tile = atomicAdd(&hdr[SortHeader::TILE_CTR + 0], 1u);
   if (tid < SORT_BINS) cnt[tid] = cnt2[tid] = 0;
   __syncthreads();
@@ -307,18 +306,17 @@ msm_entry_pass0_kernel(EntrySource src, int shift, int bits, uint32_t* __restric
       const uint32_t key = koff + v - 1u;
       const uint32_t d = (key >> shift) & mask;
       const uint32_t pos = start[d] + atomicAdd(&cnt2[d], 1u);
-      skeys[pos] = key;
-      svals[pos] = (uint32_t(size_t(w) * src.table_n) + vbase) | (neg << 31);
+      skv[pos] = make_uint2(key, (uint32_t(size_t(w) * src.table_n) + vbase) | (neg << 31));
     }
   }
   __syncthreads();
   const uint32_t items = start[SORT_BINS - 1] + cnt[SORT_BINS - 1];
   for (uint32_t j = tid; j < items; j += blockDim.x) {
-    const uint32_t key = skeys[j];
-    const uint32_t d = (key >> shift) & mask;
+    const uint2 kv = skv[j];
+    const uint32_t d = (kv.x >> shift) & mask;
     const uint32_t dst = gofs[d] + (j - start[d]);
-    out_keys[dst] = key;
-    out_vals[dst] = svals[j];
+    out_keys[dst] = kv.x;
+    out_vals[dst] = kv.y;
   }
 }
 
@@ -328,15 +326,16 @@ static __global__ void __launch_bounds__(SORT_THREADS, 4)
 sort_pass_kernel(const uint32_t* __restrict__ in_keys, const uint32_t* __restrict__ in_vals, int pass, int shift, int bits,
                  uint32_t* __restrict__ hdr, uint32_t* __restrict__ state, uint32_t* __restrict__ out_keys,
                  uint32_t* __restrict__ out_vals) {
-  extern __shared__ uint32_t gp_stage[];
+  extern __shared__ uint2 gp_stage[];   // (key, value) pairs in bin order
   __shared__ uint32_t wcnt[SORT_WARPS * SORT_WSTRIDE];
+  __shared__ uint32_t wmask[2 * SORT_WARPS * SORT_WSTRIDE];
   __shared__ uint32_t cnt[SORT_BINS], start[SORT_BINS], gofs[SORT_BINS], tmp[SORT_BINS / 32];
   __shared__ uint32_t s_tile;
-  uint32_t* skeys = gp_stage;
-  uint32_t* svals = gp_stage + SORT_TILE;
+  uint2* skv = gp_stage;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&hdr[SortHeader::TILE_CTR + pass], 1u);
   for (int k = tid; k < SORT_WARPS * SORT_WSTRIDE; k += SORT_THREADS) wcnt[k] = 0;
+  for (int k = tid; k < 2 * SORT_WARPS * SORT_WSTRIDE; k += SORT_THREADS) wmask[k] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t total = hdr[SortHeader::TOTAL];
@@ -357,12 +356,21 @@ sort_pass_kernel(const uint32_t* __restrict__ in_keys, const uint32_t* __restric
   for (int r = 0; r < SORT_IPT; r++) {
     const bool valid = wbase + 32u * r < total;
     const uint32_t d = valid ? ((key[r] >> shift) & mask) : uint32_t(SORT_BINS);
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    // Which lanes of the warp hold the same digit?  match.any answers in one instruction but runs on the ADU pipe, which it
+    // kept 75 % busy -- the kernel's limiter (profiles/r02_ncu_sort_pass.txt).  A shared-memory OR does the same on the
+    // load/store pipe: every lane ORs its bit into the warp's mask word of its digit, a warp barrier, read it back.  Two mask
+    // arrays alternate so that clearing a word (by the digit's lowest lane) never races with the next round's ORs.
+    uint32_t* mym = wmask + ((r & 1) * SORT_WARPS + warp) * SORT_WSTRIDE;
+    atomicOr(&mym[d], 1u << lane);
+    __syncwarp();
+    const uint32_t peers = mym[d];
     const uint32_t below = __popc(peers & ((1u << lane) - 1u));
     const uint32_t base = mycnt[d];
     __syncwarp();
-    if (below == 0) mycnt[d] = base + __popc(peers);
-    __syncwarp();
+    if (below == 0) {
+      mycnt[d] = base + __popc(peers);
+      mym[d] = 0;
+    }
     const uint32_t rank = base + below;
     if (r & 1) rk[r >> 1] |= rank << 16;
     else rk[r >> 1] = rank;
@@ -390,18 +398,17 @@ sort_pass_kernel(const uint32_t* __restrict__ in_keys, const uint32_t* __restric
       const uint32_t d = (key[r] >> shift) & mask;
       const uint32_t rank = (r & 1) ? (rk[r >> 1] >> 16) : (rk[r >> 1] & 0xffffu);
       const uint32_t pos = start[d] + mycnt[d] + rank;
-      skeys[pos] = key[r];
-      svals[pos] = in_vals[gi];
+      skv[pos] = make_uint2(key[r], in_vals[gi]);
     }
   }
   __syncthreads();
   const uint32_t items = total - tile_base < uint32_t(SORT_TILE) ? total - tile_base : uint32_t(SORT_TILE);
   for (uint32_t j = tid; j < items; j += SORT_THREADS) {
-    const uint32_t k = skeys[j];
-    const uint32_t d = (k >> shift) & mask;
+    const uint2 kv = skv[j];
+    const uint32_t d = (kv.x >> shift) & mask;
     const uint32_t dst = gofs[d] + (j - start[d]);
-    out_keys[dst] = k;
-    out_vals[dst] = svals[j];
+    out_keys[dst] = kv.x;
+    out_vals[dst] = kv.y;
   }
 }
 
