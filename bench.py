@@ -656,6 +656,23 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak
         t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # BASELINE.json config 5 literally: ONE batch of 64 independent proofs over all GPUs (64 / world per rank), wall clock from
+    # the call to the last proof back in host memory, max over ranks
+    per64 = max(1, 64 // world)
+    pack64 = prover.marshal(circuits[:per64])
+    prover.prove_marshalled(pack64)
+    if world > 1:
+        dist.barrier()
+    t64 = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        prover.prove_marshalled(pack64)
+        t64.append(time.perf_counter() - t0)
+    dt64 = sorted(t64)[len(t64) // 2]
+    if world > 1:
+        t = torch.tensor([dt64], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt64 = float(t.item())
     # one proof of this run checked the slow way (rank 0): the assignment satisfies the matrices
     ok = None
     if rank == 0:
@@ -703,6 +720,8 @@ def l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak
             "host_threads_per_gpu": lanes, "ms_per_batch": dt * 1e3,
             "host_assign_ms_per_proof": assign_ms, "host_cores": os.cpu_count(), "keygen_s": keygen_s, "assignment_satisfied": ok,
             "batched_equals_single": True, "roofline": roof, "cpu_baseline": cpu,
+            "batch_of_64": {"ms": dt64 * 1e3, "proofs_per_s": per64 * world / dt64, "proofs_per_gpu": per64,
+                            "what": "BASELINE.json config 5: one batch of 64 independent L2 proofs over the GPUs, median of 5"},
             "circuit": "L2BlockCircuit::dummy() shape (prover/src/l2_circuit.rs): %d constraints, %d witness variables, domain 2^13; "
                        "one zkb_l2_batch_prove call per step = %d x BatchProver::prove end to end (host witness assignment + GPU "
                        "prove + Solana bytes), %d host threads per GPU, sub-batches of 256 proofs through batched kernels, real key "
@@ -920,11 +939,15 @@ def run_prove_sharded(args):
 
 
 def accumulate_traffic(log_n, world):
-    """DRAM bytes per launch of the accumulate kernel from the committed ncu --set full capture (2^24, 1 GPU only)."""
+    """DRAM bytes per launch of the accumulate kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture of THIS round's kernel, profiles/r02_accumulate_traffic.json) for the shard size one rank processes; a number taken
+    under a profiler cannot be measured inside this run, so it is the committed capture of the same kernel and size."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_accumulate_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_accumulate_traffic.json")) as f:
             t = json.load(f)
-        return t["dram_bytes_per_launch"] if (log_n == 24 and world == 1) else None
+        shard_log = log_n - (world.bit_length() - 1)
+        v = t.get("dram_bytes_per_launch_by_log_points", {}).get(str(shard_log))
+        return v if (world & (world - 1)) == 0 else None
     except Exception:
         return None
 

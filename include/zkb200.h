@@ -56,6 +56,9 @@ const char* zkb_last_error(zkb_ctx* ctx);
  * staging copy, overlapped with compute (any host memory works; pageable memory is copied synchronously) */
 int zkb_host_alloc_pinned(size_t bytes, void** out);
 void zkb_host_free_pinned(void* p);
+/* Memory-safety check without compute-sanitizer: with ZKB_GUARD=1 in the environment every scratch buffer a context allocates is
+ * wrapped in two 4 KiB canaries; this verifies them all (ZKB_OK = intact; ZKB_ERR_INVALID_ARG if nothing was guarded). */
+int zkb_debug_check_guards(zkb_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation (bench.py's gpu_launches) */
 unsigned long long zkb_launch_count(zkb_ctx* ctx);
 /* A prove's device part (~140 launches on five streams for the L2 circuit) is captured as a CUDA graph the second time a

@@ -900,3 +900,51 @@ def test_msm_comb_tables_equal_single_msms(ctx, c):
         assert ctx.debug_msm_comb(group, bases, sd[:, 7:], n - 300, n, K, c, offset=7) == \
             [msm(bases, sc[p, 7:n - 293], offset=7) for p in range(K)]
         bases.free()
+
+
+def test_scratch_guards_stay_intact(l2_setup, mimc_setup):
+    """compute-sanitizer is closed on this GPU pool; instead every scratch buffer of a fresh context is wrapped in 4 KiB canaries
+    (ZKB_GUARD=1) and the canaries are verified after ragged / empty / degenerate MSMs of both groups, NTTs, a prove, a batched
+    prove and the MiMC / Poseidon kernels: nothing writes outside its layout."""
+    import os
+    import numpy as np
+    import torch
+    import zelana_b200
+    from zelana_b200 import l2_circuit as P2
+    os.environ["ZKB_GUARD"] = "1"
+    try:
+        g = zelana_b200.Context(0)
+        for n in (1, 31, 257, 5000, (1 << 16) + 3):
+            k = _rand_fr_np(n, 300 + n % 7)
+            b1 = g.g1_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+            s = _rand_fr_np(n, 301)
+            s[: n // 3] = 0
+            g.msm_g1(b1, s)
+            if n <= 5000:
+                b2 = g.g2_bases_generate(torch.from_numpy(k.view(np.int32)).cuda(), n)
+                g.msm_g2(b2, s)
+                sd = torch.from_numpy(np.repeat(s[None], 3, axis=0).view(np.int32).copy()).cuda()
+                g.debug_msm_batch(2, b2, sd, n, n, 3)
+                g.debug_msm_batch(1, b1, sd, n, n, 3)
+                b2.free()
+            b1.free()
+        big = (1 << 20) + 12345           # the sliced host-scalar path
+        kb = _rand_fr_np(big, 310)
+        bb = g.g1_bases_generate(torch.from_numpy(kb.view(np.int32)).cuda(), big)
+        g.msm_g1(bb, _rand_fr_np(big, 311))
+        bb.free()
+        for lg in (1, 7, 13, 17):
+            g.ntt(_rand_fr_np(1 << lg, 320 + lg), lg, inverse=True, coset=True)
+        r1cs, z, pk = mimc_setup
+        m = g.r1cs(r1cs.num_instance, r1cs.num_witness, r1cs.a, r1cs.b, r1cs.c)
+        dpk = g.proving_key(**pk_parts(pk))
+        g.prove(dpk, m, fr_bytes(z), fr_bytes([5]), fr_bytes([7]))
+        g.prove_batch(dpk, m, fr_bytes(z) * 3, (fr_bytes([5]) + fr_bytes([7])) * 3)
+        g.mimc_hash(2, _rand_fr_np(2 * 77, 330).tobytes())
+        g.l2_poseidon_hash_batch(3, _rand_fr_np(3 * 77, 331).tobytes())
+        g.debug_check_guards()
+        m.free()
+        dpk.free()
+        g.close()
+    finally:
+        os.environ.pop("ZKB_GUARD", None)

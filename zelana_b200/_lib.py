@@ -73,6 +73,7 @@ SIGNATURES = {
     "zkb_last_error": (C.c_char_p, [_P]),
     "zkb_host_alloc_pinned": (_I, [_SZ, C.POINTER(_P)]),
     "zkb_host_free_pinned": (None, [_P]),
+    "zkb_debug_check_guards": (_I, [_P]),
     "zkb_launch_count": (C.c_ulonglong, [_P]),
     "zkb_ctx_set_msm_window": (_I, [_P, _I]),
     "zkb_ctx_set_graphs": (_I, [_P, _I]),

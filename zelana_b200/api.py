@@ -57,6 +57,10 @@ class Context:
     def synchronize(self):
         self._check(self.lib.zkb_ctx_synchronize(self.h))
 
+    def debug_check_guards(self):
+        """Verify the canaries around every scratch buffer (allocated with ZKB_GUARD=1 in the environment)."""
+        self._check(self.lib.zkb_debug_check_guards(self.h))
+
     def launch_count(self):
         return int(self.lib.zkb_launch_count(self.h))
 

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -28,27 +29,60 @@ namespace zkb {
 // growing, keys / matrices / tables released.  A cached graph is replayed only while the epoch it was captured at is current.
 inline std::atomic<unsigned long long> g_alloc_epoch{0};
 
+// Scratch buffer.  With ZKB_GUARD=1 in the environment (checked when a buffer is allocated) every allocation is wrapped in two
+// 4 KiB canary regions filled with 0xA5; zkb_debug_check_guards() verifies them.  compute-sanitizer is closed on this GPU pool,
+// so this is the out-of-bounds check the scratch layouts (sort buffers, bucket arrays, head lists, batch buffers) run under in
+// tests/test_gpu_parity.py::test_scratch_guards_stay_intact.
 struct DevBuf {
-  void* p = nullptr;
+  static constexpr size_t GUARD = 4096;
+  void* p = nullptr;      // what users see
+  void* base = nullptr;   // what cudaMalloc returned (== p without guards)
   size_t cap = 0;
+  bool guarded = false;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
     g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
-    if (p) cudaFree(p);
-    p = nullptr;
+    if (base) cudaFree(base);
+    p = base = nullptr;
     cap = 0;
     if (bytes == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaSuccess) cap = bytes;
+    const char* g = getenv("ZKB_GUARD");
+    guarded = g && g[0] == '1';
+    const size_t padded = (bytes + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&base, guarded ? padded + 2 * GUARD : bytes);
+    if (e != cudaSuccess) {
+      base = nullptr;
+      return e;
+    }
+    if (guarded) {
+      cudaMemset(base, 0xA5, GUARD);
+      cudaMemset(static_cast<char*>(base) + GUARD + padded, 0xA5, GUARD);
+      p = static_cast<char*>(base) + GUARD;
+    } else {
+      p = base;
+    }
+    cap = guarded ? padded : bytes;
     return e;
   }
   void release() {
-    if (p) {
+    if (base) {
       g_alloc_epoch.fetch_add(1, std::memory_order_relaxed);
-      cudaFree(p);
+      cudaFree(base);
     }
-    p = nullptr;
+    p = base = nullptr;
     cap = 0;
+  }
+  // 0: intact (or unguarded); 1: the canary before the buffer was overwritten; 2: the one after it
+  int check_guards() const {
+    if (!base || !guarded) return 0;
+    unsigned char h[GUARD];
+    for (int side = 0; side < 2; side++) {
+      const char* src = side == 0 ? static_cast<const char*>(base) : static_cast<const char*>(base) + GUARD + cap;
+      if (cudaMemcpy(h, src, GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) return side + 1;
+      for (size_t i = 0; i < GUARD; i++)
+        if (h[i] != 0xA5) return side + 1;
+    }
+    return 0;
   }
   template <class T>
   T* as() const { return static_cast<T*>(p); }

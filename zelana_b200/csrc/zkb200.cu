@@ -180,6 +180,29 @@ extern "C" void zkb_host_free_pinned(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+// Verifies the canaries around every scratch buffer of the context (allocated while ZKB_GUARD=1 was set): ZKB_OK if intact.
+extern "C" int zkb_debug_check_guards(zkb_ctx* ctx) {
+  if (!ctx) return ZKB_ERR_INVALID_ARG;
+  ZKB_ON_DEVICE(ctx);
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  struct Named { const char* name; const DevBuf* b; };
+  const Named bufs[] = {{"msm_ws", &ctx->msm_ws}, {"lane0", &ctx->aux[0].ws}, {"lane1", &ctx->aux[1].ws}, {"lane2", &ctx->aux[2].ws},
+                        {"lane3", &ctx->aux[3].ws}, {"lane4", &ctx->aux[4].ws}, {"scal", &ctx->scal}, {"res", &ctx->res},
+                        {"tmp0", &ctx->tmp0}, {"tmp1", &ctx->tmp1}, {"tmp2", &ctx->tmp2}, {"flag", &ctx->flag}, {"pz", &ctx->pz},
+                        {"pzm", &ctx->pzm}, {"pwa", &ctx->pwa}, {"pwb", &ctx->pwb}, {"pwc", &ctx->pwc}, {"ph", &ctx->ph},
+                        {"pza", &ctx->pza}, {"pzb", &ctx->pzb}, {"pzl", &ctx->pzl}, {"prs", &ctx->prs}, {"ppts", &ctx->ppts},
+                        {"pzsa", &ctx->pzsa}, {"pzrb", &ctx->pzrb}, {"bz", &ctx->bz}, {"bzm", &ctx->bzm}, {"bw3", &ctx->bw3},
+                        {"bh", &ctx->bh}, {"brs", &ctx->brs}, {"bpart", &ctx->bpart}, {"bout", &ctx->bout}};
+  int guarded = 0;
+  for (const Named& n : bufs) {
+    if (n.b->guarded && n.b->base) guarded++;
+    int rc = n.b->check_guards();
+    if (rc) ZKB_FAIL(ctx, ZKB_ERR_CUDA, "scratch buffer %s: the canary %s it was overwritten", n.name, rc == 1 ? "before" : "after");
+  }
+  if (!guarded) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "no guarded buffer: set ZKB_GUARD=1 before the context allocates");
+  return ZKB_OK;
+}
+
 extern "C" const char* zkb_last_error(zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" unsigned long long zkb_launch_count(zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int zkb_ctx_set_graphs(zkb_ctx* ctx, int on) {
