@@ -20,6 +20,8 @@ def msm(log_n):
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
     ctx = zelana_b200.Context(0, stream=st.cuda_stream)
+    if os.environ.get("MSM_C"):
+        ctx.set_msm_window(int(os.environ["MSM_C"]))
     g = torch.Generator(device=dev)
     g.manual_seed(1)
     k = torch.randint(0, 1 << 32, (n, 8), dtype=torch.int64, device=dev, generator=g)
