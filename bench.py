@@ -604,9 +604,9 @@ def l2_real_mul32_per_proof(circ, raw, c_of):
 def msm_window_for(n, point_bytes):
     """zelana_b200/csrc/msm.cuh msm_choose_window without the memory cap (small keys)."""
     best, best_cost = 0, 0.0
-    for c in range(4, 24):
+    for c in range(10, 24):
         nwin = (255 + c - 1) // c
-        cost = nwin * n + 2.8 * (1 << (c - 1)) + 4096.0 * nwin
+        cost = nwin * n + 4.0 * (1 << (c - 1))
         if not best or cost < best_cost:
             best, best_cost = c, cost
     return best

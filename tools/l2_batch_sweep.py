@@ -17,6 +17,8 @@ from zelana_b200 import l2_circuit as l2  # noqa: E402
 
 ctx = zelana_b200.Context(0)
 circ, pk_bytes, vk_bytes, _raw = l2.keygen(ctx)
+if os.environ.get("MSM_C"):
+    ctx.set_msm_window(int(os.environ["MSM_C"]))     # window width of the key's tables (default: chosen from the key size)
 pk = ctx.proving_key_compressed(pk_bytes, validate=False)
 prover = l2.L2BatchProver(ctx, circ, pk, lanes=lanes)
 

@@ -51,17 +51,19 @@ constexpr int MSM_COL_LOG = 8;   // segment totals viewed as rows x 256 columns
 
 static inline int msm_windows_for(int c) { return (255 + c - 1) / c; }  // nwin * c >= 255: the top digit absorbs the carry
 
-// Window width for a table of n bases: minimise  nwin(c) * n  (mixed additions)  +  2.8 * 2^(c-1)  (two full additions per
-// bucket, ~1.4 mixed additions each), subject to the table fitting `mem_budget` bytes and nwin * n < 2^31 entries.
+// Window width for a table of n bases: minimise  nwin(c) * n  (mixed additions)  +  4 * 2^(c-1)  (a bucket costs two full
+// additions in the segment kernel plus its share of the reduction's later stages: ~4 mixed additions), subject to the table
+// fitting `mem_budget` bytes and nwin * n < 2^31 entries.  Measured: 2^24 points -> 22 (21: +1.8 ms, 23: +1.4 ms), 2^21 -> 20
+// (19: +0.3 ms, 21: +0.3 ms); the L2 key's 6-8 k point vectors -> 13 (a batch of 256 proofs: 5 653 proofs/s; 12: 5 570; 14: 5 069).
 static inline int msm_choose_window(size_t n, size_t point_bytes, size_t mem_budget) {
   if (n == 0) return 8;
   int best = 0;
   double best_cost = 0;
-  for (int c = 4; c <= 23; c++) {
+  for (int c = 10; c <= 23; c++) {
     int nwin = msm_windows_for(c);
     if (double(nwin) * double(n) >= 2147483648.0) continue;
     if (double(nwin) * double(n) * double(point_bytes) > double(mem_budget)) continue;
-    double cost = double(nwin) * double(n) + 2.8 * double(size_t(1) << (c - 1)) + 4096.0 * nwin;
+    double cost = double(nwin) * double(n) + 4.0 * double(size_t(1) << (c - 1));
     if (!best || cost < best_cost) {
       best = c;
       best_cost = cost;
