@@ -786,6 +786,9 @@ def test_prove_batch_equals_single_proves(ctx, l2_setup):
     assert got == expect
     assert ctx.prove_batch(dpk, m, zs[2], rs[2][0] + rs[2][1]) == [expect[2]]
     assert ctx.prove_batch(dpk, m, b"".join(zs[:5]), b"".join(r + s for r, s in rs[:5])) == expect[:5]
+    # 70 proofs: the sequential record folds (batches of >= 64 vectors) and five warps of the packed finish kernel
+    reps = [i % K for i in range(70)]
+    assert ctx.prove_batch(dpk, m, b"".join(zs[i] for i in reps), b"".join(rs[i][0] + rs[i][1] for i in reps)) == [expect[i] for i in reps]
     with pytest.raises(Exception):
         ctx.prove_batch(dpk, m, b"".join(zs[:2]), rs[0][0] + rs[0][1])      # two assignments, one (r, s)
     m.free()
@@ -794,28 +797,30 @@ def test_prove_batch_equals_single_proves(ctx, l2_setup):
 
 def test_msm_batch_equals_single_msms(ctx):
     """msm_run_batch through zkb_debug_msm_batch: K scalar vectors against one table == K separate MSMs (G1 and G2), with
-    zero / one / maximal scalars and a vector of all zeros among them."""
+    zero / one / maximal scalars and a vector of all zeros among them.  K = 9 folds the segment records with the warp levels,
+    K = 67 (>= MSM_SEQ_FOLD_BATCH) with the sequential levels."""
     import numpy as np
     import torch
-    n, K = 3000, 9
-    k = _rand_fr_np(n, 81)
-    for group in (1, 2):
-        gen = ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate
-        bases = gen(torch.from_numpy(k.view(np.int32)).cuda(), n)
-        sc = _rand_fr_np(n * K, 82 + group).reshape(K, n, 8)
-        sc[1] = 0
-        sc[2, ::2] = 0
-        sc[3, :, 1:] = 0
-        sc[3, :, 0] = 1
-        rm1 = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint32)
-        sc[4, :100] = rm1
-        single = [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p]) for p in range(K)]
-        got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda(), n, n, K)
-        assert got == single
-        # a sub-range with a stride larger than the vector length
-        got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda()[:, 5:], n - 500, n, K, offset=5)
-        assert got == [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p, 5:n - 495], offset=5) for p in range(K)]
-        bases.free()
+    for n, K in ((3000, 9), (700, 67)):
+        k = _rand_fr_np(n, 81)
+        for group in (1, 2):
+            gen = ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate
+            bases = gen(torch.from_numpy(k.view(np.int32)).cuda(), n)
+            sc = _rand_fr_np(n * K, 82 + group).reshape(K, n, 8)
+            sc[1] = 0
+            sc[2, ::2] = 0
+            sc[3, :, 1:] = 0
+            sc[3, :, 0] = 1
+            rm1 = np.frombuffer((R - 1).to_bytes(32, "little"), dtype=np.uint32)
+            sc[4, :100] = rm1
+            single = [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p]) for p in range(K)]
+            got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda(), n, n, K)
+            assert got == single
+            # a sub-range with a stride larger than the vector length
+            cut = n // 6
+            got = ctx.debug_msm_batch(group, bases, torch.from_numpy(sc.view(np.int32).copy()).cuda()[:, 5:], n - cut, n, K, offset=5)
+            assert got == [(ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, sc[p, 5:n - cut + 5], offset=5) for p in range(K)]
+            bases.free()
 
 
 def test_msm_multi_c_abi_equals_single_msm(ctx):

@@ -86,58 +86,71 @@ __global__ void prove_combine_g1_kernel(const char* parts, int world, size_t str
   }
 }
 
-// Batched prove, G1 part.  One block of three warps per proof, lane 0 of each: warp 0 finishes A and multiplies it by s,
-// warp 1 finishes B1 and multiplies it by r, warp 2 sums L + H - r s delta; thread 0 adds the three and converts to affine.
-// The two 254-step chains cost ~4000 products each on one thread -- against the ~1.3 M of the extra MSM that replaces them
-// for a lone small proof (prove_device_part): with a batch in flight, latency is hidden and only the arithmetic counts.
-__global__ void __launch_bounds__(96)
+// Batched prove, G1 part.  Two lanes per proof, 16 proofs per warp: the even lane finishes A and multiplies it by s, the odd lane
+// finishes B1 and multiplies it by r -- the same instruction stream on different data, so the lanes of a warp stay together;
+// the even lane then adds L + H - r s delta and converts C to affine.  The two 254-bit multiplications are 4-bit fixed-window
+// chains (14 additions for the table, then 252 doublings + <= 64 additions): ~3 400 products each on one thread.  This is a
+// latency-bound tail; what matters in a pipeline of sub-batches is that it holds few registers while another sub-batch's
+// accumulation fills the machine: 16 warps for 256 proofs (the first version ran a block of three warps per proof, one lane
+// of each active: measured 3.2 ms of every 45 ms sub-batch NOT hidden behind the other slots' kernels).
+__global__ void __launch_bounds__(32)
 prove_batch_finish_g1_kernel(int K, const XYZZ<Fq>* __restrict__ PA, const XYZZ<Fq>* __restrict__ PB1, const XYZZ<Fq>* __restrict__ PL,
                              const XYZZ<Fq>* __restrict__ PH, const uint32_t* __restrict__ rs, const Affine<Fq>* __restrict__ a_tail,
                              const Affine<Fq>* __restrict__ b1_tail, const Affine<Fq>* __restrict__ fb_delta, uint32_t* __restrict__ out) {
-  __shared__ XYZZ<Fq> part[3];
-  const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (p >= K) return;
-  const uint32_t* r = rs + size_t(p) * 16;
-  const uint32_t* s = r + 8;
-  if (lane == 0) {
-    uint32_t rw[8], sw[8];
-    for (int j = 0; j < 8; j++) {
-      rw[j] = r[j];
-      sw[j] = s[j];
-    }
-    if (warp == 0) {
-      XYZZ<Fq> a = load_xyzz(PA + p);
-      a.madd(a_tail[0]);
-      a.madd(a_tail[1]);
-      a.add(fixed_table_mul<Fq>(fb_delta, rw));
-      store_affine_canonical<Fq>(a.to_affine_vartime(), out + size_t(p) * 64);
-      part[0] = a.mul_words(sw);
-    } else if (warp == 1) {
-      XYZZ<Fq> b = load_xyzz(PB1 + p);
-      b.madd(b1_tail[0]);
-      b.madd(b1_tail[1]);
-      b.add(fixed_table_mul<Fq>(fb_delta, sw));
-      part[1] = b.mul_words(rw);
-    } else {
-      Fr rm, sm;
-      for (int j = 0; j < 8; j++) {
-        rm.v[j] = rw[j];
-        sm.v[j] = sw[j];
-      }
-      Fr nrs = (rm.to_mont() * sm.to_mont()).from_mont().neg();   // -(r s) mod r, canonical
-      XYZZ<Fq> l = load_xyzz(PL + p);
-      l.add(load_xyzz(PH + p));
-      l.add(fixed_table_mul<Fq>(fb_delta, nrs.v));
-      part[2] = l;
-    }
+  const int t = blockIdx.x * 32 + threadIdx.x, lane = threadIdx.x;
+  const int role = t & 1;
+  const bool live = (t >> 1) < K;
+  const int p = live ? (t >> 1) : K - 1;   // idle lanes of the last warp repeat the last proof and store nothing
+  uint32_t rw[8], sw[8];
+  for (int j = 0; j < 8; j++) {
+    rw[j] = rs[size_t(p) * 16 + j];
+    sw[j] = rs[size_t(p) * 16 + 8 + j];
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    XYZZ<Fq> acc = part[0];
-    acc.add(part[1]);
-    acc.add(part[2]);
-    store_affine_canonical<Fq>(acc.to_affine_vartime(), out + size_t(p) * 64 + 48);
+  const uint32_t* mulw = role == 0 ? sw : rw;     // the chain's multiplier: s for A, r for B1
+  const uint32_t* delw = role == 0 ? rw : sw;     // A carries r delta, B1 carries s delta
+  const Affine<Fq>* tail = role == 0 ? a_tail : b1_tail;
+  XYZZ<Fq> base = load_xyzz((role == 0 ? PA : PB1) + p);
+  base.madd(tail[0]);
+  base.madd(tail[1]);
+  base.add(fixed_table_mul<Fq>(fb_delta, delw));
+  if (role == 0 && live) store_affine_canonical<Fq>(base.to_affine_vartime(), out + size_t(p) * 64);
+  XYZZ<Fq> tab[15];   // d * base, d = 1..15 (local memory)
+  tab[0] = base;
+  tab[1] = base.dbl();
+#pragma unroll 1
+  for (int d = 2; d < 15; d++) {
+    XYZZ<Fq> v = tab[d - 1];
+    v.add(base);
+    tab[d] = v;
   }
+  XYZZ<Fq> acc = XYZZ<Fq>::inf();
+#pragma unroll 1
+  for (int w = 63; w >= 0; w--) {
+    if (w != 63) {
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) acc = acc.dbl();
+    }
+    uint32_t word = mulw[0];
+#pragma unroll
+    for (int j = 1; j < 8; j++)
+      if ((w >> 3) == j) word = mulw[j];
+    const uint32_t d = (word >> (4 * (w & 7))) & 15u;
+    if (d) acc.add(tab[d - 1]);
+  }
+  XYZZ<Fq> other = shfl_xyzz(acc, lane ^ 1);   // the even lane receives r * B1
+  if (role != 0) return;
+  acc.add(other);
+  Fr rm, sm;
+  for (int j = 0; j < 8; j++) {
+    rm.v[j] = rw[j];
+    sm.v[j] = sw[j];
+  }
+  Fr nrs = (rm.to_mont() * sm.to_mont()).from_mont().neg();   // -(r s) mod r, canonical
+  XYZZ<Fq> l = load_xyzz(PL + p);
+  l.add(load_xyzz(PH + p));
+  l.add(fixed_table_mul<Fq>(fb_delta, nrs.v));
+  acc.add(l);
+  if (live) store_affine_canonical<Fq>(acc.to_affine_vartime(), out + size_t(p) * 64 + 48);
 }
 
 }  // namespace
@@ -145,7 +158,7 @@ prove_batch_finish_g1_kernel(int K, const XYZZ<Fq>* __restrict__ PA, const XYZZ<
 int prove_batch_finish_g1(zkb_ctx* ctx, int K, const void* PA, const void* PB1, const void* PL, const void* PH, const void* rs,
                           const void* a_tail, const void* b1_tail, const void* fb_delta1, void* out) {
   ProfScope ps(ctx, PH_ASSEMBLE);
-  prove_batch_finish_g1_kernel<<<unsigned(K), 96, 0, ctx->stream>>>(
+  prove_batch_finish_g1_kernel<<<unsigned((2 * K + 31) / 32), 32, 0, ctx->stream>>>(
       K, static_cast<const XYZZ<Fq>*>(PA), static_cast<const XYZZ<Fq>*>(PB1), static_cast<const XYZZ<Fq>*>(PL),
       static_cast<const XYZZ<Fq>*>(PH), static_cast<const uint32_t*>(rs), static_cast<const Affine<Fq>*>(a_tail),
       static_cast<const Affine<Fq>*>(b1_tail), static_cast<const Affine<Fq>*>(fb_delta1), static_cast<uint32_t*>(out));

@@ -462,12 +462,19 @@ __device__ __forceinline__ XYZZ<F> warp_sum_xyzz(XYZZ<F> v, int lane) {
 //   T' = sum_j T_j,   B' = m sum_j j T_j + sum_j B_j,   W' = sum_j W_j.
 // At the first level the records are the segments themselves (Bin == nullptr: B = 0, m = 1).
 
-// Sequential version, one THREAD per group of `cnt` (small, e.g. 4) records: keeps the segment kernel's chains short
-// (segments of 8 buckets instead of 32) without quadrupling the number of records the warp levels have to fold.
+// Sequential version, one THREAD per group of `cnt` (4 or 8) records: 2 additions per record for T' and sum_j j T_j (running
+// sums), one each for W' and the incoming B_j, log_m doublings for the factor m.  Used (a) as a pre-fold that keeps the segment
+// kernel's chains short (segments of 8 buckets instead of 32) without quadrupling the number of records the warp levels have to
+// fold and (b), for batches of many vectors, for EVERY level: a chain of ~30 additions per level is slow (0.3-0.5 ms) but
+// holds one lane per group, where the warp version holds three warps of ~200 registers per group -- measured in a pipeline of
+// 256-proof sub-batches, the warp levels' 2.8 ms were not hidden behind the other sub-batches' accumulation at all (they occupy
+// the register file while waiting on their own dependent chains); the sequential levels are.
+// `finish`: the group is a whole vector; write R = W' + 2^seg_log B' to outT.
 template <class F>
 __global__ void __launch_bounds__(64)
-msm_fold_seq_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__ Win, size_t groups, int cnt,
-                    XYZZ<F>* __restrict__ outT, XYZZ<F>* __restrict__ outB, XYZZ<F>* __restrict__ outW) {
+msm_fold_seq_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__ Bin, const XYZZ<F>* __restrict__ Win, size_t groups,
+                    int cnt, int log_m, int finish, int seg_log, XYZZ<F>* __restrict__ outT, XYZZ<F>* __restrict__ outB,
+                    XYZZ<F>* __restrict__ outW) {
   const size_t g = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (g >= groups) return;
   const XYZZ<F>* t = Tin + g * cnt;
@@ -478,10 +485,20 @@ msm_fold_seq_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict__
     b.add(run);
   }
   run.add(load_xyzz(t));
-  for (int j = 0; j < cnt; j++) ws.add(load_xyzz(w + j));
-  store_xyzz(outT + g, run);
-  store_xyzz(outB + g, b);
-  store_xyzz(outW + g, ws);
+  for (int k = 0; k < log_m; k++) b = b.dbl();
+  for (int j = 0; j < cnt; j++) {
+    ws.add(load_xyzz(w + j));
+    if (Bin) b.add(load_xyzz(Bin + g * cnt + j));
+  }
+  if (finish) {
+    for (int k = 0; k < seg_log; k++) b = b.dbl();
+    b.add(ws);
+    store_xyzz(outT + g, b);
+  } else {
+    store_xyzz(outT + g, run);
+    store_xyzz(outB + g, b);
+    store_xyzz(outW + g, ws);
+  }
 }
 
 // Warp version: a block of three warps combines `cnt` (<= 32) consecutive records, lane j of every warp holding record j.
@@ -530,6 +547,10 @@ msm_fold_level_kernel(const XYZZ<F>* __restrict__ Tin, const XYZZ<F>* __restrict
     store_xyzz(outW + g, sh[0]);
   }
 }
+
+// batches of at least this many vectors fold every level sequentially (throughput regime); smaller ones use the warp levels
+// (latency regime: few groups, nothing else to fill the machine with)
+constexpr int MSM_SEQ_FOLD_BATCH = 64;
 
 // XYZZ -> canonical affine bytes, one thread per point (the K results of a batched MSM)
 template <class F>
@@ -821,29 +842,47 @@ cudaError_t msm_reduce(zkb_ctx* ctx, const MsmLayout<F>& L, XYZZ<F>* out_xyzz, u
     P* scratch = buckets;
     int log_m = 0;
     ctx->launches++;
-    if (cnt_items >= 128) {   // sequential pre-fold of 4 records per thread: 4x fewer records for the warp levels
-      const size_t groups = size_t(L.batch) * (cnt_items / 4);
-      msm_fold_seq_kernel<F><<<unsigned((groups + 63) / 64), 64, 0, st>>>(tin, win, groups, 4, scratch, scratch + groups, scratch + 2 * groups);
-      ctx->launches++;
-      tin = scratch, bin = scratch + groups, win = scratch + 2 * groups;
-      scratch += 3 * groups;
-      cnt_items /= 4;
-      log_m = 2;
-    }
-    while (true) {
-      const int cnt = cnt_items > 32 ? 32 : int(cnt_items);
-      const size_t groups = size_t(L.batch) * (cnt_items / cnt);
-      const int finish = cnt_items <= 32 ? 1 : 0;
-      P* oT = finish ? res : scratch;
-      P* oB = scratch + groups;
-      P* oW = scratch + 2 * groups;
-      msm_fold_level_kernel<F><<<unsigned(groups), 96, 0, st>>>(tin, bin, win, cnt, log_m, finish, L.seg_log, oT, oB, oW);
-      ctx->launches++;
-      if (finish) break;
-      tin = oT, bin = oB, win = oW;
-      scratch += 3 * groups;
-      cnt_items /= 32;
-      log_m += 5;
+    if (L.batch >= MSM_SEQ_FOLD_BATCH) {   // many vectors: every level by threads, 8 records each (see msm_fold_seq_kernel)
+      while (true) {
+        const int cnt = cnt_items > 8 ? 8 : int(cnt_items);
+        const size_t groups = size_t(L.batch) * (cnt_items / cnt);
+        const int finish = cnt_items <= 8 ? 1 : 0;
+        P* oT = finish ? res : scratch;
+        msm_fold_seq_kernel<F><<<unsigned((groups + 63) / 64), 64, 0, st>>>(tin, bin, win, groups, cnt, log_m, finish, L.seg_log, oT,
+                                                                           scratch + groups, scratch + 2 * groups);
+        ctx->launches++;
+        if (finish) break;
+        tin = oT, bin = scratch + groups, win = scratch + 2 * groups;
+        scratch += 3 * groups;
+        cnt_items /= 8;
+        log_m += 3;
+      }
+    } else {
+      if (cnt_items >= 128) {   // sequential pre-fold of 4 records per thread: 4x fewer records for the warp levels
+        const size_t groups = size_t(L.batch) * (cnt_items / 4);
+        msm_fold_seq_kernel<F><<<unsigned((groups + 63) / 64), 64, 0, st>>>(tin, nullptr, win, groups, 4, 0, 0, L.seg_log, scratch,
+                                                                           scratch + groups, scratch + 2 * groups);
+        ctx->launches++;
+        tin = scratch, bin = scratch + groups, win = scratch + 2 * groups;
+        scratch += 3 * groups;
+        cnt_items /= 4;
+        log_m = 2;
+      }
+      while (true) {
+        const int cnt = cnt_items > 32 ? 32 : int(cnt_items);
+        const size_t groups = size_t(L.batch) * (cnt_items / cnt);
+        const int finish = cnt_items <= 32 ? 1 : 0;
+        P* oT = finish ? res : scratch;
+        P* oB = scratch + groups;
+        P* oW = scratch + 2 * groups;
+        msm_fold_level_kernel<F><<<unsigned(groups), 96, 0, st>>>(tin, bin, win, cnt, log_m, finish, L.seg_log, oT, oB, oW);
+        ctx->launches++;
+        if (finish) break;
+        tin = oT, bin = oB, win = oW;
+        scratch += 3 * groups;
+        cnt_items /= 32;
+        log_m += 5;
+      }
     }
     if (out_affine) {
       xyzz_to_affine_bytes_kernel<F><<<unsigned((L.batch + 63) / 64), 64, 0, st>>>(res, size_t(L.batch), out_affine);
