@@ -823,6 +823,29 @@ def test_msm_batch_equals_single_msms(ctx):
             bases.free()
 
 
+def test_sharded_msm_engine_orders_a_default_stream_context(ctx):
+    """zelana_b200.multi.GpuMsmEngine / ShardedMsm with the DEFAULT Context (its own non-blocking stream, not torch's): the
+    scalars are produced by torch kernels on torch's stream immediately before the MSM and the result is read by torch right
+    after the combine -- the engine has to order the two streams itself (round-1 advisor finding).  Both groups, run twice."""
+    import numpy as np
+    import torch
+    from zelana_b200.multi import GpuMsmEngine, ShardedMsm
+    assert ctx.stream_handle != torch.cuda.current_stream().cuda_stream
+    n = 200_000
+    k = torch.from_numpy(_rand_fr_np(n, 71).view(np.int32)).cuda()
+    for group, cnt in ((1, n), (2, 20_000)):
+        bases = (ctx.g1_bases_generate if group == 1 else ctx.g2_bases_generate)(k, cnt)
+        sm = ShardedMsm(GpuMsmEngine(ctx, bases, group=group))
+        host = _rand_fr_np(cnt, 72 + group)
+        want = (ctx.msm_g1 if group == 1 else ctx.msm_g2)(bases, host)
+        for rep in range(2):
+            big = torch.from_numpy(host.view(np.int32)).cuda()
+            sc = (big ^ 0x55555555) ^ 0x55555555            # a torch kernel writes the scalars just before the MSM reads them
+            got = sm.run(sc, cnt).cpu().numpy().tobytes()
+            assert got == want, (group, rep)
+        bases.free()
+
+
 def test_msm_multi_c_abi_equals_single_msm(ctx):
     """zkb_msm_g1_multi / zkb_msm_g2_multi (one process, one context per GPU, range-sharded bases, host
     gather of the partial sums): same bytes as one MSM over all points.  Contexts sit on distinct GPUs when the box has them,
