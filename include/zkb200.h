@@ -255,6 +255,12 @@ int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* 
  * valid until _end, which waits and copies the results out.  One batch in flight per context. */
 int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
                           size_t k);
+/* flags = ZKB_BATCH_Z_MONTGOMERY: z_host holds Montgomery limbs (x * 2^256 mod r as 32 B little-endian, < r) instead of
+ * canonical values -- the form ark-ff's Fp<MontBackend<_, 4>> keeps in memory, so a host synthesiser
+ * hands its assignment over without 6 000 from-Montgomery products per L2-circuit proof; (r, s) stay canonical.  Same proofs. */
+#define ZKB_BATCH_Z_MONTGOMERY 1u
+int zkb_prove_batch_begin_ex(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
+                             size_t k, unsigned flags);
 int zkb_prove_batch_end(zkb_ctx* ctx, size_t k, uint8_t* out);
 int zkb_prove_batch(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host, size_t k,
                     uint8_t* out);

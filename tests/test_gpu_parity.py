@@ -789,6 +789,12 @@ def test_prove_batch_equals_single_proves(ctx, l2_setup):
     # 70 proofs: the sequential record folds (batches of >= 64 vectors) and five warps of the packed finish kernel
     reps = [i % K for i in range(70)]
     assert ctx.prove_batch(dpk, m, b"".join(zs[i] for i in reps), b"".join(rs[i][0] + rs[i][1] for i in reps)) == [expect[i] for i in reps]
+    # the same assignments handed over as Montgomery limbs (ZKB_BATCH_Z_MONTGOMERY: what the native batch prover's host threads write)
+    def mont(zb):
+        return b"".join(((int.from_bytes(zb[i:i + 32], "little") << 256) % R).to_bytes(32, "little") for i in range(0, len(zb), 32))
+    assert ctx.prove_batch(dpk, m, b"".join(mont(z) for z in zs[:5]), b"".join(r + s for r, s in rs[:5]), montgomery=True) == expect[:5]
+    with pytest.raises(Exception):                                          # a limb pattern >= r is refused in either form
+        ctx.prove_batch(dpk, m, mont(zs[0])[:-32] + R.to_bytes(32, "little"), rs[0][0] + rs[0][1], montgomery=True)
     with pytest.raises(Exception):
         ctx.prove_batch(dpk, m, b"".join(zs[:2]), rs[0][0] + rs[0][1])      # two assignments, one (r, s)
     m.free()

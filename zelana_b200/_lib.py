@@ -131,6 +131,7 @@ SIGNATURES = {
     "zkb_pk_synthetic": (_I, [_P, _SZ, _SZ, _SZ, _P, _SZ, C.POINTER(_P)]),
     "zkb_prove": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "zkb_prove_batch_begin": (_I, [_P, _P, _P, _P, _P, _SZ]),
+    "zkb_prove_batch_begin_ex": (_I, [_P, _P, _P, _P, _P, _SZ, C.c_uint]),
     "zkb_prove_batch_end": (_I, [_P, _SZ, _P]),
     "zkb_prove_batch": (_I, [_P, _P, _P, _P, _P, _SZ, _P]),
     "zkb_setup": (_I, [_P, C.POINTER(R1csDesc), C.POINTER(SetupParams), C.POINTER(SetupOut)]),

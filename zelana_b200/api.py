@@ -390,9 +390,10 @@ class Context:
                                                ob.ctypes.data_as(C.c_void_p), oc.ctypes.data_as(C.c_void_p)))
         return oa.tobytes(), ob.tobytes(), oc.tobytes()
 
-    def prove_batch(self, pk, r1cs, z_bytes, rs_bytes):
+    def prove_batch(self, pk, r1cs, z_bytes, rs_bytes, montgomery=False):
         """K proofs of one circuit/key in one set of batched launches (zkb_prove_batch).  z_bytes: K assignments back to back;
-        rs_bytes: K x (r || s).  -> list of (A, B, C) byte triples, identical to K calls of prove()."""
+        rs_bytes: K x (r || s).  -> list of (A, B, C) byte triples, identical to K calls of prove().
+        montgomery=True: z_bytes holds Montgomery limbs (x * 2^256 mod r), zkb_prove_batch_begin_ex / ZKB_BATCH_Z_MONTGOMERY."""
         pz, kz = _buf(z_bytes)
         prs, krs = _buf(rs_bytes)
         per = (r1cs.num_instance + r1cs.num_witness) * 32
@@ -401,7 +402,11 @@ class Context:
             raise ZkbError(-6, "prove_batch: %d bytes of assignments and %d bytes of (r, s) do not describe the same number of proofs"
                            % (len(kz), len(krs)))
         out = np.empty(k * 256, dtype=np.uint8)
-        self._check(self.lib.zkb_prove_batch(self.h, pk.h, r1cs.h, pz, prs, k, out.ctypes.data_as(C.c_void_p)))
+        if montgomery:
+            self._check(self.lib.zkb_prove_batch_begin_ex(self.h, pk.h, r1cs.h, pz, prs, k, 1))
+            self._check(self.lib.zkb_prove_batch_end(self.h, k, out.ctypes.data_as(C.c_void_p)))
+        else:
+            self._check(self.lib.zkb_prove_batch(self.h, pk.h, r1cs.h, pz, prs, k, out.ctypes.data_as(C.c_void_p)))
         o = out.tobytes()
         return [(o[256 * i:256 * i + 64], o[256 * i + 64:256 * i + 192], o[256 * i + 192:256 * i + 256]) for i in range(k)]
 

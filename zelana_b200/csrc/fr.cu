@@ -69,6 +69,15 @@ __global__ void to_mont_kernel(const Fr* in, Fr* out, size_t n, int* bad) {
   out[i] = x.to_mont();
 }
 
+// Montgomery limbs -> canonical; flags values >= r (the host's Montgomery form is the same 256-bit R: zkb_prove_batch_begin_ex)
+__global__ void from_mont_kernel(const Fr* in, Fr* out, size_t n, int* bad) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x = in[i];
+  if (!fr_is_canonical(x)) { atomicExch(bad, 1); return; }
+  out[i] = x.from_mont();
+}
+
 // out[i] = <row_i, z> for i < nc ; optionally out[nc + j] = z[j] for j < ni ; zero up to n.
 // One thread per row; a row of CSR_LONG_ROW terms or more (the 254-term bit-packing rows of ark-r1cs-std's comparison
 // gadget, the ~60-term rows of Poseidon's partial rounds) is handed to the whole warp afterwards: 32 lanes stride over it
@@ -532,6 +541,14 @@ int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n) {
   return ZKB_OK;
 }
 
+int fr_from_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n) {
+  if (!n) return ZKB_OK;
+  from_mont_kernel<<<blocks_for(n, 128), 128, 0, ctx->stream>>>(in, out, n, ctx->flag.as<int>());
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return ZKB_OK;
+}
+
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail) {
   prove_tail_scalars_kernel<<<1, 32, 0, ctx->stream>>>(r, s, za_tail, zl_tail);
   ctx->launches++;
@@ -683,7 +700,7 @@ int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev
 // [a-chain of every proof | b-chains | c-chains] so that each NTT stage is ONE batched launch over 3 K polynomials;
 // zm: K x nv scratch; h_out: K x n canonical coefficients of the K quotients.
 int witness_map_batch_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
-                          int lg, int K, const Fr* z, Fr* zm, Fr* w3, Fr* h_out) {
+                          int lg, int K, const Fr* z, Fr* zm, bool zm_ready, Fr* w3, Fr* h_out) {
   const size_t n = size_t(1) << lg;
   const size_t nv = ni + nw;
   cudaStream_t st = ctx->stream;
@@ -692,7 +709,7 @@ int witness_map_batch_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const 
   Fr* wc = w3 + 2 * size_t(K) * n;
   {
     ProfScope ps(ctx, PH_MATVEC);
-    ZKB_TRY(fr_to_mont(ctx, z, zm, nv * size_t(K)));
+    if (!zm_ready) ZKB_TRY(fr_to_mont(ctx, z, zm, nv * size_t(K)));
     dim3 grid(blocks_for(n, 128), unsigned(K));
     csr_matvec_kernel<<<grid, 128, 0, st>>>(A.row_ptr, A.col, A.coeff, zm, nc, ni, 1, n, wa, nv);
     csr_matvec_kernel<<<grid, 128, 0, st>>>(B.row_ptr, B.col, B.coeff, z, nc, ni, 0, n, wb, nv);

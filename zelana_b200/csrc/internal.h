@@ -332,6 +332,7 @@ struct CsrDev {
 };
 int fr_field_op(zkb_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int fr_to_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);
+int fr_from_mont(zkb_ctx* ctx, const Fr* in, Fr* out, size_t n);   // flags values >= r like fr_to_mont
 // MiMC-7 (forge stack): n hashes of `arity` elements; n Merkle roots along depth-long paths.  Flag non-canonical input in ctx->flag.
 // Poseidon of the L2 circuit: params_canonical = 64 x 3 round constants | 3 x 3 MDS (canonical bytes; needed on the first call)
 int poseidon_hash_dev(zkb_ctx* ctx, const uint8_t* params_canonical, int arity, const Fr* in, size_t n, Fr* out);
@@ -346,7 +347,7 @@ struct WitnessBufs {
 int witness_map_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
                     int log_domain, const WitnessBufs& w, Fr* h_out);
 int witness_map_batch_dev(zkb_ctx* ctx, const CsrDev& A, const CsrDev& B, const CsrDev& C, uint64_t nc, uint64_t ni, uint64_t nw,
-                          int log_domain, int K, const Fr* z, Fr* zm, Fr* w3, Fr* h_out);
+                          int log_domain, int K, const Fr* z, Fr* zm, bool zm_ready, Fr* w3, Fr* h_out);
 int prove_tail_scalars(zkb_ctx* ctx, const Fr* r, const Fr* s, Fr* za_tail, Fr* zl_tail);
 int fr_scale(zkb_ctx* ctx, const Fr* in, const Fr* k_dev, Fr* out, size_t n);  // out[i] = k * in[i], all canonical
 int setup_scalars_dev(zkb_ctx* ctx, const uint64_t* const col_ptr[3], const uint32_t* const row[3], const Fr* const coeff[3],

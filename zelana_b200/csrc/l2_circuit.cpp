@@ -1628,8 +1628,11 @@ int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, con
           std::vector<l2::Fr> z;
           rc = l2_assign(c, inputs + i, witnesses + i, &z);
           if (rc == ZKB_OK) {
+            // Montgomery limbs as they are (little-endian host: the same 32 bytes the device's 8 x 32-bit form reads):
+            // zkb_prove_batch_begin_ex converts on the GPU, the host saves one Montgomery product per variable
+            static_assert(sizeof(l2::Fr) == 32, "Fr is four 64-bit limbs");
             if (z.size() != nv) rc = ZKB_ERR_SHAPE;
-            else l2_z_to_bytes(z, zdst);
+            else memcpy(zdst, z.data(), nv * 32);
           }
         } catch (const std::bad_alloc&) {
           rc = ZKB_ERR_OOM;
@@ -1646,7 +1649,7 @@ int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, con
         zkb_l2_prover_randomness(inputs[i].batch_id, s.rs + 64 * k, s.rs + 64 * k + 32);
       };
       b->pool->parallel_for(s.count, assign_one);
-      int rc = zkb_prove_batch_begin(s.ctx, pk, m, s.z, s.rs, s.count);
+      int rc = zkb_prove_batch_begin_ex(s.ctx, pk, m, s.z, s.rs, s.count, ZKB_BATCH_Z_MONTGOMERY);
       if (rc != ZKB_OK) {
         note(rc, zkb_last_error(s.ctx));
         for (size_t k = 0; k < s.count; ++k)

@@ -1288,7 +1288,17 @@ int ensure_lanes(zkb_ctx* ctx) {
 // the K x 256 B results into pinned memory; _end waits and hands them out.  z_host and rs_host must stay valid until _end.
 extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
                                      size_t K) {
+  return zkb_prove_batch_begin_ex(ctx, pk_c, m, z_host, rs_host, K, 0u);
+}
+
+// flags & ZKB_BATCH_Z_MONTGOMERY: the assignments are Montgomery limbs (x * 2^256 mod r, little-endian), the form a host
+// synthesiser computes in -- the device needs both forms anyway (Montgomery for the A mat-vec, canonical for the MSM digits), so
+// the conversion costs one kernel either way, and the host keeps the ~0.15 ms per L2-circuit proof of 6 000 from_mont products.
+extern "C" int zkb_prove_batch_begin_ex(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb_r1cs* m, const uint8_t* z_host, const uint8_t* rs_host,
+                                        size_t K, unsigned flags) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
+  if (flags & ~unsigned(ZKB_BATCH_Z_MONTGOMERY)) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: unknown flag bits %#x", flags);
+  const bool z_mont = (flags & ZKB_BATCH_Z_MONTGOMERY) != 0;
   if (!pk_c || !m || !z_host || !rs_host || K < 1 || K > 4096) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: bad argument (1 <= K <= 4096)");
   zkb_pk* pk = const_cast<zkb_pk*>(pk_c);   // the delta tables are built on first use
   if (pk->world != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_batch: sharded key");
@@ -1376,8 +1386,9 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
   Fr* z = ctx->bz.as<Fr>();
   Fr* rs = ctx->brs.as<Fr>();
   ZKB_TRY(clear_flag(ctx));
-  CUDA_TRY(ctx, cudaMemcpyAsync(z, z_host, K * nv * 32, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(z_mont ? ctx->bzm.p : ctx->bz.p, z_host, K * nv * 32, cudaMemcpyHostToDevice, st));
   CUDA_TRY(ctx, cudaMemcpyAsync(rs, rs_host, K * 64, cudaMemcpyHostToDevice, st));
+  if (z_mont) ZKB_TRY(fr_from_mont(ctx, ctx->bzm.as<Fr>(), z, K * nv));   // the MSM lanes read canonical scalars
   CUDA_TRY(ctx, cudaEventRecord(ctx->ev_inputs, st));
   BatchOut o = batch_out(ctx, K);
   // A, B1, B2, L depend on z only: four lanes next to the witness maps + H on the main stream
@@ -1414,7 +1425,7 @@ extern "C" int zkb_prove_batch_begin(zkb_ctx* ctx, const zkb_pk* pk_c, const zkb
   on_lane(3, [&] { return msm1(pk->l_ext, z + ni, nw, nv, o.pL); });
   int mrc = ZKB_OK;
   if (lane_rc == ZKB_OK) {
-    mrc = witness_map_batch_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, Ki, z, ctx->bzm.as<Fr>(), ctx->bw3.as<Fr>(),
+    mrc = witness_map_batch_dev(ctx, m->a, m->b, m->c, m->nc, m->ni, m->nw, m->log_domain, Ki, z, ctx->bzm.as<Fr>(), z_mont, ctx->bw3.as<Fr>(),
                                 ctx->bh.as<Fr>());
     if (mrc == ZKB_OK) mrc = msm1(pk->h, ctx->bh.as<Fr>(), hn, n, o.pH);
   }
