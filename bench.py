@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-log-n", type=int, default=0, help="0 = choose for ~10-30 s of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-l2", action="store_true", help="msm_g1 workload: skip the L2-circuit proofs/s leg (size sweeps)")
     ap.add_argument("--workload", default="msm_g1", choices=["msm_g1", "ntt", "msm_sweep", "prove", "prove_sharded"],
                     help="msm_g1 = the contract line (default); ntt / msm_sweep = BASELINE.json configs 3 / 2 as extra sweeps")
     ap.add_argument("--concurrency", type=int, default=1, help="prove workload: contexts (host threads + streams) per GPU")
@@ -418,7 +419,8 @@ def run_ours(args):
         del scal
         if rank == 0 and world == 1 and args.log_n == 24:
             extras = compact_config_lines(np, torch, zelana_b200, ctx, stream, dev, peak)
-        proofs = l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak, cpu_baseline=not args.no_cpu_baseline)
+        if not args.no_l2:
+            proofs = l2_sized_proofs_per_s(np, torch, dist, zelana_b200, local, world, rank, peak, cpu_baseline=not args.no_cpu_baseline)
 
     if rank == 0:
         line = {
