@@ -755,6 +755,16 @@ def test_l2_batch_prove_equals_single_proofs(ctx, l2_setup):
     n, _xs, _ws, _keep, out, status = pack
     assert list(status)[:7] == [0, 0, 0, 0, -6, 0, 0]
     assert [out.raw[256 * i:256 * i + 256] for i in (0, 1, 2, 3, 5, 6)] == expect[:6]
+    # calls of <= 8 proofs take the per-proof path (one context each), larger ones the batched kernels: both sides of the switch
+    assert bp.prove(circuits[:8]) == expect[:8]
+    assert bp.prove(circuits[:9]) == expect[:9]
+    pack = bp.marshal(circuits[:10] + [wrong] + circuits[10:12])
+    with pytest.raises(ZkbError) as e:
+        bp.prove_marshalled(pack)
+    assert e.value.code == -6
+    n, _xs, _ws, _keep, out, status = pack
+    assert list(status) == [0] * 10 + [-6, 0, 0]
+    assert [out.raw[256 * i:256 * i + 256] for i in list(range(10)) + [11, 12]] == expect[:12]
     bp.close()
     single.m.free()
     dpk.free()

@@ -1467,6 +1467,7 @@ struct BatchSlot {
 }  // namespace
 
 constexpr int L2_MAX_SLOTS = 8;
+constexpr size_t L2_SMALL_BATCH = 8;   // <= L2_MAX_SLOTS: calls of at most this many proofs run zkb_prove per proof, one context each
 
 // device slots in flight per batch object: env ZKB_L2_SLOTS (2..8), default 4.  More than two, because a sub-batch ends in
 // latency-bound kernels (bucket folds, the two scalar-multiplication chains) that only overlap with ANOTHER sub-batch's
@@ -1541,7 +1542,14 @@ static size_t l2_subbatch(size_t n) {
     }
     return size_t(256);
   }();
-  size_t kb = (n + 3) / 4;   // at least four sub-batches per call, so that assignment and proving overlap
+  static const size_t split = [] {
+    if (const char* e = getenv("ZKB_L2_SPLIT")) {
+      long v = atol(e);
+      if (v >= 1 && v <= 64) return size_t(v);
+    }
+    return size_t(4);
+  }();
+  size_t kb = (n + split - 1) / split;   // at least `split` (4) sub-batches per call, so that assignment and proving overlap
   if (kb < 16) kb = 16;
   if (kb > cap) kb = cap;
   return kb;
@@ -1587,6 +1595,55 @@ int zkb_l2_batch_prove(zkb_l2_batch* b, const zkb_pk* pk, const zkb_r1cs* m, con
         l2_format_solana(r, r + 64, r + 192, proofs_out + 256 * (s.base + k));
       }
     };
+    if (n >= 1 && n <= L2_SMALL_BATCH) {
+      // A handful of proofs: the batched kernels are latency-bound here (one sub-batch of 8 takes 6.9 ms, most of it the
+      // 254-step finishing chains), while zkb_prove -- which trades those chains for two more small MSMs and replays a captured
+      // graph -- takes 1.7 ms per proof and runs side by side on separate contexts: 8 proofs in 4.6 ms.  One context per proof.
+      for (size_t k = 0; k < n; ++k) {
+        if (b->slots[k].ctx) continue;
+        int rc = zkb_ctx_create(b->device, &b->slots[k].ctx);
+        if (rc != ZKB_OK) {
+          g_l2_error = "zkb_l2_batch_prove: zkb_ctx_create failed";
+          return rc;
+        }
+        zkb_ctx_set_blocking_sync(b->slots[k].ctx, 1);
+      }
+      std::function<void(size_t)> prove_one = [&](size_t i) {
+        int rc;
+        try {
+          std::vector<l2::Fr> z;
+          rc = l2_assign(c, inputs + i, witnesses + i, &z);
+          if (rc == ZKB_OK && z.size() != nv) rc = ZKB_ERR_SHAPE;
+          if (rc == ZKB_OK) {
+            std::vector<uint8_t> zb(nv * 32);
+            l2_z_to_bytes(z, zb.data());
+            uint8_t r[32], sc[32], pa[64], pb[128], pc[64];
+            zkb_l2_prover_randomness(inputs[i].batch_id, r, sc);
+            rc = zkb_prove(b->slots[i].ctx, pk, m, zb.data(), r, sc, pa, pb, pc);
+            if (rc == ZKB_OK) l2_format_solana(pa, pb, pc, proofs_out + 256 * i);
+            else g_l2_error = zkb_last_error(b->slots[i].ctx);
+          }
+        } catch (const std::bad_alloc&) {
+          rc = ZKB_ERR_OOM;
+          g_l2_error = "out of host memory";
+        } catch (...) {
+          rc = ZKB_ERR_INVALID_ARG;
+          g_l2_error = "exception in the witness assignment";
+        }
+        if (rc != ZKB_OK) {
+          status[i] = rc;
+          note(rc, g_l2_error);
+        }
+      };
+      b->pool->parallel_for(n, prove_one);
+      if (status_out)
+        for (size_t i = 0; i < n; ++i) status_out[i] = status[i];
+      if (first_rc != ZKB_OK) {
+        g_l2_error = first_msg;
+        return first_rc;
+      }
+      return ZKB_OK;
+    }
     const size_t kb = l2_subbatch(n);
     for (size_t j = 0; j * kb < n; ++j) {
       BatchSlot& s = b->slots[j % size_t(b->nslots)];
