@@ -16,9 +16,13 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k(const unsigned* seed, int iters, unsigned long long* sink) {
   unsigned a = seed[threadIdx.x & 31] | 1u, b = seed[32 + (threadIdx.x & 31)] | 1u;
   unsigned long long w[CH];
-  unsigned lo[CH], hi[CH], ad[CH], cl[CH], chh[CH];
+  unsigned lo[CH], hi[CH], ad[CH], cl[CH], chh[CH], bank[CH];
+  double fd[CH];
+  unsigned x0[CH / 4 + 1], x1[CH / 4 + 1], x2[CH / 4 + 1], x3[CH / 4 + 1], x4[CH / 4 + 1], x5[CH / 4 + 1], x6[CH / 4 + 1], x7[CH / 4 + 1];
 #pragma unroll
-  for (int c = 0; c < CH; c++) { w[c] = seed[c] + threadIdx.x; lo[c] = seed[c + 8]; hi[c] = seed[c + 16]; ad[c] = seed[c + 24]; cl[c] = seed[c] ^ 5; chh[c] = seed[c] ^ 9; }
+  for (int c = 0; c < CH; c++) { w[c] = seed[c] + threadIdx.x; lo[c] = seed[c + 8]; hi[c] = seed[c + 16]; ad[c] = seed[c + 24]; cl[c] = seed[c] ^ 5; chh[c] = seed[c] ^ 9; bank[c] = 0; fd[c] = 1.0 + 1e-9 * (seed[c] & 1023);
+    x0[c / 4] = seed[c]; x1[c / 4] = seed[c + 1]; x2[c / 4] = seed[c + 2]; x3[c / 4] = seed[c + 3]; x4[c / 4] = seed[c + 4]; x5[c / 4] = seed[c + 5]; x6[c / 4] = seed[c + 6]; x7[c / 4] = seed[c + 7]; }
+  const double fk = 1.0 + 1e-12 * (seed[3] & 7);
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int r = 0; r < INNER; r++) {
@@ -29,13 +33,26 @@ __global__ void __launch_bounds__(256) k(const unsigned* seed, int iters, unsign
         if (MODE & 4) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(lo[c]) : "r"(a + c));
         if (MODE & 8) asm volatile("mad.hi.u32 %0, %0, %0, %1;" : "+r"(hi[c]) : "r"(a + c));
         if (MODE & 16) asm volatile("xor.b32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(ad[c]) : "r"(a + c), "r"(b));
+        // round 2: 64 = DFMA; 128 = 32x32->64 accumulate with carry-OUT only, the carry banked by an addc (the chain-head form);
+        // 256 = one chain of four 32x32->64 accumulates linked by carries (what a row of the Montgomery product is), per 4 chains
+        if (MODE & 64) asm volatile("fma.rn.f64 %0, %0, %1, %0;" : "+d"(fd[c]) : "d"(fk));
+        if (MODE & 128) asm volatile("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;" : "+r"(cl[c]), "+r"(chh[c]), "+r"(bank[c]) : "r"(a + c), "r"(cl[c] | 1u));
+        if ((MODE & 256) && (c & 3) == 0) asm volatile(
+            "mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+            "madc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+            "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %10, %7;"
+            : "+r"(x0[c / 4]), "+r"(x1[c / 4]), "+r"(x2[c / 4]), "+r"(x3[c / 4]), "+r"(x4[c / 4]), "+r"(x5[c / 4]), "+r"(x6[c / 4]), "+r"(x7[c / 4])
+            : "r"(x0[c / 4] | 1u), "r"(a + c), "r"(b), "r"(a ^ b));
         if (MODE & 32) asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;\n\tmadc.hi.u32 %1, %0, %2, %1;" : "+r"(cl[c]), "+r"(chh[c]) : "r"(a + c));
       }
     }
   }
   unsigned long long s = 0;
 #pragma unroll
-  for (int c = 0; c < CH; c++) s ^= w[c] ^ lo[c] ^ hi[c] ^ ad[c] ^ cl[c] ^ chh[c];
+  for (int c = 0; c < CH; c++) s ^= w[c] ^ lo[c] ^ hi[c] ^ ad[c] ^ cl[c] ^ chh[c] ^ bank[c] ^ (unsigned long long)__double_as_longlong(fd[c]);
+#pragma unroll
+  for (int c = 0; c < CH; c += 4) s ^= x0[c / 4] + 3 * x1[c / 4] + 5 * x2[c / 4] + 7 * x3[c / 4] + 11 * x4[c / 4] + 13 * x5[c / 4] + 17 * x6[c / 4] + 19 * x7[c / 4];
   if ((unsigned)(s ^ (s >> 32)) == 0x12345678u) sink[0] = s;
 }
 
@@ -78,5 +95,12 @@ int main(int argc, char** argv) {
   run<32 | 16>("carry pair + XOR+IADD", 4, seed, sink, sms, mhz);
   run<32 | 4>("carry pair + IMAD lo", 3, seed, sink, sms, mhz);
   run<1 | 4 | 16>("IMAD.WIDE + IMAD lo + XOR+IADD", 4, seed, sink, sms, mhz);
+  // round 2 additions: the FP64 pipe and the carry forms of the wide multiply
+  run<64>("DFMA", 1, seed, sink, sms, mhz);
+  run<64 | 1>("DFMA + IMAD.WIDE", 2, seed, sink, sms, mhz);
+  run<64 | 16>("DFMA + XOR+IADD", 3, seed, sink, sms, mhz);
+  run<128>("wide MAD, carry OUT only + addc bank (3 PTX)", 3, seed, sink, sms, mhz);
+  run<256>("chain of 4 wide MADs linked by carries (8 PTX) /4", 2, seed, sink, sms, mhz);   // 8 PTX per 4 chains = 2 per chain
+  run<256 | 64>("carry chain of 4 + DFMA", 3, seed, sink, sms, mhz);
   return 0;
 }

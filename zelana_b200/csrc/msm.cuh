@@ -83,6 +83,21 @@ __device__ __forceinline__ Affine<F> load_affine(const Affine<F>* __restrict__ p
   for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++) dst[k] = __ldg(src + k);
   return r;
 }
+// The same for the random gathers of the accumulation, with the L2 told to fetch only the 64 bytes around the address
+// (ld.global.nc.L2::64B -> LDG.E.LTC64B): a G1 point is one aligned 64 B record, and without the hint every gather pulled its
+// whole 128 B line from HBM -- 28.9 GB of DRAM reads per 2^24-point MSM against 14.5 GB algorithmic; with it 16.1 GB
+// (profiles/r02_l2_fetch_granularity.txt; cudaLimitMaxL2FetchGranularity changes nothing).  The kernel is bound by the multiply
+// pipe, so its time does not move (29.7 ms); the HBM energy and the bandwidth left to a concurrent upload do.
+template <class F>
+__device__ __forceinline__ Affine<F> gather_affine(const Affine<F>* __restrict__ p) {
+  Affine<F> r;
+  uint4* dst = reinterpret_cast<uint4*>(&r);
+  const uint4* src = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int k = 0; k < int(sizeof(Affine<F>) / 16); k++)
+    asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(dst[k].x), "=r"(dst[k].y), "=r"(dst[k].z), "=r"(dst[k].w) : "l"(src + k));
+  return r;
+}
 
 template <class F>
 __device__ __forceinline__ void store_affine(Affine<F>* p, const Affine<F>& v) {
@@ -181,7 +196,7 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
   XYZZ<F> acc = XYZZ<F>::inf();
   // software pipeline: the point of entry j+1 is in flight while entry j is added
   uint32_t v = vals[start];
-  Affine<F> nxt = load_affine(table + (v & 0x7fffffffu));
+  Affine<F> nxt = gather_affine(table + (v & 0x7fffffffu));
   uint32_t nxt_neg = v >> 31;
   for (size_t j = start; j < end; j++) {
     Affine<F> pt = nxt;
@@ -191,7 +206,7 @@ msm_accumulate_kernel(const Affine<F>* __restrict__ table, const uint32_t* __res
     if (more) {
       k = keys[j + 1];
       uint32_t v2 = vals[j + 1];
-      nxt = load_affine(table + (v2 & 0x7fffffffu));
+      nxt = gather_affine(table + (v2 & 0x7fffffffu));
       nxt_neg = v2 >> 31;
     }
     if (neg) pt.y = pt.y.neg();

@@ -90,6 +90,12 @@ extern "C" int zkb_ctx_create(int device, zkb_ctx** out) {
   }
   ctx->own_stream = true;
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* fg = getenv("ZKB_L2_FETCH_GRANULARITY")) {
+    // experiment knob: the L2's DRAM fetch granularity for this device, 32 / 64 / 128 bytes; a hint the driver may ignore
+    int v = atoi(fg);
+    if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(v));
+    cudaGetLastError();
+  }
   if (const char* sl = getenv("ZKB_MSM_SLICES")) {
     int v = atoi(sl);
     if (v >= 1 && v <= ZKB_MAX_SLICES - 1) ctx->msm_slices = v;
