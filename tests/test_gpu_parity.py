@@ -862,6 +862,42 @@ def test_sharded_msm_engine_orders_a_default_stream_context(ctx):
         bases.free()
 
 
+def test_entry_points_on_a_second_gpu_from_a_thread_on_the_first(l2_setup):
+    """A host thread's current CUDA device is 0 unless it says otherwise; every entry point must put ITS context's device in
+    place for everything it does, including the wait at the end (a blocking-sync event created on the wrong device is an
+    'invalid resource handle': found by the 8-GPU bench, where ranks 1..7 prove small batches through zkb_prove).
+    Needs two GPUs; the single-GPU box skips it."""
+    import torch
+    import zelana_b200
+    from zelana_b200 import l2_circuit as P2
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    circ, pk_bytes, vk_bytes, raw = l2_setup
+    torch.cuda.set_device(0)
+    c0, c1 = zelana_b200.Context(0), zelana_b200.Context(1)
+    for c in (c0, c1):
+        assert c.lib.zkb_ctx_set_blocking_sync(c.h, 1) == 0
+    proofs = []
+    for c in (c0, c1):
+        dpk = c.proving_key_compressed(pk_bytes, validate=False)
+        single = P2.L2Prover(c, circ, dpk, vk_bytes)
+        ck = P2.L2BlockCircuit(transactions=[P2.TransactionWitness(bytes([1] * 32), bytes([2] * 32), 5)],
+                               initial_accounts={bytes([1] * 32): 1000, bytes([2] * 32): 7}, batch_id=9)
+        ck = ck.with_inputs(P2.satisfying_inputs(ck))
+        one = single.prove_circuit(ck).proof_bytes
+        bp = P2.L2BatchProver(c, circ, dpk, lanes=4)
+        assert bp.prove([ck] * 3) == [one] * 3            # per-proof path (<= 8), worker threads of the pool
+        assert bp.prove([ck] * 12) == [one] * 12          # batched path
+        bp.close()
+        proofs.append(one)
+        single.m.free()
+        dpk.free()
+        assert torch.cuda.current_device() == 0           # the caller's device is left alone
+    assert proofs[0] == proofs[1]
+    c0.close()
+    c1.close()
+
+
 def test_msm_multi_c_abi_equals_single_msm(ctx):
     """zkb_msm_g1_multi / zkb_msm_g2_multi (one process, one context per GPU, range-sharded bases, host
     gather of the partial sums): same bytes as one MSM over all points.  Contexts sit on distinct GPUs when the box has them,

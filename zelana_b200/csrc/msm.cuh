@@ -35,6 +35,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "internal.h"
 #include "sort.cuh"
 
@@ -981,11 +983,12 @@ cudaError_t msm_run_comb(zkb_ctx* ctx, const Affine<F>* comb, int c, int nwin, c
   const size_t nb = (n + ppb - 1) / ppb;
   size_t smem = ppb * nwin * 4;
   if (smem < size_t(T::ACC_THREADS) * sizeof(P)) smem = size_t(T::ACC_THREADS) * sizeof(P);   // the tree sum reuses the list's memory
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<unsigned long long> attr_done{0};   // per device (see msm_sort_entries)
+  const unsigned long long bit = 1ull << (ctx->device & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     cudaError_t ea = cudaFuncSetAttribute(comb_accumulate_kernel<F, T::ACC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (ea != cudaSuccess) return ea;
-    attr_done = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   cudaError_t e = ctx->msm_ws.reserve(size_t(batch) * nb * sizeof(P));
   if (e != cudaSuccess) return e;

@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdint>
 
 namespace zkb {
@@ -449,13 +451,19 @@ constexpr size_t SORT_PASS_SMEM = size_t(SORT_TILE) * 2 * sizeof(uint32_t);
 static inline cudaError_t msm_sort_entries(const EntrySource& src, const SortLayout& L, int sm_count, uint32_t* hdr, uint32_t* k0,
                                            uint32_t* v0, uint32_t* k1, uint32_t* v1, cudaStream_t st, const uint32_t** out_keys,
                                            const uint32_t** out_vals, unsigned long long* launches) {
-  static bool attr_done = false;   // per process; harmless if repeated by a racing thread
-  if (!attr_done) {
+  // Function attributes belong to the DEVICE that is current when they are set: once per device, not once per process (a
+  // process driving several GPUs launched the 64 KB tiles on its second GPU without the opt-in).  Harmless if a racing
+  // thread repeats it.
+  static std::atomic<unsigned long long> attr_done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cudaGetLastError();
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     cudaError_t e = cudaFuncSetAttribute(sort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SORT_PASS_SMEM));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(msm_entry_pass0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sort_p0_smem(64)));
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   if (src.nwin > 128) return cudaErrorInvalidValue;   // c >= 2
   if (L.max_entries >= (size_t(1) << 30)) return cudaErrorInvalidValue;   // look-back words carry 30-bit counts

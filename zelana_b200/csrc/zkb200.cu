@@ -19,6 +19,7 @@ static int ensure_pinned(zkb_ctx* ctx) {
 }
 
 int check_flag(zkb_ctx* ctx, const char* what) {
+  ZKB_ON_DEVICE(ctx);   // the blocking-sync event below belongs to the device that is current when it is created
   ZKB_TRY(ensure_pinned(ctx));
   int* hf = reinterpret_cast<int*>(ctx->pinned + 256);
   CUDA_TRY(ctx, cudaMemcpyAsync(hf, ctx->flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1477,6 +1478,7 @@ extern "C" int zkb_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, cons
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!pk || !m || !z_host || !r || !s || !out_a || !out_b || !out_c) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: null argument");
   if (pk->world != 1) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove: this key is shard %d of %d (use zkb_prove_partial)", pk->shard, pk->world);
+  ZKB_ON_DEVICE(ctx);   // also covers the copies and the wait after prove_enqueue (a host thread's current device is 0 by default)
   ZKB_TRY(prove_enqueue(ctx, pk, m, z_host, r, s, false, "zkb_prove"));
   ProveOut o = prove_out(ctx);
   cudaStream_t st = ctx->stream;
@@ -1496,6 +1498,7 @@ extern "C" int zkb_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs*
                                  const uint8_t s[32], void* out_partial_dev) {
   if (!ctx) return ZKB_ERR_INVALID_ARG;
   if (!pk || !m || !z_host || !r || !s || !out_partial_dev) ZKB_FAIL(ctx, ZKB_ERR_INVALID_ARG, "zkb_prove_partial: null argument");
+  ZKB_ON_DEVICE(ctx);
   ZKB_TRY(prove_enqueue(ctx, pk, m, z_host, r, s, true, "zkb_prove_partial"));
   CUDA_TRY(ctx, cudaMemcpyAsync(out_partial_dev, ctx->ppts.p, ZKB_PROVE_PARTIAL_BYTES, cudaMemcpyDeviceToDevice, ctx->stream));
   return check_flag(ctx, "witness assignment");
