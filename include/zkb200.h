@@ -384,6 +384,7 @@ int zkb_l2_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_r1cs* m, const zkb_l2
  * A zkb_l2_batch owns a pool of `lanes` host threads and a few device contexts (env ZKB_L2_SLOTS, default 4).  A batch is cut into sub-batches (<= 256 proofs,
  * env ZKB_L2_SUBBATCH): the pool assigns a sub-batch's witnesses into pinned memory, zkb_prove_batch_begin proves it with one
  * set of batched kernels, and the next sub-batch is assigned meanwhile.  pk, m and c are shared, read-only.
+ * A call of at most 8 proofs runs zkb_prove per proof instead, one context each (lower latency when there is nothing to batch).
  * proofs_out: n x 256 B.  status_out (may be NULL): per-proof zkb_status.  Returns the first error, ZKB_OK if all succeeded;
  * a failed proof does not invalidate the others. */
 typedef struct zkb_l2_batch zkb_l2_batch;
